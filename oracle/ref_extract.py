@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE - run the reference's OWN hot-path functions on a synthetic case.
+
+Only usable where /root/reference is mounted (the build container).  Nothing
+from the reference is copied into this repository: the wanted top-level
+``def``/``class`` nodes are parsed out of the reference files with ``ast`` at
+run time and executed in a scratch namespace that is pre-seeded with synthetic
+globals.  Used by oracle/make_golden.py to produce the
+fixtures under tests/golden/ and by tests/test_oracle_vs_reference.py (skipped
+when the reference is absent) to pin oracle/vmat_oracle.py.
+
+Product code must never import this module.
+"""
+from __future__ import annotations
+
+import ast
+import contextlib
+import io
+import math
+import os
+import random
+import sys
+import time
+
+import numpy as np
+from scipy import sparse
+from scipy.optimize import minimize
+
+REFERENCE_ROOT = os.environ.get("VMAT_REFERENCE_ROOT", "/root/reference")
+
+WANTED = {
+    "greedyVMATsampling": ["region", "apertureList", "vmat_class", "calcObjGrad", "fvalidbeamlets",
+                           "PPsubroutine", "parallelizationPricingProblem", "solveRMC",
+                           "updateOpenAperture"],
+    "kmedoids": ["distancemin", "listdiff", "insertnewelement", "givemewholelist"],
+}
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "greedyVMATsampling.py"))
+
+
+def _numpy_shim():
+    """numpy with the three aliases the reference still uses (np.int, np.float, np.NAN)."""
+    import types
+    shim = types.ModuleType("numpy_shim")
+    shim.__dict__.update(np.__dict__)
+    shim.int = int
+    shim.float = float
+    shim.NAN = np.nan
+    return shim
+
+
+def extract(module: str, names=None) -> dict:
+    """exec the wanted top-level definitions of /root/reference/<module>.py; return the namespace."""
+    path = os.path.join(REFERENCE_ROOT, module + ".py")
+    tree = ast.parse(open(path).read())
+    names = set(names or WANTED[module])
+    keep = [n for n in tree.body
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    if module == "kmedoids":
+        keep = [n for n in tree.body if isinstance(n, ast.ImportFrom) and n.module == "scipy.spatial"] + keep
+    ns = {"np": _numpy_shim(), "sparse": sparse, "math": math, "time": time, "random": random,
+          "sys": sys, "minimize": minimize, "__name__": "reference_extract"}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+@contextlib.contextmanager
+def quiet():
+    """The reference prints a lot; swallow it."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def reference_namespace(case, module: str = "greedyVMATsampling") -> dict:
+    """Namespace with the reference's functions bound to `case` through the globals
+    they read: ``data``, ``DlistT``, ``quadHelperThresh/Over/Under`` (Appendix A step 3)."""
+    ns = extract(module)
+    data = ns["vmat_class"]()
+    data.numvoxels = case.V
+    data.numbeams = case.nb
+    data.xinter = np.array(case.xinter)
+    data.yinter = np.array(case.yinter)
+    data.xdirection = [np.array(a) for a in case.xdirection]
+    data.ydirection = [np.array(a) for a in case.ydirection]
+    data.Dlist = case.Dlist()
+    data.llist = [[-1] * case.M for _ in range(case.nb)]
+    data.rlist = [[case.N + 1] * case.M for _ in range(case.nb)]
+    data.openApertureMaps = [[] for _ in range(case.nb)]
+    data.diagmakers = [[] for _ in range(case.nb)]
+    data.strengths = [[] for _ in range(case.nb)]
+    data.currentIntensities = np.zeros(case.nb)
+    data.pointtoAngle = list(case.angles)
+    data.notinC = ns["apertureList"]()
+    data.caligraphicC = ns["apertureList"]()
+    data.listIndexofAperturesRemovedEachStep = []
+    ns["data"] = data
+    ns["DlistT"] = [d.transpose() for d in data.Dlist]
+    ns["quadHelperThresh"] = np.array(case.thr)
+    ns["quadHelperOver"] = np.array(case.over)
+    ns["quadHelperUnder"] = np.array(case.under)
+    ns["N"] = case.N
+    ns["M"] = case.M
+    return ns
+
+
+def ref_pricing_problem(ns, C, C2, C3, b, vmax, speedlim, N, M, bw):
+    """Serial stand-in for the reference's PricingProblem (greedyVMATsampling.py:824-856),
+    which cannot be extracted because its Pool lives under ``if __name__ == '__main__'``:
+    map the reference's own per-candidate function over notinC.loc, np.argmin of p."""
+    data = ns["data"]
+    with quiet():
+        res = [ns["parallelizationPricingProblem"](i, C, C2, C3, b, vmax, speedlim, N, M, bw)
+               for i in data.notinC.loc]
+    pvalues = np.array([r[0] for r in res])
+    k = int(np.argmin(pvalues))
+    return res[k][0], res[k][1], res[k][2], res[k][3], res
+
+
+def ref_colgen(ns, case, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vmax=2.25,
+               speedlim=0.83, bw=0.5, RU=10.0):
+    """The reference's colGen loop (greedyVMATsampling.py:937-1046) driven over the
+    reference's own functions, without its plotting / pickle side effects.
+    Returns the list of (bestApertureIndex, l, r, pstar, rmp.x copy, rmp.fun)."""
+    data = ns["data"]
+    YU = RU / speedlim
+    kappa = list(range(case.nb))
+    random.seed(13)
+    kappa = random.sample(kappa, len(kappa))
+    for _ in range(min(kappasize, len(kappa))):
+        i = kappa.pop(0)
+        data.notinC.insertAngle(i, data.pointtoAngle[i])
+    data.caligraphicC = ns["apertureList"]()
+    pstar = -np.inf
+    history = []
+    while (pstar < 0) and (data.notinC.len() > 0):
+        data.calcDose()
+        data.calcGradientandObjValue()
+        pstar, lm, rm, best, _ = ref_pricing_problem(ns, C, C2, C3, b, vmax, speedlim, case.N, case.M, bw)
+        if pstar >= 0:
+            break
+        data.caligraphicC.insertAngle(best, data.notinC(best))
+        data.notinC.removeIndex(best)
+        data.llist[best] = lm
+        data.rlist[best] = rm
+        with quiet():
+            oam, dm, st = ns["updateOpenAperture"](best)
+        data.openApertureMaps[best], data.diagmakers[best], data.strengths[best] = oam, dm, st
+        with quiet():
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = ns["solveRMC"](YU)
+        data.rmpres = res
+        history.append(dict(idx=int(best), l=[int(v) for v in lm], r=[int(v) for v in rm],
+                            pstar=float(pstar), x=np.array(res.x, dtype=float), fun=float(res.fun),
+                            nit=int(res.nit), nfev=int(res.nfev)))
+        while not data.notinC.isEmpty():
+            kappa.append(data.notinC.loc[0])
+            data.notinC.removeIndex(data.notinC.loc[0])
+        random.seed(13)
+        for i in random.sample(kappa, min(kappasize, len(kappa))):
+            data.notinC.insertAngle(i, data.pointtoAngle[i])
+            kappa.remove(i)
+        if max_iter is not None and len(history) >= max_iter:
+            break
+    return history
