@@ -1,0 +1,159 @@
+/*
+ * vmat_b200.h - C ABI of libvmat_b200.so, the B200 (sm_100a) implementation of the
+ * dose / objective / gradient evaluation and aperture pricing of VMATwPenCode.
+ *
+ * The reference is pure Python and has no FFI; this is the boundary its scripts
+ * would bind with ctypes.  Each entry point names the
+ * reference code it replaces (paths under the reference root).
+ *
+ * Conventions: every function returns 0 on success or a negative VMAT_E_* code and
+ * never throws; the plan handle is opaque; one host thread per plan; one plan per
+ * GPU (rank).  Host arrays are caller-owned; the library keeps its own device
+ * copies.  Index arrays are int32 except row pointers (int64).  "f64" host
+ * vectors are what the reference's numpy code holds.
+ */
+#ifndef VMAT_B200_H
+#define VMAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vmat_plan vmat_plan_t;
+
+enum { VMAT_F32 = 0, VMAT_BF16 = 1, VMAT_F64 = 2 };          /* value / accumulate dtypes */
+enum { VMAT_HOST = 0, VMAT_DEVICE = 1 };                     /* where the CSR arrays live */
+
+enum {
+    VMAT_OK = 0,
+    VMAT_E_ARG = -1,        /* bad argument */
+    VMAT_E_CUDA = -2,       /* CUDA runtime error (vmat_last_error has the text) */
+    VMAT_E_NOMEM = -3,
+    VMAT_E_UNSUPPORTED = -4,
+    VMAT_E_STATE = -5       /* call order (e.g. pricing before any evaluation) */
+};
+
+typedef struct vmat_options {
+    int32_t store_dtype;    /* VMAT_F32 | VMAT_BF16 | VMAT_F64: how D is kept in HBM          */
+    int32_t acc_dtype;      /* VMAT_F32 | VMAT_F64: accumulation, and dtype of x, dose, vg     */
+    int32_t tile_voxels;    /* voxels per column tile of the transposed layout (0 = default)   */
+    int32_t k1_threads;     /* threads per CTA of the dose kernel (0 = default)                */
+    int32_t k2_threads;     /* threads per CTA of the transposed kernel (0 = default)          */
+    int32_t k2_tasks;       /* CTAs of the transposed kernel (0 = default)                     */
+    int32_t use_graph;      /* 1: replay the three-kernel evaluation as one CUDA graph         */
+    int32_t reserved[9];
+} vmat_options_t;
+
+/* Library / build identification. */
+int         vmat_version(void);
+const char* vmat_last_error(void);
+void        vmat_default_options(vmat_options_t* opt);
+
+/*
+ * Build a plan from the dose-deposition matrix D (V voxels x B beamlets) given twice:
+ * voxel-major CSR (rows = voxels, cols = global beamlet ids) and beamlet-major CSR
+ * (rows = beamlets, cols = voxel ids ascending).  B = beam_ptr[nb]; control point i owns
+ * beamlets [beam_ptr[i], beam_ptr[i+1]).  Replaces the per-control-point lists
+ * data.Dlist[i] / DlistT[i] (greedyVMATsampling.py:482-483,524-525) and the per-voxel
+ * penalty tables quadHelperThresh/Over/Under (greedyVMATsampling.py:564-576).
+ * `src_dtype` is the dtype of vval/bval (VMAT_F32 or VMAT_F64); `location` says whether
+ * the six CSR arrays are host or device pointers.  thr/over/under are host f64[V].
+ * In a multi-GPU run each rank passes its own voxel slab (V = slab size).
+ */
+int vmat_plan_create(vmat_plan_t** plan, int device, int64_t V, int64_t B, int32_t nb,
+                     const int32_t* beam_ptr,
+                     const int64_t* vrowptr, const int32_t* vcol, const void* vval,
+                     const int64_t* browptr, const int32_t* bcol, const void* bval,
+                     int src_dtype, int location,
+                     const double* thr, const double* over, const double* under,
+                     const vmat_options_t* opt);
+int vmat_plan_destroy(vmat_plan_t* plan);
+
+/* Bytes of HBM one evaluation must move for this plan's layouts, and the SURVEY 8(d)
+ * algorithmic figure 2*nnz*(s_v+4) + 28V + 12B for the same matrix. */
+int vmat_plan_info(const vmat_plan_t* plan, int64_t* nnz, int64_t* layout_bytes_per_eval,
+                   int64_t* algorithmic_bytes_per_eval, int32_t* launches_per_eval);
+
+/*
+ * Set the two beamlet weight vectors of control point `beam` (length beam_ptr[beam+1]-
+ * beam_ptr[beam]): w_dose = openApertureStrength scattered over openApertureMaps, w_grad =
+ * diagmaker - the outputs of updateOpenAperture (greedyVMATsampling.py:1070-1130) as used by
+ * calcDose (:250-251).  NULL pointers close the control point (weights 0).
+ */
+int vmat_set_aperture(vmat_plan_t* plan, int32_t beam, const double* w_dose, const double* w_grad);
+
+/*
+ * One evaluation = calcObjGrad(x) (greedyVMATsampling.py:578-582): dose d = D x with
+ * x_j = y[beam(j)] w_dose[j] (calcDose :243-251), objective f and voxel gradient
+ * (calcGradientandObjValue :254-271), beamlet gradient gb = D^T vg (PPsubroutine :646) and
+ * aperture gradient g_i = sum_j w_grad[j] gb[j] (:272).  y, g are host f64[nb].
+ * Copies y in, runs the kernels, copies f and g out, synchronises.
+ */
+int vmat_eval(vmat_plan_t* plan, const double* y, double* f, double* g);
+
+/* Resident variants: y already on the device (vmat_set_intensities), results stay on the
+ * device until fetched.  `stream` is a cudaStream_t (NULL = the plan's own stream).
+ * vmat_eval_async enqueues the evaluation and returns without synchronising.  In a
+ * multi-GPU run phase 0 = everything (single GPU), 1 = up to the local [gb | f] partial
+ * (to be all-reduced by the caller: vmat_reduce_buffer), 2 = after the all-reduce. */
+int vmat_set_intensities(vmat_plan_t* plan, const double* y);
+int vmat_eval_async(vmat_plan_t* plan, void* stream, int phase);
+int vmat_fetch_result(vmat_plan_t* plan, double* f, double* g);
+int vmat_sync(vmat_plan_t* plan);
+
+/* Per-kernel device timing: while enabled, every vmat_eval_async records CUDA events around
+ * its kernels on the launch stream; vmat_get_timing synchronises and returns the mean
+ * milliseconds of [dose kernel (K1, with the x expansion), transposed kernel (K2),
+ * reductions (K3), whole evaluation] over the last n (<= 1024) evaluations. */
+int vmat_set_timing(vmat_plan_t* plan, int enable);
+int vmat_get_timing(vmat_plan_t* plan, double* ms /* 4 */, int32_t* n);
+
+/* Device pointer and element count (B+1 doubles: gb then f) of the buffer a multi-GPU
+ * caller must sum across ranks between phase 1 and phase 2. */
+int vmat_reduce_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);
+
+/* Read back state of the last evaluation as f64: data.currentDose (:244-250),
+ * data.voxelgradient (:271), and beamGrad of every control point (:646) concatenated. */
+int vmat_get_dose(vmat_plan_t* plan, double* d_out /* V */);
+int vmat_get_voxelgrad(vmat_plan_t* plan, double* vg_out /* V */);
+int vmat_get_beamlet_grad(vmat_plan_t* plan, double* gb_out /* B */);
+
+/*
+ * Pricing: PPsubroutine (greedyVMATsampling.py:618-789) for `ncand` candidate control
+ * points in one launch, on the beamlet gradient of the last evaluation.
+ */
+typedef struct vmat_price_row {     /* one leaf row of one candidate (host-built, :664-680,713-724) */
+    double l_first;                 /* first left-leaf position (integer valued, or the fractional midpoint) */
+    int32_t n_l;                    /* number of consecutive l values (step 1)                */
+    int32_t vb_min;                 /* min(validbeamlets) of this row (fvalidbeamlets :589-602) */
+    double r_lo;                    /* max(rcm - travel-, rcp - travel+)  (before max with l+1) */
+    double r_hi;                    /* min(N, rcm + travel-, rcp + travel+)                    */
+    double r_mid;                   /* first r of the midpoint fallback used when the r range is empty */
+    uint64_t vb_mask;               /* bit n set: beamlet n exists in this row                 */
+    int32_t grad_offset;            /* beamGrad index of y index vb_min in this row, quirk Q1 applied */
+    int32_t n_r_mid;                /* how many r values the midpoint fallback yields: len(np.arange(mid, mid+1)), 1 or 2 */
+} vmat_price_row_t;
+
+typedef struct vmat_price_params {
+    double C, C2, C3, b;
+    int32_t M, N;
+} vmat_price_params_t;
+
+int vmat_price(vmat_plan_t* plan, int32_t ncand, const int32_t* cand_beam,
+               const vmat_price_params_t* params, const vmat_price_row_t* rows /* ncand*M */,
+               double* p /* ncand */, int32_t* l /* ncand*M */, int32_t* r /* ncand*M */);
+
+/*
+ * k-medoid insertion costs (kmedoids.py:32-60): for every candidate point c, the sum over
+ * all n points j of min(curmin[j], dist(c, j)); points are n x dim f64 (host).  The caller
+ * keeps curmin (distance to the nearest already-chosen medoid) and picks the first minimum.
+ */
+int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
+                       const double* curmin, double* cost /* n */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMAT_B200_H */

@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE - freeze outputs of the reference's own functions into tests/golden/.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+Each fixture stores the synthetic inputs together with what the reference's AST-extracted
+functions (oracle/ref_extract.py) returned for them, so the pin travels to machines without
+the reference.  Nothing here copies reference code; only its outputs are recorded.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_extract as R                                   # noqa: E402
+from vmatwpencode_b200.synth import make_case, case_to_arrays          # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def select(ns, case, beam, l, r):
+    """Select control point `beam` with leaf vectors l, r through the reference's own
+    updateOpenAperture."""
+    data = ns["data"]
+    if beam in data.notinC.loc:
+        data.notinC.removeIndex(beam)
+    data.caligraphicC.insertAngle(beam, case.angles[beam])
+    data.llist[beam] = list(l)
+    data.rlist[beam] = list(r)
+    with R.quiet():
+        out = ns["updateOpenAperture"](beam)
+    data.openApertureMaps[beam], data.diagmakers[beam], data.strengths[beam] = out
+    return out
+
+
+def eval_and_price_fixture(name, case, selected, y, price_settings):
+    ns = R.reference_namespace(case)
+    data = ns["data"]
+    for i in range(case.nb):
+        data.notinC.insertAngle(i, case.angles[i])
+    out = case_to_arrays(case)
+    sel_beams = []
+    for beam, (l, r) in selected.items():
+        oam, dm, stg = select(ns, case, beam, l, r)
+        sel_beams.append(beam)
+        out[f"sel{beam}_l"] = np.asarray(l, dtype=float)
+        out[f"sel{beam}_r"] = np.asarray(r, dtype=float)
+        out[f"sel{beam}_oam"] = np.asarray(oam, dtype=np.int64)
+        out[f"sel{beam}_diag"] = np.asarray(dm, dtype=float)
+        out[f"sel{beam}_strength"] = np.asarray(stg, dtype=float)
+    out["selected"] = np.asarray(sel_beams, dtype=np.int64)
+    out["y"] = np.asarray(y, dtype=float)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f, g = ns["calcObjGrad"](np.array(y, dtype=float))
+    out["f"] = np.float64(f)
+    out["g"] = np.asarray(g, dtype=float).ravel()
+    out["dose"] = np.asarray(data.currentDose, dtype=float)
+    out["vg"] = np.asarray(data.voxelgradient, dtype=float)
+    settings = []
+    for k, (C, vmax, speedlim, bw) in enumerate(price_settings):
+        ps, ls, rs, idxs = [], [], [], []
+        for i in list(data.notinC.loc):
+            with R.quiet():
+                p, l, r, idx = ns["parallelizationPricingProblem"](i, C, 1.0, 1.0, 0.5, vmax, speedlim, case.N, case.M, bw)
+            ps.append(float(p)); ls.append([int(v) for v in l]); rs.append([int(v) for v in r]); idxs.append(idx)
+        out[f"price{k}_params"] = np.array([C, 1.0, 1.0, 0.5, vmax, speedlim, bw])
+        out[f"price{k}_idx"] = np.asarray(idxs, dtype=np.int64)
+        out[f"price{k}_p"] = np.asarray(ps)
+        out[f"price{k}_l"] = np.asarray(ls, dtype=np.int64)
+        out[f"price{k}_r"] = np.asarray(rs, dtype=np.int64)
+        settings.append(k)
+    out["n_price"] = np.int64(len(settings))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "f =", float(f), "candidates", len(data.notinC.loc))
+
+
+def colgen_fixture(name, case, C, kappasize, max_iter):
+    ns = R.reference_namespace(case)
+    hist = R.ref_colgen(ns, case, C=C, kappasize=kappasize, max_iter=max_iter)
+    out = case_to_arrays(case)
+    out["C"] = np.float64(C)
+    out["kappasize"] = np.int64(kappasize)
+    out["max_iter"] = np.int64(max_iter)
+    out["idx"] = np.asarray([h["idx"] for h in hist], dtype=np.int64)
+    out["l"] = np.asarray([h["l"] for h in hist], dtype=np.int64)
+    out["r"] = np.asarray([h["r"] for h in hist], dtype=np.int64)
+    out["pstar"] = np.asarray([h["pstar"] for h in hist])
+    out["x"] = np.asarray([h["x"] for h in hist])
+    out["fun"] = np.asarray([h["fun"] for h in hist])
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "iterations", len(hist), "sequence", [h["idx"] for h in hist])
+
+
+def kmedoids_fixture():
+    """The reference's only embedded known answer: the hard-coded kappa list
+    (greedyVMAT.py:28) equals givemewholelist(range(6,178,11), range(178)); plus small runs
+    of the reference's own functions."""
+    tree = ast.parse(open(os.path.join(R.REFERENCE_ROOT, "greedyVMAT.py")).read())
+    kappa = None
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", None) == "kappa":
+            kappa = ast.literal_eval(node.value)
+            break
+    assert kappa is not None and len(kappa) == 178
+    ns = R.extract("kmedoids")
+    out = {"kappa178": np.asarray(kappa, dtype=np.int64)}
+    for n, start in ((23, [3, 11, 19]), (40, [5, 20, 35]), (31, [0])):
+        with R.quiet():
+            order = ns["givemewholelist"](list(start), range(0, n))
+        out[f"order_n{n}"] = np.asarray(order, dtype=np.int64)
+        out[f"start_n{n}"] = np.asarray(start, dtype=np.int64)
+        with R.quiet():
+            out[f"dmin_n{n}"] = np.float64(ns["distancemin"](list(start), range(0, n)))
+    np.savez_compressed(os.path.join(GOLDEN, "kmedoids.npz"), **out)
+    print("kmedoids fixtures written")
+
+
+def main():
+    if not R.reference_available():
+        raise SystemExit("reference not mounted at " + R.REFERENCE_ROOT)
+    os.makedirs(GOLDEN, exist_ok=True)
+    # A: full rectangle grid, two selected control points, loose and tight leaf speeds.
+    caseA = make_case(V=1500, nb=10, M=4, N=6, density=0.05, seed=21, gastep=10)
+    yA = np.zeros(10); yA[3] = 1.7; yA[6] = 0.9
+    eval_and_price_fixture("evalprice_A", caseA, {3: ([0, 0, 1, 1], [5, 6, 5, 4]), 6: ([1, 0, 0, 2], [4, 5, 6, 6])},
+                           yA, [(0.0, 2.25, 0.83, 0.5), (0.02, 2.25, 0.83, 0.5), (1.0, 2.25, 0.83, 0.5),
+                                (0.02, 0.05, 0.83, 0.5), (0.02, 0.02, 0.83, 0.5)])
+    # B: ragged beamlet rows (min(validbeamlets) > 0 in places), gastep 2, three selected.
+    caseB = make_case(V=1800, nb=12, M=5, N=7, density=0.05, seed=22, gastep=2, ragged=True)
+    yB = np.zeros(12); yB[2] = 2.0; yB[5] = 0.4; yB[9] = 1.1
+    eval_and_price_fixture("evalprice_B", caseB,
+                           {2: ([0, 1, 1, 0, 2], [6, 5, 7, 4, 5]), 5: ([1, 1, 1, 1, 1], [5, 5, 5, 5, 5]),
+                            9: ([-1, 0, 2, 1, 0], [7, 3, 6, 7, 2])},
+                           yB, [(0.0, 2.25, 0.83, 0.5), (0.05, 2.25, 0.83, 0.5), (0.05, 0.3, 0.83, 0.5),
+                                (0.5, 0.1, 0.83, 0.5)])
+    # C: fractional leaves through updateOpenAperture (strength edge cases Q2/Q3).
+    caseC = make_case(V=1200, nb=6, M=3, N=8, density=0.06, seed=23, gastep=10)
+    yC = np.zeros(6); yC[1] = 1.0; yC[4] = 2.5
+    eval_and_price_fixture("evalprice_C", caseC, {1: ([0.5, 2, 2], [5.25, 5, 4]), 4: ([1, -1, 3.75], [6, 8, 5.5])},
+                           yC, [(0.01, 2.25, 0.83, 0.5)])
+    colgen_fixture("colgen_A", make_case(V=2500, nb=12, M=5, N=6, density=0.04, seed=31, gastep=10), 0.02, 5, 10)
+    colgen_fixture("colgen_B", make_case(V=2000, nb=18, M=4, N=7, density=0.04, seed=32, gastep=2, ragged=True), 0.0, 6, 12)
+    colgen_fixture("colgen_C", make_case(V=2000, nb=36, M=3, N=5, density=0.05, seed=33, gastep=1), 0.5, 8, 14)
+    kmedoids_fixture()
+
+
+if __name__ == "__main__":
+    main()

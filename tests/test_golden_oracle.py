@@ -1,0 +1,103 @@
+"""The oracle (oracle/vmat_oracle.py) against the fixtures frozen from the reference's own
+functions (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import vmat_oracle as O
+from helpers import load_golden, oracle_state_from_golden, relerr
+
+
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+def test_eval_matches_reference_bitwise(name):
+    z, case = load_golden(name)
+    st = oracle_state_from_golden(z, case)
+    for beam in z["selected"]:
+        beam = int(beam)
+        assert np.array_equal(st.openApertureMaps[beam], z[f"sel{beam}_oam"])
+        assert np.array_equal(st.diagmakers[beam], z[f"sel{beam}_diag"])
+        assert np.array_equal(np.asarray(st.strengths[beam], dtype=float), z[f"sel{beam}_strength"])
+    f, g = O.calc_obj_grad_literal(st, np.array(z["y"]))
+    assert f == float(z["f"])
+    assert np.array_equal(np.asarray(g).ravel(), z["g"])
+    assert np.array_equal(st.currentDose, z["dose"])
+    assert np.array_equal(st.voxelgradient, z["vg"])
+    # the global ("clean") form the kernels implement agrees to rounding
+    f2, g2, d2, vg2, gb2 = O.calc_obj_grad_clean(st, np.array(z["y"]))
+    assert abs(f2 - float(z["f"])) <= 1e-13 * abs(float(z["f"]))
+    assert relerr(g2, z["g"]) <= 1e-13
+    assert relerr(d2, z["dose"]) <= 1e-13
+
+
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+def test_pricing_matches_reference_bitwise(name):
+    z, case = load_golden(name)
+    st = oracle_state_from_golden(z, case)
+    O.calc_obj_grad_literal(st, np.array(z["y"]))
+    for k in range(int(z["n_price"])):
+        C, C2, C3, b, vmax, speedlim, bw = [float(v) for v in z[f"price{k}_params"]]
+        for n, idx in enumerate(z[f"price{k}_idx"]):
+            p, l, r, i = O.price_candidate(st, int(idx), C, C2, C3, b, vmax, speedlim, case.N, case.M, bw)
+            assert p == z[f"price{k}_p"][n], (name, k, idx)
+            assert l == list(z[f"price{k}_l"][n]) and r == list(z[f"price{k}_r"][n]), (name, k, idx)
+
+
+def test_fallback_midpoints_are_exercised():
+    """The tight leaf-speed settings of the fixtures must reach the fractional-midpoint
+    branch (quirk Q7), otherwise that code is unpinned."""
+    z, case = load_golden("evalprice_B")
+    st = oracle_state_from_golden(z, case)
+    hit = 0
+    for k in range(int(z["n_price"])):
+        C, C2, C3, b, vmax, speedlim, bw = [float(v) for v in z[f"price{k}_params"]]
+        for idx in z[f"price{k}_idx"]:
+            predec, succ, am, ap = O.neighbours(st, int(idx))
+            if isinstance(predec, list) or isinstance(succ, list):
+                continue
+            tm, tp = vmax * (am / speedlim) / bw, vmax * (ap / speedlim) / bw
+            win = O.leaf_window(case.N, case.M, st.llist[predec], st.llist[succ], st.rlist[predec],
+                                st.rlist[succ], tm, tp, am, ap)
+            for row in win:
+                for l, rs in row:
+                    if not float(l).is_integer() or any(not float(r).is_integer() for r in rs):
+                        hit += 1
+    assert hit > 0
+
+
+@pytest.mark.parametrize("name", ["colgen_A", "colgen_B", "colgen_C"])
+def test_colgen_sequence_matches_reference(name):
+    z, case = load_golden(name)
+    st = O.OracleState(case)
+    hist = O.col_gen(st, C=float(z["C"]), kappasize=int(z["kappasize"]), max_iter=int(z["max_iter"]))
+    assert [h["idx"] for h in hist] == list(z["idx"])
+    for h, l, r, p, x, fun in zip(hist, z["l"], z["r"], z["pstar"], z["x"], z["fun"]):
+        assert h["l"] == list(l) and h["r"] == list(r)
+        assert h["pstar"] == p and h["fun"] == fun
+        assert np.array_equal(h["x"], x)
+    # the global-form evaluation drives the same greedy sequence
+    st2 = O.OracleState(case)
+    hist2 = O.col_gen(st2, C=float(z["C"]), kappasize=int(z["kappasize"]), max_iter=int(z["max_iter"]), clean=True)
+    assert [h["idx"] for h in hist2] == list(z["idx"])
+    for h, l, r in zip(hist2, z["l"], z["r"]):
+        assert h["l"] == list(l) and h["r"] == list(r)
+
+
+def test_kmedoids_known_answer_and_reference_runs():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "kmedoids.npz"))
+    for n in (23, 40, 31):
+        start = [int(v) for v in z[f"start_n{n}"]]
+        assert O.km_givemewholelist(start, list(range(n))) == list(z[f"order_n{n}"])
+        assert O.km_distancemin(start, list(range(n))) == float(z[f"dmin_n{n}"])
+    # first steps of the 178-angle ordering embedded in the reference (greedyVMAT.py:28)
+    kappa = list(range(6, 178, 11))
+    for _ in range(4):
+        kappa = O.km_insertnewelement(kappa, list(range(178)))
+    assert kappa == list(z["kappa178"][:len(kappa)])
+
+
+def test_numpy_sum_order_restatement():
+    rng = np.random.default_rng(5)
+    for n in range(0, 65):
+        for _ in range(20):
+            a = rng.standard_normal(n) * 10.0 ** rng.integers(-4, 4, size=n)
+            if n:
+                assert O.numpy_pairwise_sum(a) == a[np.arange(n)].sum()

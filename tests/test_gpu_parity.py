@@ -1,0 +1,278 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the
+C ABI (ctypes), against the oracle and against the fixtures frozen from the reference.
+
+Tolerances: leaf positions and candidate choice bit-exact; dose / objective / gradients
+within 1e-5 relative (max-norm) for fp32 accumulation (BASELINE.json north_star), 1e-11 for
+fp64 accumulation."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import vmat_oracle as O
+from vmatwpencode_b200 import VMATlibrary as vl
+from vmatwpencode_b200 import _lib
+from vmatwpencode_b200.plan import DosePlan
+from vmatwpencode_b200.synth import make_case, make_config
+from helpers import load_golden, all_candidates, select, oracle_state_from_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 1e-5, "f64": 1e-11}
+
+
+def product_state_from_golden(z, case, **kw):
+    data = vl.bind(case, **kw)
+    all_candidates(data, case)
+    for beam in z["selected"]:
+        beam = int(beam)
+        select(data, case, beam, z[f"sel{beam}_l"], z[f"sel{beam}_r"], vl.updateOpenAperture)
+    return data
+
+
+def test_native_library_is_the_in_tree_build():
+    lib = _lib.load()
+    assert os.path.dirname(_lib.LIB_PATH).endswith("vmatwpencode_b200")
+    assert lib.vmat_version() >= 100
+
+
+@pytest.mark.parametrize("acc", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+def test_eval_against_reference_fixture(name, acc):
+    z, case = load_golden(name)
+    data = product_state_from_golden(z, case, store="f32", acc=acc)
+    f, g = vl.calcObjGrad(np.array(z["y"]))
+    tol = TOL[acc]
+    assert abs(f - float(z["f"])) <= tol * abs(float(z["f"]))
+    assert g.shape == (case.nb, 1)
+    assert relerr(g, z["g"]) <= tol
+    assert relerr(data.currentDose, z["dose"]) <= tol
+    assert relerr(data.voxelgradient, z["vg"]) <= tol
+    data.plan.close()
+
+
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+def test_pricing_against_reference_fixture(name):
+    z, case = load_golden(name)
+    data = product_state_from_golden(z, case, store="f32", acc="f64")
+    vl.calcObjGrad(np.array(z["y"]))
+    for k in range(int(z["n_price"])):
+        C, C2, C3, b, vmax, speedlim, bw = [float(v) for v in z[f"price{k}_params"]]
+        # one candidate at a time through the reference's per-candidate entry point ...
+        for n, idx in enumerate(z[f"price{k}_idx"]):
+            p, l, r, i = vl.parallelizationPricingProblem(int(idx), C, C2, C3, b, vmax, speedlim, case.N, case.M, bw)
+            assert [int(v) for v in l] == list(z[f"price{k}_l"][n]), (name, k, idx)
+            assert [int(v) for v in r] == list(z[f"price{k}_r"][n]), (name, k, idx)
+            assert abs(p - z[f"price{k}_p"][n]) <= 1e-11 * max(1.0, abs(z[f"price{k}_p"][n]))
+        # ... and all candidates in one launch
+        pstar, l, r, best = vl.PricingProblem(C, C2, C3, b, vmax, speedlim, case.N, case.M, bw)
+        want = int(np.argmin(z[f"price{k}_p"]))
+        assert best == int(z[f"price{k}_idx"][want])
+        assert [int(v) for v in l] == list(z[f"price{k}_l"][want])
+        assert [int(v) for v in r] == list(z[f"price{k}_r"][want])
+    data.plan.close()
+
+
+@pytest.mark.parametrize("name", ["colgen_A", "colgen_B", "colgen_C"])
+def test_greedy_sequence_against_reference_fixture(name):
+    z, case = load_golden(name)
+    data = vl.bind(case, store="f32", acc="f64")
+    vl.colGen(float(z["C"]), False, int(z["kappasize"]), max_iter=int(z["max_iter"]))
+    hist = data.history
+    assert [h["idx"] for h in hist] == list(z["idx"])
+    for h, l, r, p, x, fun in zip(hist, z["l"], z["r"], z["pstar"], z["x"], z["fun"]):
+        assert h["l"] == list(l) and h["r"] == list(r)          # bit-exact leaf positions
+        assert abs(h["pstar"] - p) <= 1e-9 * abs(p)
+        assert abs(h["fun"] - fun) <= 1e-9 * abs(fun)
+        assert np.abs(h["x"] - x).max() <= 1e-7 * max(1.0, np.abs(x).max())
+    data.plan.close()
+
+
+def random_weights(case, rng, frac_selected=0.5):
+    w_dose = np.zeros(case.B)
+    w_grad = np.zeros(case.B)
+    y = np.zeros(case.nb)
+    for i in range(case.nb):
+        if rng.random() < frac_selected:
+            lo, hi = int(case.beam_ptr[i]), int(case.beam_ptr[i + 1])
+            w_dose[lo:hi] = (rng.random(hi - lo) > 0.4) * np.round(rng.random(hi - lo) * 4) / 4
+            w_grad[lo:hi] = (rng.random(hi - lo) > 0.4) * 1.0
+            y[i] = rng.random() * 3
+    return y, w_dose, w_grad
+
+
+@pytest.mark.parametrize("store,acc,val_dtype,tol", [
+    ("f32", "f32", "f32", 1e-5), ("f32", "f64", "f32", 1e-11), ("f64", "f64", "f64", 1e-11),
+    ("bf16", "f32", "bf16", 1e-5), ("bf16", "f64", "bf16", 1e-11), ("f64", "f32", "f32", 1e-5)])
+@pytest.mark.parametrize("shape", [
+    dict(V=50_000, nb=24, M=6, N=8, density=0.01, seed=61),
+    dict(V=4099, nb=7, M=3, N=5, density=0.05, seed=62, ragged=True),       # V % 32 != 0, ragged rows
+    dict(V=33, nb=2, M=1, N=3, density=0.3, seed=63),                       # tiny
+    dict(V=20_000, nb=10, M=4, N=6, density=0.002, seed=64, model="uniform"),   # many empty voxel rows
+])
+def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol):
+    case = make_case(val_dtype=val_dtype, **shape)
+    st = O.OracleState(case)
+    rng = np.random.default_rng(shape["seed"])
+    plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store=store, acc=acc,
+                    tile_voxels=4096 if shape["V"] > 10_000 else 64)
+    for trial in range(3):
+        y, w_dose, w_grad = random_weights(case, rng, frac_selected=[0.5, 1.0, 0.0][trial])
+        plan.set_weights(w_dose, w_grad)
+        f, g = plan.eval(y)
+        f0, g0, d0, vg0, gb0 = O.calc_obj_grad_clean(st, y, w_dose, w_grad)
+        assert abs(f - f0) <= tol * abs(f0)
+        assert relerr(g, g0) <= tol
+        assert relerr(plan.dose(), d0) <= tol
+        assert relerr(plan.voxelgrad(), vg0) <= tol
+        assert relerr(plan.beamlet_grad(), gb0) <= tol
+    plan.close()
+
+
+@pytest.mark.parametrize("opts", [dict(use_graph=False), dict(tile_voxels=128), dict(tile_voxels=64, k2_tasks=7),
+                                  dict(k1_threads=256), dict(k2_threads=128, k2_tasks=1000)])
+def test_plan_options_do_not_change_results(opts):
+    case = make_case(V=9000, nb=8, M=4, N=6, density=0.02, seed=71)
+    st = O.OracleState(case)
+    y, w_dose, w_grad = random_weights(case, np.random.default_rng(2), 0.7)
+    f0, g0, d0, vg0, gb0 = O.calc_obj_grad_clean(st, y, w_dose, w_grad)
+    plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc="f64", **opts)
+    plan.set_weights(w_dose, w_grad)
+    f, g = plan.eval(y)
+    assert abs(f - f0) <= 1e-11 * abs(f0) and relerr(g, g0) <= 1e-11 and relerr(plan.beamlet_grad(), gb0) <= 1e-11
+    # resident path: same numbers without host round trips
+    plan.set_intensities(y)
+    plan.eval_async()
+    f2, g2 = plan.fetch_result()
+    assert f2 == f and np.array_equal(g2, g)
+    plan.close()
+
+
+def test_evaluation_is_bitwise_reproducible_and_apertures_update():
+    case = make_case(V=30_000, nb=12, M=5, N=8, density=0.01, seed=72)
+    rng = np.random.default_rng(3)
+    y, w_dose, w_grad = random_weights(case, rng, 0.6)
+    plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc="f32")
+    plan.set_weights(w_dose, w_grad)
+    f1, g1 = plan.eval(y)
+    gb1 = plan.beamlet_grad()
+    for _ in range(3):
+        f2, g2 = plan.eval(y)
+        assert f2 == f1 and np.array_equal(g1, g2) and np.array_equal(gb1, plan.beamlet_grad())
+    # closing every control point gives the zero-dose objective sum(under * thr^2)
+    for i in range(case.nb):
+        plan.set_aperture(i, None, None)
+    f0, g0 = plan.eval(y)
+    want = float(np.sum(case.under * case.thr * case.thr))
+    assert abs(f0 - want) <= 1e-5 * want and np.all(g0 == 0)
+    assert np.all(plan.dose() == 0)
+    plan.close()
+
+
+def test_argument_errors_are_reported_not_ignored():
+    case = make_case(V=500, nb=3, M=2, N=4, density=0.1, seed=73)
+    plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under)
+    with pytest.raises(_lib.VmatError):
+        plan.set_aperture(99, None, None)
+    with pytest.raises(_lib.VmatError):
+        plan.set_aperture(0, np.zeros(3), np.zeros(3))
+    with pytest.raises(_lib.VmatError):
+        DosePlan(case.D, case.beam_ptr[:-1], case.thr, case.over, case.under)
+    plan.close()
+
+
+def test_pricing_random_states_vs_oracle():
+    """Bigger leaf grids, ragged rows, tight leaf speeds (fractional fallbacks), C in {0, >0}."""
+    for seed, (nb, M, N, ragged, gastep) in enumerate([(10, 6, 12, True, 2), (8, 9, 9, False, 10), (14, 4, 20, True, 1)]):
+        case = make_case(V=6000, nb=nb, M=M, N=N, density=0.03, seed=80 + seed, gastep=gastep, ragged=ragged)
+        st = O.OracleState(case)
+        data = vl.bind(case, store="f32", acc="f64")
+        rng = np.random.default_rng(seed)
+        for state in (st, data):
+            all_candidates(state, case)
+        chosen = sorted(rng.choice(nb, size=3, replace=False).tolist())
+        y = np.zeros(nb)
+        for bm in chosen:
+            l = [int(rng.integers(-1, N - 2)) for _ in range(M)]
+            r = [int(min(N, lv + rng.integers(1, 6))) for lv in l]
+            select(st, case, bm, l, r, lambda k: O.update_open_aperture(st, k))
+            select(data, case, bm, l, r, vl.updateOpenAperture)
+            y[bm] = rng.random() * 2
+        O.calc_obj_grad_literal(st, y.copy())
+        vl.calcObjGrad(y.copy())
+        for C, vmax in [(0.0, 2.25), (0.03, 2.25), (1.0, 2.25), (0.03, 0.2), (0.0, 0.05), (0.2, 0.02)]:
+            ref = [O.price_candidate(st, i, C, 1.0, 1.0, 0.5, vmax, 0.83, N, M, 0.5) for i in st.notinC.loc]
+            for (p0, l0, r0, i0) in ref:
+                p, l, r, i = vl.parallelizationPricingProblem(i0, C, 1.0, 1.0, 0.5, vmax, 0.83, N, M, 0.5)
+                assert [int(v) for v in l] == l0 and [int(v) for v in r] == r0, (seed, C, vmax, i0)
+                assert abs(p - p0) <= 1e-10 * max(1.0, abs(p0))
+            got = vl.PricingProblem(C, 1.0, 1.0, 0.5, vmax, 0.83, N, M, 0.5)
+            want = O.pricing_problem(st, C, 1.0, 1.0, 0.5, vmax, 0.83, N, M, 0.5)
+            assert got[3] == want[3] and [int(v) for v in got[1]] == want[1] and [int(v) for v in got[2]] == want[2]
+        data.plan.close()
+
+
+def test_pricing_before_any_evaluation_is_an_error():
+    case = make_case(V=500, nb=3, M=2, N=4, density=0.1, seed=74)
+    data = vl.bind(case)
+    all_candidates(data, case)
+    with pytest.raises(_lib.VmatError):
+        vl.PricingProblem(0.0, 1.0, 1.0, 0.5, 2.25, 0.83, case.N, case.M, 0.5)
+    data.plan.close()
+
+
+def test_greedy_loop_vs_oracle_medium_case():
+    """A config-1-like case (smaller V) end to end: same aperture sequence as the oracle."""
+    case = make_case(V=8000, nb=36, M=7, N=8, density=0.01, seed=1001, gastep=10)
+    want = O.col_gen(O.OracleState(case), C=0.01, kappasize=16, max_iter=12, clean=True)
+    data = vl.bind(case, store="f32", acc="f64")
+    vl.colGen(0.01, False, 16, max_iter=12)
+    assert [h["idx"] for h in data.history] == [h["idx"] for h in want]
+    for a, b in zip(data.history, want):
+        assert a["l"] == b["l"] and a["r"] == b["r"]
+    data.plan.close()
+
+
+def test_kmedoids_known_answer():
+    from vmatwpencode_b200 import kmedoids as km
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmedoids.npz"))
+    for n in (23, 40, 31):
+        start = [int(v) for v in z[f"start_n{n}"]]
+        assert km.givemewholelist(start, range(0, n)) == list(z[f"order_n{n}"])
+        assert km.distancemin(start, range(0, n)) == float(z[f"dmin_n{n}"])
+    # the one known answer the reference embeds (greedyVMAT.py:28)
+    assert km.givemewholelist(list(range(6, 178, 11)), range(0, 178)) == list(z["kappa178"])
+    # coordinates in 3-D (voxel use): against the oracle
+    rng = np.random.default_rng(4)
+    P = rng.random((300, 3))
+    got = km.insertnewelement([0, 5], P)
+    assert got == O.km_insertnewelement([0, 5], P)
+
+
+@pytest.mark.parametrize("acc", ["f32", "f64"])
+def test_full_size_config2_properties(acc):
+    """BASELINE.json configs[1] at full size (300k voxels x 10 080 beamlets, ~30 M nnz):
+    size-independent properties plus a direct comparison with the C oracle."""
+    from oracle.c_oracle import COracle
+    case = make_config("cfg2")
+    rng = np.random.default_rng(7)
+    y, w_dose, w_grad = random_weights(case, rng, 0.5)
+    plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc=acc)
+    plan.set_weights(w_dose, w_grad)
+    tol = TOL[acc]
+    f, g = plan.eval(y)
+    d, vg, gb = plan.dose(), plan.voxelgrad(), plan.beamlet_grad()
+    co = COracle(case)
+    f0, g0 = co.eval(y, w_dose, w_grad)
+    assert abs(f - f0) <= tol * abs(f0)
+    assert relerr(g, g0) <= tol and relerr(d, co.d) <= tol and relerr(vg, co.vg) <= tol and relerr(gb, co.gb) <= tol
+    # adjoint identity <D x, vg> == <x, D^T vg>
+    x = np.repeat(y, np.diff(case.beam_ptr)) * w_dose
+    lhs, rhs = float(np.dot(d, vg)), float(np.dot(x, gb))
+    assert abs(lhs - rhs) <= 10 * tol * max(abs(lhs), abs(rhs))
+    # dose is linear in y
+    plan.eval(2 * y)
+    assert relerr(plan.dose(), 2 * d) <= tol
+    # aperture gradient is the w_grad-weighted beamlet gradient
+    assert relerr(g, np.add.reduceat(w_grad * gb, case.beam_ptr[:-1].astype(np.int64))) <= tol
+    plan.close()

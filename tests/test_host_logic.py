@@ -1,0 +1,137 @@
+"""Host-side logic of the product (no GPU): library symbols, aperture bookkeeping, price-row
+descriptors, updateOpenAperture - each against the oracle / golden fixtures."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import vmat_oracle as O
+from vmatwpencode_b200 import VMATlibrary as vl
+from vmatwpencode_b200 import _lib
+from vmatwpencode_b200._lib import PriceRow
+from vmatwpencode_b200.synth import make_case
+from helpers import load_golden, all_candidates, select, oracle_state_from_golden
+from k5_emulator import nodes_from_row
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vmat_b200.h")).read()
+    declared = set(re.findall(r"\b(vmat_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert os.path.isfile(_lib.LIB_PATH), "libvmat_b200.so not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/vmat_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert _lib.load().vmat_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(PriceRow) == 56
+    assert ctypes.sizeof(_lib.PriceParams) == 40
+    assert ctypes.sizeof(_lib.Options) == 64
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product must raise, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    case = make_case(V=300, nb=3, M=2, N=4, density=0.1, seed=1, gastep=10)
+    with pytest.raises(_lib.VmatError):
+        vl.bind(case)
+    data = vl.bind(case, gpu=False)
+    with pytest.raises(_lib.VmatError):
+        data.calcDose()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "vmatwpencode_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+def test_update_open_aperture_matches_golden(name):
+    z, case = load_golden(name)
+    data = vl.bind(case, gpu=False)
+    all_candidates(data, case)
+    for beam in z["selected"]:
+        beam = int(beam)
+        oam, dm, stg = select(data, case, beam, z[f"sel{beam}_l"], z[f"sel{beam}_r"], vl.updateOpenAperture)
+        assert np.array_equal(oam, z[f"sel{beam}_oam"])
+        assert np.array_equal(dm, z[f"sel{beam}_diag"])
+        assert np.array_equal(np.asarray(stg, dtype=float), z[f"sel{beam}_strength"])
+
+
+def test_update_open_aperture_random_vs_oracle():
+    case = make_case(V=500, nb=4, M=4, N=9, density=0.08, seed=44, gastep=10, ragged=True)
+    data = vl.bind(case, gpu=False)
+    st = O.OracleState(case)
+    rng = np.random.default_rng(9)
+    for trial in range(60):
+        beam = int(rng.integers(0, case.nb))
+        l = [float(rng.integers(-1, case.N - 1)) + (rng.choice([0.0, 0.25, 0.5, 0.995]) if trial % 2 else 0.0)
+             for _ in range(case.M)]
+        r = [min(case.N + 1.0, lv + float(rng.integers(0, 5)) + (rng.choice([0.0, 0.3, 0.75, 0.005]) if trial % 3 else 0.0))
+             for lv in l]
+        for state in (data, st):
+            state.llist[beam] = list(l)
+            state.rlist[beam] = list(r)
+        a = vl.updateOpenAperture(beam)
+        b = O.update_open_aperture(st, beam)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and list(a[2]) == list(b[2])
+
+
+def test_fvalidbeamlets_and_neighbours():
+    case = make_case(V=500, nb=6, M=4, N=7, density=0.08, seed=45, gastep=10, ragged=True)
+    data = vl.bind(case, gpu=False)
+    st = O.OracleState(case)
+    for i in range(case.nb):
+        for m in range(case.M):
+            vb, special = vl.fvalidbeamlets(m, i)
+            assert np.array_equal(vb, O.valid_beamlets(st, m, i))
+            assert special[0] == vb.min() - 1 and special[-1] == vb.max() + 1
+    for state in (data, st):
+        all_candidates(state, case)
+        for b in (1, 4):
+            state.caligraphicC.insertAngle(b, case.angles[b])
+            state.notinC.removeIndex(b)
+    for i in (0, 2, 3, 5):
+        assert vl._neighbours(i) == O.neighbours(st, i)
+
+
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B"])
+def test_price_row_descriptors_enumerate_the_oracle_network(name):
+    z, case = load_golden(name)
+    st = oracle_state_from_golden(z, case)
+    data = vl.bind(case, gpu=False)
+    all_candidates(data, case)
+    for beam in z["selected"]:
+        beam = int(beam)
+        select(data, case, beam, z[f"sel{beam}_l"], z[f"sel{beam}_r"], vl.updateOpenAperture)
+    for k in range(int(z["n_price"])):
+        C, C2, C3, b, vmax, speedlim, bw = [float(v) for v in z[f"price{k}_params"]]
+        for idx in z[f"price{k}_idx"]:
+            idx = int(idx)
+            predec, succ, am, ap = vl._neighbours(idx)
+            rows = (PriceRow * case.M)()
+            vl._fill_price_rows(rows, 0, am, ap, vmax, speedlim, predec, succ, case.N, case.M, idx, bw)
+            lcm, rcm, lcp, rcp, vmaxm, vmaxp = vl._neighbour_leaves(predec, succ, case.N, case.M, vmax)
+            win = O.leaf_window(case.N, case.M, lcm, lcp, rcm, rcp, vmaxm * (am / speedlim) / bw,
+                                vmaxp * (ap / speedlim) / bw, am, ap)
+            offset = 0
+            for m in range(case.M):
+                got = nodes_from_row(rows[m])
+                want = [(float(l), [float(r) for r in rs]) for l, rs in win[m]]
+                assert got == want, (name, k, idx, m)
+                vb = O.valid_beamlets(st, m, idx)
+                assert rows[m].vb_min == vb.min() and rows[m].vb_mask == sum(1 << int(v) for v in vb)
+                assert rows[m].grad_offset == (0 if m == 0 else offset)
+                offset = len(vb) - 1 if m == 0 else offset + len(vb)

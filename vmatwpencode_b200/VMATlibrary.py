@@ -1,0 +1,525 @@
+"""Drop-in objective / gradient / pricing functions on the B200 path.
+
+The reference's driver scripts (greedyVMATsampling.py and its earlier generations)
+define these names at module level and let them close over the singleton ``data``:
+
+    data.calcDose(), data.calcGradientandObjValue()      greedyVMATsampling.py:243-272
+    calcObjGrad(x, user_data=None)                        :578-582
+    fvalidbeamlets(i, index)                              :589-602
+    PPsubroutine(C, C2, C3, b, angdistancem, angdistancep, vmax, speedlim,
+                 predec, succ, N, M, thisApertureIndex, bw)              :618-789
+    parallelizationPricingProblem(i, C, C2, C3, b, vmax, speedlim, N, M, bw)   :791-822
+    PricingProblem(C, C2, C3, b, vmax, speedlim, N, M, bw)               :824-856
+    solveRMC(YU)                                          :858-885
+    colGen(C, WholeCircle, initialApertures)              :937-1061
+    updateOpenAperture(i)                                 :1070-1130
+
+This module provides the same names with the same arguments, return values and error
+behaviour (sampling-variant semantics, quirks Q1-Q8 of SURVEY.md included), but the sparse
+arithmetic runs in libvmat_b200.so on the GPU: ``bind(case)`` uploads D once, and each
+``calcObjGrad`` is three CUDA kernels.  There is no CPU fallback.
+
+Not reproduced: plotting, pickling and the debug prints of the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+import sys
+import time
+import warnings
+
+import numpy as np
+from scipy.optimize import minimize
+
+from ._lib import PriceParams, PriceRow, VmatError
+from .plan import DosePlan
+
+# module globals the reference scripts also have
+data = None
+N = None          # beamlets per leaf row  (len(data.yinter), :466)
+M = None          # leaf rows              (len(data.xinter), :468)
+kappa = []        # candidate ordering used by the WholeCircle branch (:30,959-966)
+eliminationThreshold = 10E-3
+kappasize = 16
+numcores = 8
+
+
+class region:
+    """Structure bookkeeping (greedyVMATsampling.py:74-91)."""
+
+    def __init__(self, iind, iindi, ifullindi, itarget):
+        self.index = iind
+        self.sizeInVoxels = len(iindi)
+        self.indices = iindi
+        self.fullIndices = ifullindi
+        self.target = itarget
+
+
+class apertureList:
+    """Control-point locations with their gantry angles, kept ascending
+    (greedyVMATsampling.py:97-140).  loc and angle are sorted separately, as there."""
+
+    def __init__(self):
+        self.loc = []
+        self.angle = []
+
+    def insertAngle(self, i, aperangle):
+        self.angle.append(aperangle)
+        self.loc.append(i)
+        self.loc.sort()
+        self.angle.sort()
+
+    def removeIndex(self, index):
+        k = self.loc.index(index)
+        del self.loc[k]
+        del self.angle[k]
+
+    def removeAngle(self, tangl):
+        k = self.angle.index(tangl)
+        del self.loc[k]
+        del self.angle[k]
+
+    def __call__(self, index):
+        return self.angle[self.loc.index(index)]
+
+    def len(self):
+        return len(self.loc)
+
+    def isEmpty(self):
+        return not self.loc
+
+
+class _LazyDZdK:
+    """Stand-in for the reference's dense V x numbeams ``dZdK`` (:246,251).  It is never
+    formed on the GPU path (11.5 GB at 4M voxels x 360 control points); ``toarray()`` builds
+    it on demand from the beamlet weights for anyone who really wants it."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def toarray(self):
+        raise VmatError("dZdK is not materialised on the GPU path; aperturegradient is computed "
+                        "as sum_j w_grad[j] * (D^T vg)[j]")
+
+
+class vmat_class:
+    """The reference's global state object (greedyVMATsampling.py:145-276) with the two
+    evaluation methods backed by a DosePlan."""
+
+    def __init__(self):
+        self.numX = 0
+        self.numvoxels = 0
+        self.numstructs = 0
+        self.numoars = 0
+        self.numtargets = 0
+        self.numbeams = 0
+        self.totaldijs = 0
+        self.objectiveValue = float("inf")
+        self.beamletsPerBeam = []
+        self.dijsPerBeam = []
+        self.maskValue = []
+        self.fullMaskValue = []
+        self.regionIndices = []
+        self.targets = []
+        self.oars = []
+        self.regions = []
+        self.functionData = []
+        self.notinC = apertureList()
+        self.caligraphicC = apertureList()
+        self.currentIntensities = np.empty(1)
+        self.xinter = []
+        self.yinter = []
+        self.xdirection = []
+        self.ydirection = []
+        self.llist = []
+        self.rlist = []
+        self.rmpres = []
+        self.aperturegradient = []
+        self.openApertureMaps = []
+        self.diagmakers = []
+        self.strengths = []
+        self.dZdK = 0.0
+        self.pointtoAngle = []
+        self.Dlist = []
+        self.entryCounter = 0
+        self.listIndexofAperturesRemovedEachStep = []
+        self.history = []
+        # GPU side
+        self.plan = None
+        self.beam_ptr = None
+        self._uploaded = {}
+        self._dose = None
+        self._vg = None
+        self._gb = None
+        self._fg = None
+        self._vb_cache = {}
+
+    # currentDose / voxelgradient are read back from the GPU only when somebody looks
+    @property
+    def currentDose(self):
+        if self._dose is None and self.plan is not None and self._fg is not None:
+            self._dose = self.plan.dose()
+        return self._dose
+
+    @currentDose.setter
+    def currentDose(self, v):
+        self._dose = v
+
+    @property
+    def voxelgradient(self):
+        if self._vg is None and self.plan is not None and self._fg is not None:
+            self._vg = self.plan.voxelgrad()
+        return self._vg
+
+    @voxelgradient.setter
+    def voxelgradient(self, v):
+        self._vg = v
+
+    @property
+    def beamletgradient(self):
+        """D^T voxelgradient for every beamlet: each control point's ``beamGrad`` (:646)."""
+        if self._gb is None and self.plan is not None and self._fg is not None:
+            self._gb = self.plan.beamlet_grad()
+        return self._gb
+
+    def _sync_apertures(self):
+        sel = set(self.caligraphicC.loc)
+        for i in list(self._uploaded):
+            if i not in sel:
+                self.plan.set_aperture(i, None, None)
+                del self._uploaded[i]
+        for i in self.caligraphicC.loc:
+            key = (id(self.openApertureMaps[i]), id(self.diagmakers[i]), id(self.strengths[i]))
+            if self._uploaded.get(i) == key:
+                continue
+            nbl = int(self.beam_ptr[i + 1] - self.beam_ptr[i])
+            w_dose = np.zeros(nbl)
+            oam = np.asarray(self.openApertureMaps[i], dtype=np.int64)
+            if oam.size:
+                w_dose[oam] = np.asarray(self.strengths[i], dtype=float)
+            w_grad = np.zeros(nbl)
+            dm = np.asarray(self.diagmakers[i], dtype=float)
+            w_grad[:len(dm)] = dm
+            self.plan.set_aperture(i, w_dose, w_grad)
+            self._uploaded[i] = key
+
+    def calcDose(self):
+        """Dose of the current apertures and intensities (greedyVMATsampling.py:243-251).
+        On this path the same launch sequence also produces objective and gradients; they are
+        published by calcGradientandObjValue()."""
+        if self.plan is None:
+            raise VmatError("no GPU plan bound: call VMATlibrary.bind(case) first")
+        self._sync_apertures()
+        y = np.asarray(self.currentIntensities, dtype=float).ravel()
+        self._fg = self.plan.eval(y)
+        self._dose = self._vg = self._gb = None
+        self.dZdK = _LazyDZdK(self)
+
+    def calcGradientandObjValue(self):
+        """Objective, voxel gradient, aperture gradient (greedyVMATsampling.py:254-272)."""
+        if self._fg is None:
+            self.calcDose()
+        f, g = self._fg
+        self.objectiveValue = np.float64(f)
+        self.aperturegradient = np.asmatrix(g).transpose()
+
+
+def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool = True, **plan_opts):
+    """Create the module-level ``data`` for a case (anything with the attributes of
+    vmatwpencode_b200.synth.Case) and upload its D to GPU `device`.
+
+    `acc="f64"` (default here) accumulates in double so that the greedy loop reproduces the
+    reference's aperture sequence; `acc="f32"` is the throughput mode."""
+    global data, N, M
+    d = vmat_class()
+    d.numvoxels = case.V
+    d.numbeams = case.nb
+    d.beam_ptr = np.asarray(case.beam_ptr, dtype=np.int64)
+    d.numX = int(d.beam_ptr[-1])
+    d.beamletsPerBeam = np.diff(d.beam_ptr)
+    d.xinter = np.asarray(case.xinter)
+    d.yinter = np.asarray(case.yinter)
+    d.xdirection = [np.asarray(a) for a in case.xdirection]
+    d.ydirection = [np.asarray(a) for a in case.ydirection]
+    d.pointtoAngle = list(case.angles)
+    d.currentIntensities = np.zeros(case.nb, dtype=float)
+    d.openApertureMaps = [[] for _ in range(case.nb)]
+    d.diagmakers = [[] for _ in range(case.nb)]
+    d.strengths = [[] for _ in range(case.nb)]
+    d.llist = [[-1] * len(d.xinter) for _ in range(case.nb)]           # fully open (:952-954)
+    d.rlist = [[len(d.yinter) + 1] * len(d.xinter) for _ in range(case.nb)]
+    d.totaldijs = int(case.D.nnz)
+    if gpu:     # gpu=False: host-side bookkeeping only (geometry, updateOpenAperture); no evaluation
+        d.plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, device=device,
+                          store=store, acc=acc, **plan_opts)
+    data = d
+    N = len(d.yinter)
+    M = len(d.xinter)
+    return d
+
+
+def calcObjGrad(x, user_data=None):
+    """(objective, aperture gradient) at intensities x (greedyVMATsampling.py:578-582)."""
+    data.currentIntensities = x
+    data.calcDose()
+    data.calcGradientandObjValue()
+    return data.objectiveValue, data.aperturegradient
+
+
+def fvalidbeamlets(i, index):
+    """Beamlet y-indices that exist in leaf row i of control point `index`, and the same
+    range with both neighbours appended (greedyVMATsampling.py:589-602)."""
+    key = (i, index)
+    hit = data._vb_cache.get(key)
+    if hit is None:
+        inrow = data.xdirection[index] == data.xinter[i]
+        vb = np.flatnonzero(np.isin(data.yinter, data.ydirection[index][inrow]))
+        if vb.size == 0:
+            raise ValueError("min() arg is an empty sequence")       # what the reference raises
+        hit = (vb, np.concatenate(([vb.min() - 1], vb, [vb.max() + 1])))
+        data._vb_cache[key] = hit
+    return hit
+
+
+def _neighbour_leaves(predec, succ, Nn, Mm, vmax):
+    """Leaf limits and leaf speeds of the adjacent selected apertures (:620-642)."""
+    vmaxm = vmaxp = vmax
+    if type(predec) is list:
+        lcm, rcm, vmaxm = [-1] * Mm, [Nn] * Mm, float("inf")
+    else:
+        lcm, rcm = data.llist[predec], data.rlist[predec]
+    if type(succ) is list:
+        lcp, rcp, vmaxp = [-1] * Mm, [Nn] * Mm, float("inf")
+    else:
+        lcp, rcp = data.llist[succ], data.rlist[succ]
+    return lcm, rcm, lcp, rcp, vmaxm, vmaxp
+
+
+def _fill_price_rows(rows, base, angdistancem, angdistancep, vmax, speedlim, predec, succ, Nn, Mm,
+                     thisApertureIndex, bw):
+    """Host part of PPsubroutine: the leaf windows of every row (:664,672-680,713-724) and the
+    beamlet bookkeeping (fvalidbeamlets, the running ``leftmostleaf`` of :705,756)."""
+    if Nn > 62:
+        raise VmatError("pricing kernel supports at most 62 beamlets per leaf row")
+    lcm, rcm, lcp, rcp, vmaxm, vmaxp = _neighbour_leaves(predec, succ, Nn, Mm, vmax)
+    travelm = vmaxm * (angdistancem / speedlim) / bw
+    travelp = vmaxp * (angdistancep / speedlim) / bw
+    leftmost = 0
+    for m in range(Mm):
+        vb, _ = fvalidbeamlets(m, thisApertureIndex)
+        row = rows[base + m]
+        lo = math.ceil(max(-1, lcm[m] - travelm, lcp[m] - travelp))
+        hi = 1 + math.floor(min(Nn - 1, lcm[m] + travelm, lcp[m] + travelp))
+        if hi - lo <= 0:
+            # np.arange(mid, mid + 1) of the reference: one value, or two when mid + 1 rounds up
+            mid = (angdistancep * lcm[m] + angdistancem * lcp[m]) / (angdistancep + angdistancem)
+            row.l_first = mid
+            row.n_l = len(np.arange(mid, mid + 1))
+        else:
+            row.l_first = float(lo)
+            row.n_l = hi - lo
+        row.r_lo = max(rcm[m] - travelm, rcp[m] - travelp)
+        row.r_hi = min(Nn, rcm[m] + travelm, rcp[m] + travelp)
+        if math.isinf(angdistancem) or math.isinf(angdistancep):
+            row.r_mid = float("nan")          # unreachable: an infinite travel never empties a range
+            row.n_r_mid = 1
+        else:
+            row.r_mid = (angdistancep * rcm[m] + angdistancem * rcp[m]) / (angdistancep + angdistancem)
+            row.n_r_mid = len(np.arange(row.r_mid, row.r_mid + 1))
+        mask = 0
+        for yv in vb:
+            mask |= 1 << int(yv)
+        row.vb_mask = mask
+        row.vb_min = int(vb.min())
+        if m == 0:
+            row.grad_offset = 0
+            leftmost = len(vb) - 1                     # quirk Q1
+        else:
+            row.grad_offset = leftmost
+            leftmost = len(vb) + leftmost
+
+
+def _price(cands, C_, C2, C3, b, vmax, speedlim, Nn, Mm, bw):
+    """Price a list of (index, predec, succ, angdistancem, angdistancep) in one launch."""
+    if data._fg is None:
+        raise VmatError("pricing needs the beamlet gradient of an evaluation: call data.calcDose() first")
+    rows = (PriceRow * (len(cands) * Mm))()
+    for k, (idx, predec, succ, am, ap) in enumerate(cands):
+        _fill_price_rows(rows, k * Mm, am, ap, vmax, speedlim, predec, succ, Nn, Mm, idx, bw)
+    prm = PriceParams(C=float(C_), C2=float(C2), C3=float(C3), b=float(b), M=Mm, N=Nn)
+    return data.plan.price([c[0] for c in cands], prm, rows)
+
+
+def PPsubroutine(C, C2, C3, b, angdistancem, angdistancep, vmax, speedlim, predec, succ, N, M,
+                 thisApertureIndex, bw):
+    """Best aperture for one control point: (p, l, r) with len(l) == len(r) == M
+    (greedyVMATsampling.py:618-789).  Uses the beamlet gradient of the last evaluation."""
+    p, l, r = _price([(thisApertureIndex, predec, succ, angdistancem, angdistancep)],
+                     C, C2, C3, b, vmax, speedlim, N, M, bw)
+    return np.float64(p[0]), [np.int64(v) for v in l[0]], [np.int64(v) for v in r[0]]
+
+
+def _neighbours(thisApertureIndex):
+    """Nearest selected predecessor / successor and angular gaps (:796-818)."""
+    succs = [i for i in data.caligraphicC.loc if i > thisApertureIndex]
+    predecs = [i for i in data.caligraphicC.loc if i < thisApertureIndex]
+    if 0 == len(succs):
+        succ, angdistancep = [], np.inf
+    else:
+        succ = min(succs)
+        angdistancep = data.caligraphicC(succ) - data.notinC(thisApertureIndex)
+    if 0 == len(predecs):
+        predec, angdistancem = [], np.inf
+    else:
+        predec = max(predecs)
+        angdistancem = data.notinC(thisApertureIndex) - data.caligraphicC(predec)
+    return predec, succ, angdistancem, angdistancep
+
+
+def parallelizationPricingProblem(i, C, C2, C3, b, vmax, speedlim, N, M, bw):
+    """(p, l, r, i) for candidate control point i (greedyVMATsampling.py:791-822)."""
+    predec, succ, am, ap = _neighbours(i)
+    p, l, r = PPsubroutine(C, C2, C3, b, am, ap, vmax, speedlim, predec, succ, N, M, i, bw)
+    return p, l, r, i
+
+
+def PricingProblem(C, C2, C3, b, vmax, speedlim, N, M, bw):
+    """Price every candidate in data.notinC and return the most negative one:
+    (pstar, l, r, bestApertureIndex) (greedyVMATsampling.py:824-856).  The reference forks a
+    process pool over candidates; here all candidates are one kernel launch."""
+    cands = []
+    for i in data.notinC.loc:
+        predec, succ, am, ap = _neighbours(i)
+        cands.append((i, predec, succ, am, ap))
+    p, l, r = _price(cands, C, C2, C3, b, vmax, speedlim, N, M, bw)
+    indstar = int(np.argmin(p))
+    for k in range(len(cands)):
+        if M != len(l[k]):
+            sys.exit("Length of left vector is less than 28")
+    return (np.float64(p[indstar]), [np.int64(v) for v in l[indstar]], [np.int64(v) for v in r[indstar]],
+            cands[indstar][0])
+
+
+def updateOpenAperture(i):
+    """Leaf positions of control point i -> (open beamlet indices, diagmaker, strengths)
+    (greedyVMATsampling.py:1070-1130), including its quirks: the first open beamlet of a row
+    has strength ceil(left)-left (0 for integer leaves), and fractional right-edge strengths
+    are written to the LAST element of the beam-wide diagmaker."""
+    nbl = int(data.beam_ptr[i + 1] - data.beam_ptr[i])
+    diagmaker = np.zeros(nbl, dtype=float)
+    open_idx = []
+    open_strength = []
+    seen = 0
+    for m in range(len(data.llist[i])):
+        vb, _ = fvalidbeamlets(m, i)
+        first_y, last_y, count = int(vb.min()), int(vb.max()), len(vb)
+        lpos, rpos = data.llist[i][m], data.rlist[i][m]
+        indleft = (lpos + 1 + seen - first_y) if lpos >= first_y - 1 else 0
+        if rpos > last_y:
+            indright = count + seen
+        else:
+            indright = (rpos - 1 + seen - first_y) if rpos >= first_y else 0
+        seen += count
+        k0, k1 = int(np.floor(indleft)), int(np.ceil(indright))
+        if k0 >= k1:
+            continue
+        run = list(range(k0, k1))
+        s = [1.0] * len(run)
+        s[0] = np.ceil(indleft) - indleft
+        for k, sv in zip(run, s):
+            diagmaker[k] = sv
+        open_idx.extend(run)
+        open_strength.extend(s)
+        edge = indright - np.floor(indright)
+        if edge > 0.01:
+            open_strength[-1] = edge
+            diagmaker[-1] = edge
+        if k1 - k0 == 1:
+            open_strength[-1] = indright - indleft
+            diagmaker[-1] = indright - indleft
+    return np.array(open_idx, dtype=int), diagmaker, open_strength
+
+
+def solveRMC(YU):
+    """Restricted master problem: scipy L-BFGS-B over all control-point intensities, free
+    only where an aperture is selected (greedyVMATsampling.py:858-885).  scipy stays on the
+    host so that the iterates are the reference's; every callback is one GPU evaluation."""
+    start = time.time()
+    calcObjGrad(data.currentIntensities)
+    boundschoice = [(0, YU) if k in data.caligraphicC.loc else (0, 0) for k in range(data.numbeams)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = minimize(calcObjGrad, data.currentIntensities, method="L-BFGS-B", jac=True,
+                       bounds=boundschoice, options={"ftol": 1e-1, "maxiter": 200})
+    data.rmp_seconds = time.time() - start
+    return res
+
+
+def colGen(C, WholeCircle, initialApertures, max_iter=None):
+    """Greedy column generation (greedyVMATsampling.py:937-1061): price, add the best
+    aperture, re-optimise intensities, resample candidates; returns pstar.  Each step is
+    appended to data.history.  (`max_iter` is an addition for bounded test runs.)"""
+    global kappa
+    C2 = 1.0
+    C3 = 1.0
+    eliminationPhase = False
+    vmax = 2.25
+    speedlim = 0.83
+    beamletwidth = 0.5
+    RU = 10.0
+    YU = RU / speedlim
+    data.llist = [[-1] * len(data.xinter) for _ in range(data.numbeams)]
+    data.rlist = [[len(data.yinter) + 1] * len(data.xinter) for _ in range(data.numbeams)]
+    if not WholeCircle or not kappa:
+        kappa = list(range(data.numbeams))
+    random.seed(13)
+    kappa = random.sample(kappa, len(kappa))
+    for _ in range(min(initialApertures, len(kappa))):
+        i = kappa.pop(0)
+        data.notinC.insertAngle(i, data.pointtoAngle[i])
+    data.caligraphicC = apertureList()
+    pstar = -np.inf
+    data.history = []
+    while (pstar < 0) & (data.notinC.len() > 0):
+        data.calcDose()
+        data.calcGradientandObjValue()
+        pstar, lm, rm, bestApertureIndex = PricingProblem(C, C2, C3, 0.5, vmax, speedlim, N, M, beamletwidth)
+        if pstar >= 0:
+            break
+        data.caligraphicC.insertAngle(bestApertureIndex, data.notinC(bestApertureIndex))
+        data.notinC.removeIndex(bestApertureIndex)
+        data.llist[bestApertureIndex] = lm
+        data.rlist[bestApertureIndex] = rm
+        (data.openApertureMaps[bestApertureIndex], data.diagmakers[bestApertureIndex],
+         data.strengths[bestApertureIndex]) = updateOpenAperture(bestApertureIndex)
+        rmpres = solveRMC(YU)
+        data.rmpres = rmpres
+        removed = []
+        for thisindex in range(data.numbeams):
+            if thisindex in data.caligraphicC.loc:
+                if (rmpres.x[thisindex] < eliminationThreshold) & eliminationPhase:
+                    data.entryCounter += 1
+                    removed.append(thisindex)
+                    data.notinC.insertAngle(thisindex, data.pointtoAngle[thisindex])
+                    data.caligraphicC.removeIndex(thisindex)
+        if len(data.listIndexofAperturesRemovedEachStep) > 1:
+            if np.any(np.isin(removed, data.listIndexofAperturesRemovedEachStep[-1])):
+                break
+            if np.any(np.isin(removed, data.listIndexofAperturesRemovedEachStep[-2])):
+                break
+        data.listIndexofAperturesRemovedEachStep.append(removed)
+        data.history.append(dict(idx=int(bestApertureIndex), l=[int(v) for v in lm], r=[int(v) for v in rm],
+                                 pstar=float(pstar), x=np.array(rmpres.x, dtype=float), fun=float(rmpres.fun),
+                                 nit=int(rmpres.nit), nfev=int(rmpres.nfev)))
+        while not data.notinC.isEmpty():
+            kappa.append(data.notinC.loc[0])
+            data.notinC.removeIndex(data.notinC.loc[0])
+        random.seed(13)
+        for i in random.sample(kappa, min(initialApertures, len(kappa))):
+            data.notinC.insertAngle(i, data.pointtoAngle[i])
+            kappa.remove(i)
+        if max_iter is not None and len(data.history) >= max_iter:
+            break
+    return pstar

@@ -1,0 +1,708 @@
+// libvmat_b200.so - C ABI (include/vmat_b200.h) over the sm_100a kernels.
+// Plan construction (CSR -> row-sorted sliced-ELL layouts), evaluation launch sequence
+// (K1 -> K2 -> K3, optionally replayed as one CUDA graph), result transfer.
+#include "../../include/vmat_b200.h"
+#include "vmat_eval_kernels.cuh"
+#include "vmat_price_kernels.cuh"
+#include "vmat_kmedoid_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace vmat;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            return fail(VMAT_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+        }                                                                                 \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        return cudaMalloc(&p, n ? n : 16);
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct vmat_plan {
+    int device = 0;
+    int64_t V = 0, B = 0, nnz = 0;
+    int32_t nb = 0;
+    vmat_options_t opt{};
+    size_t acc_size = 4;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int smem_optin = 0;
+
+    std::vector<int32_t> beam_ptr;
+    // K1 layout
+    DevBuf sell1, off1, rows1, thr_s, over_s, under_s;
+    int32_t nslices1 = 0;
+    int64_t units1 = 0;
+    // K2 layout
+    DevBuf sell2, off2, rows2, tasks2;
+    int32_t nslices2 = 0, ntasks2 = 0, ntiles = 0, T = 0;
+    int64_t units2 = 0;
+    // state
+    DevBuf y, beam_of, beam_ptr_d, w_dose, w_grad, xg, d, vg, fpart, partial, gbf, result, counter, scratch64;
+    double* h_y = nullptr;       // pinned
+    double* h_res = nullptr;     // pinned
+    bool x_in_smem = true;
+    int k1_threads = 1024, k1_grid = 148, k2_threads = 256;
+    size_t k1_smem = 0, k2_smem = 0;
+    bool evaluated = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    // pricing scratch
+    DevBuf price_rows, price_cand, price_p, price_l, price_r, price_dad;
+    size_t price_cap_cand = 0, price_cap_dad = 0;
+    // per-kernel timing (vmat_set_timing)
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;      // 4 events per evaluation slot
+    int64_t tcount = 0;
+    static constexpr int kTimingSlots = 1024;
+
+    ~vmat_plan() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph) cudaGraphDestroy(graph);
+        for (auto e : tev) cudaEventDestroy(e);
+        if (h_y) cudaFreeHost(h_y);
+        if (h_res) cudaFreeHost(h_res);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+extern "C" int vmat_version(void) { return 100; }
+extern "C" const char* vmat_last_error(void) { return g_err.c_str(); }
+
+extern "C" void vmat_default_options(vmat_options_t* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->store_dtype = VMAT_F32;
+    o->acc_dtype = VMAT_F32;
+    o->use_graph = 1;
+}
+
+// ---------------------------------------------------------------------------------
+// dispatch helpers
+// ---------------------------------------------------------------------------------
+#define DISPATCH_STORE(dt, VT, ...)                                          \
+    switch (dt) {                                                            \
+        case VMAT_F32:  { using VT = float; __VA_ARGS__; break; }            \
+        case VMAT_BF16: { using VT = __nv_bfloat16; __VA_ARGS__; break; }    \
+        case VMAT_F64:  { using VT = double; __VA_ARGS__; break; }           \
+        default: return fail(VMAT_E_ARG, "bad store dtype");                 \
+    }
+#define DISPATCH_ACC(dt, AT, ...)                                            \
+    switch (dt) {                                                            \
+        case VMAT_F32: { using AT = float; __VA_ARGS__; break; }             \
+        case VMAT_F64: { using AT = double; __VA_ARGS__; break; }            \
+        default: return fail(VMAT_E_ARG, "bad accumulate dtype");            \
+    }
+
+template <typename VT> struct Unroll { static constexpr int U = 4; };
+template <> struct Unroll<double> { static constexpr int U = 2; };
+
+static int store_units(int dt) { return dt == VMAT_F32 ? 64 : dt == VMAT_BF16 ? 48 : 96; }
+static int store_bytes(int dt) { return dt == VMAT_F32 ? 4 : dt == VMAT_BF16 ? 2 : 8; }
+
+template <typename AT>
+static int upload_cast(DevBuf& dst, const std::vector<double>& src, cudaStream_t st) {
+    std::vector<AT> tmp(src.size());
+    for (size_t i = 0; i < src.size(); ++i) tmp[i] = (AT)src[i];
+    CU(dst.alloc(tmp.size() * sizeof(AT)));
+    CU(cudaMemcpyAsync(dst.p, tmp.data(), tmp.size() * sizeof(AT), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+template <typename Tv>
+static int upload_vec(DevBuf& dst, const std::vector<Tv>& src, cudaStream_t st) {
+    CU(dst.alloc(src.size() * sizeof(Tv)));
+    if (!src.empty()) {
+        CU(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(Tv), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// Build one SELL layout from segment descriptors (already grouped in slices of 32).
+static int build_sell(vmat_plan* P, int store_dtype, int src_dtype,
+                      const std::vector<int64_t>& slice_off, const std::vector<int64_t>& seg_start,
+                      const std::vector<int32_t>& seg_len, const std::vector<int32_t>& seg_colbase,
+                      const int32_t* d_col, const void* d_val, DevBuf& sell, DevBuf& off_d) {
+    const int32_t nslices = (int32_t)slice_off.size() - 1;
+    const int64_t units = slice_off.back();
+    CU(sell.alloc((size_t)units * 16));
+    if (upload_vec(off_d, slice_off, P->stream)) return VMAT_E_CUDA;
+    if (nslices == 0) return 0;
+    DevBuf dstart, dlen, dcb;
+    if (upload_vec(dstart, seg_start, P->stream)) return VMAT_E_CUDA;
+    if (upload_vec(dlen, seg_len, P->stream)) return VMAT_E_CUDA;
+    if (upload_vec(dcb, seg_colbase, P->stream)) return VMAT_E_CUDA;
+    const int threads = 256;
+    const int64_t blocks = ((int64_t)nslices * 32 + threads - 1) / threads;
+    DISPATCH_STORE(store_dtype, VT, {
+        if (src_dtype == VMAT_F32)
+            k_fill_sell<VT, float><<<(unsigned)blocks, threads, 0, P->stream>>>(
+                nslices, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
+                d_col, static_cast<const float*>(d_val), sell.as<uint4>());
+        else
+            k_fill_sell<VT, double><<<(unsigned)blocks, threads, 0, P->stream>>>(
+                nslices, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
+                d_col, static_cast<const double*>(d_val), sell.as<uint4>());
+    });
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(P->stream));
+    return 0;
+}
+
+static int capture_graph(vmat_plan* P);
+static int launch_eval(vmat_plan* P, cudaStream_t st, int phase);
+
+extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_t B, int32_t nb,
+                                const int32_t* beam_ptr,
+                                const int64_t* vrowptr, const int32_t* vcol, const void* vval,
+                                const int64_t* browptr, const int32_t* bcol, const void* bval,
+                                int src_dtype, int location,
+                                const double* thr, const double* over, const double* under,
+                                const vmat_options_t* opt_in) {
+    if (!out || V <= 0 || B <= 0 || nb <= 0 || !beam_ptr || !vrowptr || !browptr || !thr || !over || !under)
+        return fail(VMAT_E_ARG, "vmat_plan_create: null or non-positive argument");
+    if (src_dtype != VMAT_F32 && src_dtype != VMAT_F64) return fail(VMAT_E_ARG, "src_dtype must be f32 or f64");
+    if (beam_ptr[0] != 0 || beam_ptr[nb] != B) return fail(VMAT_E_ARG, "beam_ptr must run from 0 to B");
+    if (V >= (int64_t)1 << 31 || B >= (int64_t)1 << 31) return fail(VMAT_E_UNSUPPORTED, "V and B must fit int32");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VMAT_E_ARG, "no such CUDA device");
+    CU(cudaSetDevice(device));
+
+    vmat_plan* P = new (std::nothrow) vmat_plan();
+    if (!P) return fail(VMAT_E_NOMEM, "out of host memory");
+    struct Guard { vmat_plan* p; ~Guard() { delete p; } } guard{P};
+    P->device = device; P->V = V; P->B = B; P->nb = nb;
+    if (opt_in) P->opt = *opt_in; else vmat_default_options(&P->opt);
+    if (P->opt.acc_dtype != VMAT_F32 && P->opt.acc_dtype != VMAT_F64) return fail(VMAT_E_ARG, "bad acc_dtype");
+    if (P->opt.store_dtype < 0 || P->opt.store_dtype > 2) return fail(VMAT_E_ARG, "bad store_dtype");
+    P->acc_size = P->opt.acc_dtype == VMAT_F64 ? 8 : 4;
+    P->beam_ptr.assign(beam_ptr, beam_ptr + nb + 1);
+    CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaDeviceGetAttribute(&P->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    cudaStream_t st = P->stream;
+
+    // ---- bring row pointers to the host, CSR payload to the device ----------------
+    std::vector<int64_t> h_vrow(V + 1), h_brow(B + 1);
+    const cudaMemcpyKind to_host = location == VMAT_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+    CU(cudaMemcpy(h_vrow.data(), vrowptr, (V + 1) * sizeof(int64_t), to_host));
+    CU(cudaMemcpy(h_brow.data(), browptr, (B + 1) * sizeof(int64_t), to_host));
+    const int64_t nnz = h_vrow[V];
+    if (nnz != h_brow[B]) return fail(VMAT_E_ARG, "voxel-major and beamlet-major CSR disagree on nnz");
+    if (nnz > 0 && (!vcol || !vval || !bcol || !bval)) return fail(VMAT_E_ARG, "null CSR payload");
+    P->nnz = nnz;
+    const size_t sv = src_dtype == VMAT_F32 ? 4 : 8;
+    DevBuf up_vcol, up_vval, up_bcol, up_bval, up_brow;
+    const int32_t *d_vcol = vcol, *d_bcol = bcol;
+    const void *d_vval = vval, *d_bval = bval;
+    const int64_t* d_brow = browptr;
+    if (location == VMAT_HOST) {
+        CU(up_vcol.alloc(nnz * 4)); CU(up_vval.alloc(nnz * sv));
+        CU(cudaMemcpy(up_vcol.p, vcol, nnz * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(up_vval.p, vval, nnz * sv, cudaMemcpyHostToDevice));
+        d_vcol = up_vcol.as<int32_t>(); d_vval = up_vval.p;
+    }
+
+    // ---- K1 layout: voxels sorted by row length (descending, stable) ----------------
+    {
+        std::vector<int32_t> order(V);
+        {
+            int64_t maxlen = 0;
+            for (int64_t v = 0; v < V; ++v) maxlen = std::max(maxlen, h_vrow[v + 1] - h_vrow[v]);
+            std::vector<int64_t> cnt(maxlen + 2, 0);
+            for (int64_t v = 0; v < V; ++v) cnt[maxlen - (h_vrow[v + 1] - h_vrow[v]) + 1]++;
+            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+            for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - (h_vrow[v + 1] - h_vrow[v])]++] = (int32_t)v;
+        }
+        const int32_t ns = (int32_t)((V + 31) / 32);
+        const int units = store_units(P->opt.store_dtype);
+        std::vector<int64_t> off(ns + 1, 0), seg_start((size_t)ns * 32, 0);
+        std::vector<int32_t> seg_len((size_t)ns * 32, 0), seg_cb((size_t)ns * 32, 0), rows((size_t)ns * 32, -1);
+        std::vector<double> t_s((size_t)ns * 32, 0.0), o_s((size_t)ns * 32, 0.0), u_s((size_t)ns * 32, 0.0);
+        for (int32_t s = 0; s < ns; ++s) {
+            int64_t mx = 0;
+            for (int k = 0; k < 32; ++k) {
+                const int64_t pos = (int64_t)s * 32 + k;
+                if (pos >= V) break;
+                const int32_t v = order[pos];
+                const int64_t len = h_vrow[v + 1] - h_vrow[v];
+                seg_start[pos] = h_vrow[v]; seg_len[pos] = (int32_t)len; rows[pos] = v;
+                t_s[pos] = thr[v]; o_s[pos] = over[v]; u_s[pos] = under[v];
+                mx = std::max(mx, len);
+            }
+            off[s + 1] = off[s] + (mx + 3) / 4 * units;
+        }
+        P->nslices1 = ns; P->units1 = off[ns];
+        if (int rc = build_sell(P, P->opt.store_dtype, src_dtype, off, seg_start, seg_len, seg_cb,
+                                d_vcol, d_vval, P->sell1, P->off1)) return rc;
+        if (upload_vec(P->rows1, rows, st)) return VMAT_E_CUDA;
+        int rc = 0;
+        DISPATCH_ACC(P->opt.acc_dtype, AT, {
+            rc |= upload_cast<AT>(P->thr_s, t_s, st);
+            rc |= upload_cast<AT>(P->over_s, o_s, st);
+            rc |= upload_cast<AT>(P->under_s, u_s, st);
+        });
+        if (rc) return VMAT_E_CUDA;
+    }
+    up_vcol.alloc(0); up_vval.alloc(0);   // release the voxel-major CSR copy
+
+    if (location == VMAT_HOST) {
+        CU(up_bcol.alloc(nnz * 4)); CU(up_bval.alloc(nnz * sv)); CU(up_brow.alloc((B + 1) * 8));
+        CU(cudaMemcpy(up_bcol.p, bcol, nnz * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(up_bval.p, bval, nnz * sv, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(up_brow.p, browptr, (B + 1) * 8, cudaMemcpyHostToDevice));
+        d_bcol = up_bcol.as<int32_t>(); d_bval = up_bval.p; d_brow = up_brow.as<int64_t>();
+    }
+
+    // ---- K2 layout: column tiles of T voxels; per tile, beamlet segments sorted by length
+    {
+        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : (P->opt.acc_dtype == VMAT_F64 ? 8192 : 16384);
+        T = (T + 63) / 64 * 64;
+        if ((size_t)T * P->acc_size > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
+        const int32_t nt = (int32_t)((V + T - 1) / T);
+        P->T = T; P->ntiles = nt;
+        DevBuf d_seg;
+        const int64_t nseg = (int64_t)B * (nt + 1);
+        CU(d_seg.alloc(nseg * 8));
+        k_segment_bounds<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>((int32_t)B, nt, T, d_brow, d_bcol, d_seg.as<int64_t>());
+        CU(cudaGetLastError());
+        std::vector<int64_t> segstart(nseg);
+        CU(cudaMemcpyAsync(segstart.data(), d_seg.p, nseg * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        d_seg.alloc(0);
+
+        const int units = store_units(P->opt.store_dtype);
+        std::vector<int64_t> off(1, 0), seg_start;
+        std::vector<int32_t> seg_len, seg_cb, rows;
+        std::vector<int32_t> tile_sbegin(nt + 1, 0);
+        std::vector<int64_t> slice_chunks;
+        std::vector<std::pair<int32_t, int32_t>> items;   // (len, beamlet)
+        for (int32_t t = 0; t < nt; ++t) {
+            items.clear();
+            for (int32_t b = 0; b < (int32_t)B; ++b) {
+                const int64_t s0 = segstart[(int64_t)b * (nt + 1) + t], s1 = segstart[(int64_t)b * (nt + 1) + t + 1];
+                if (s1 > s0) items.emplace_back((int32_t)(s1 - s0), b);
+            }
+            std::stable_sort(items.begin(), items.end(),
+                             [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first > b.first; });
+            for (size_t i0 = 0; i0 < items.size(); i0 += 32) {
+                int32_t mx = 0;
+                for (int k = 0; k < 32; ++k) {
+                    if (i0 + k < items.size()) {
+                        const int32_t len = items[i0 + k].first, b = items[i0 + k].second;
+                        seg_start.push_back(segstart[(int64_t)b * (nt + 1) + t]);
+                        seg_len.push_back(len); seg_cb.push_back(t * T); rows.push_back(b);
+                        mx = std::max(mx, len);
+                    } else {
+                        seg_start.push_back(0); seg_len.push_back(0); seg_cb.push_back(0); rows.push_back(-1);
+                    }
+                }
+                const int64_t nch = (mx + 3) / 4;
+                slice_chunks.push_back(nch);
+                off.push_back(off.back() + nch * units);
+            }
+            tile_sbegin[t + 1] = (int32_t)slice_chunks.size();
+        }
+        P->nslices2 = (int32_t)slice_chunks.size(); P->units2 = off.back();
+        // tasks: contiguous slice ranges of one tile with ~equal chunk counts
+        P->k2_threads = P->opt.k2_threads > 0 ? P->opt.k2_threads : 256;
+        P->k2_smem = (size_t)T * P->acc_size;
+        int occ = std::max<int>(1, std::min<int>({(int)(P->smem_optin / std::max<size_t>(P->k2_smem + 1024, 1)),
+                                                  2048 / P->k2_threads, 8}));
+        int64_t target = P->opt.k2_tasks > 0 ? P->opt.k2_tasks : std::max<int64_t>((int64_t)P->sm_count * occ, 8LL * nt);
+        const int64_t total_chunks = std::accumulate(slice_chunks.begin(), slice_chunks.end(), (int64_t)0);
+        std::vector<K2Task> tasks;
+        for (int32_t t = 0; t < nt; ++t) {
+            const int32_t sb = tile_sbegin[t], se = tile_sbegin[t + 1];
+            if (se == sb) continue;
+            int64_t w = 0;
+            for (int32_t s = sb; s < se; ++s) w += slice_chunks[s] + 1;
+            int64_t n_t = total_chunks > 0 ? (target * w + total_chunks / 2) / std::max<int64_t>(total_chunks, 1) : 1;
+            n_t = std::max<int64_t>(1, std::min<int64_t>(n_t, se - sb));
+            int32_t cur = sb;
+            int64_t acc = 0;
+            for (int64_t k = 0; k < n_t; ++k) {
+                const int64_t goal = w * (k + 1) / n_t;
+                int32_t end = cur;
+                while (end < se && (acc < goal || end == cur)) { acc += slice_chunks[end] + 1; ++end; }
+                if (k == n_t - 1) end = se;
+                if (end > cur) tasks.push_back(K2Task{t, cur, end, 0});
+                cur = end;
+            }
+        }
+        P->ntasks2 = (int32_t)tasks.size();
+        if (int rc = build_sell(P, P->opt.store_dtype, src_dtype, off, seg_start, seg_len, seg_cb,
+                                d_bcol, d_bval, P->sell2, P->off2)) return rc;
+        if (upload_vec(P->rows2, rows, st)) return VMAT_E_CUDA;
+        if (upload_vec(P->tasks2, tasks, st)) return VMAT_E_CUDA;
+    }
+    up_bcol.alloc(0); up_bval.alloc(0); up_brow.alloc(0);
+
+    // ---- evaluation state -----------------------------------------------------------
+    {
+        std::vector<int32_t> beam_of(B);
+        for (int32_t i = 0; i < nb; ++i)
+            for (int32_t j = beam_ptr[i]; j < beam_ptr[i + 1]; ++j) beam_of[j] = i;
+        if (upload_vec(P->beam_of, beam_of, st)) return VMAT_E_CUDA;
+        if (upload_vec(P->beam_ptr_d, P->beam_ptr, st)) return VMAT_E_CUDA;
+    }
+    const size_t as = P->acc_size;
+    CU(P->y.alloc(nb * 8));            CU(cudaMemset(P->y.p, 0, nb * 8));
+    CU(P->w_dose.alloc(B * as));       CU(cudaMemset(P->w_dose.p, 0, B * as));
+    CU(P->w_grad.alloc(B * 8));        CU(cudaMemset(P->w_grad.p, 0, B * 8));
+    CU(P->xg.alloc(B * as));           CU(cudaMemset(P->xg.p, 0, B * as));
+    CU(P->d.alloc(V * as));            CU(cudaMemset(P->d.p, 0, V * as));
+    CU(P->vg.alloc(V * as));           CU(cudaMemset(P->vg.p, 0, V * as));
+    CU(P->partial.alloc((size_t)P->ntiles * B * as));
+    CU(cudaMemset(P->partial.p, 0, (size_t)P->ntiles * B * as));
+    CU(P->gbf.alloc((B + 1) * 8));     CU(cudaMemset(P->gbf.p, 0, (B + 1) * 8));
+    CU(P->result.alloc((nb + 1) * 8)); CU(cudaMemset(P->result.p, 0, (nb + 1) * 8));
+    CU(P->counter.alloc(64));          CU(cudaMemset(P->counter.p, 0, 64));
+    CU(P->scratch64.alloc(std::max<int64_t>(V, B) * 8));
+    CU(cudaMallocHost(&P->h_y, nb * 8));
+    CU(cudaMallocHost(&P->h_res, (nb + 1) * 8));
+
+    // K1 launch shape: one CTA per SM, x staged once per SM
+    P->k1_smem = (size_t)B * as;
+    P->x_in_smem = P->k1_smem + 2048 <= (size_t)P->smem_optin;
+    if (!P->x_in_smem) P->k1_smem = 0;
+    P->k1_threads = P->opt.k1_threads > 0 ? P->opt.k1_threads : 1024;
+    P->k1_grid = P->sm_count;
+    CU(P->fpart.alloc(P->k1_grid * 8)); CU(cudaMemset(P->fpart.p, 0, P->k1_grid * 8));
+    CU(cudaDeviceSynchronize());
+
+    if (P->opt.use_graph) { if (int rc = capture_graph(P)) return rc; }
+    guard.p = nullptr;
+    *out = P;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_plan_destroy(vmat_plan_t* P) {
+    if (!P) return VMAT_OK;
+    cudaSetDevice(P->device);
+    cudaDeviceSynchronize();
+    delete P;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layout_bytes, int64_t* algo_bytes,
+                              int32_t* launches) {
+    if (!P) return fail(VMAT_E_ARG, "null plan");
+    const int64_t as = (int64_t)P->acc_size, sv = store_bytes(P->opt.store_dtype);
+    if (nnz) *nnz = P->nnz;
+    if (layout_bytes) {
+        // what the three kernels stream: both SELL layouts (padding included), slice metadata,
+        // penalty tables, d/vg writes, vg tile reads, tile partials (write + read), x inputs, gb.
+        int64_t b = (P->units1 + P->units2) * 16;
+        b += (int64_t)P->nslices1 * (8 + 32 * 4) + (int64_t)P->nslices2 * (8 + 32 * 4);
+        b += 3 * P->V * as + 2 * P->V * as + P->V * as;
+        b += 2 * (int64_t)P->ntiles * P->B * as;
+        b += P->B * (as + 4) + P->B * 8 * 2;
+        *layout_bytes = b;
+    }
+    if (algo_bytes) *algo_bytes = 2 * P->nnz * (sv + 4) + 28 * P->V + 12 * P->B;
+    if (launches) *launches = P->x_in_smem ? 3 : 4;
+    return VMAT_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// evaluation
+// ---------------------------------------------------------------------------------
+template <typename VT, typename AT>
+static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
+    constexpr int U = Unroll<VT>::U;
+    cudaEvent_t* ev = nullptr;
+    if (P->timing && phase == 0) {
+        ev = &P->tev[(P->tcount % vmat_plan::kTimingSlots) * 4];
+        P->tcount++;
+        CU(cudaEventRecord(ev[0], st));
+    }
+    if (phase != 2) {
+        if (!P->x_in_smem) {
+            k4_expand_x<AT><<<(unsigned)((P->B + 255) / 256), 256, 0, st>>>(
+                (int32_t)P->B, P->y.as<double>(), P->beam_of.as<int32_t>(), P->w_dose.as<AT>(), P->xg.as<AT>());
+        }
+        K1Args<AT> a1{};
+        a1.sell = P->sell1.as<uint4>(); a1.slice_off = P->off1.as<int64_t>(); a1.slice_rows = P->rows1.as<int32_t>();
+        a1.nslices = P->nslices1; a1.B = (int32_t)P->B; a1.y = P->y.as<double>(); a1.beam_of = P->beam_of.as<int32_t>();
+        a1.w_dose = P->w_dose.as<AT>(); a1.x_global = P->xg.as<AT>();
+        a1.thr_s = P->thr_s.as<AT>(); a1.over_s = P->over_s.as<AT>(); a1.under_s = P->under_s.as<AT>();
+        a1.d = P->d.as<AT>(); a1.vg = P->vg.as<AT>(); a1.fpart = P->fpart.as<double>();
+        a1.counter = P->counter.as<unsigned int>();
+        if (P->x_in_smem) {
+            auto kern = k1_dose_penalty<VT, AT, true, U>;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
+            kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
+        } else {
+            auto kern = k1_dose_penalty<VT, AT, false, U>;
+            kern<<<P->k1_grid, P->k1_threads, 0, st>>>(a1);
+        }
+        if (ev) CU(cudaEventRecord(ev[1], st));
+        K2Args<AT> a2{};
+        a2.sell = P->sell2.as<uint4>(); a2.slice_off = P->off2.as<int64_t>(); a2.slice_rows = P->rows2.as<int32_t>();
+        a2.tasks = P->tasks2.as<K2Task>(); a2.vg = P->vg.as<AT>(); a2.partial = P->partial.as<AT>();
+        a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.k1_counter = P->counter.as<unsigned int>();
+        if (P->ntasks2 > 0) {
+            auto kern2 = k2_beamlet_grad<VT, AT, U>;
+            CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
+            kern2<<<P->ntasks2, P->k2_threads, P->k2_smem, st>>>(a2);
+        } else {
+            CU(cudaMemsetAsync(P->counter.p, 0, 4, st));
+        }
+    }
+    if (ev) CU(cudaEventRecord(ev[2], st));
+    K3Args<AT> a3{};
+    a3.partial = P->partial.as<AT>(); a3.ntiles = P->ntiles; a3.B = (int32_t)P->B; a3.nb = P->nb;
+    a3.beam_ptr = P->beam_ptr_d.as<int32_t>(); a3.w_grad = P->w_grad.as<double>();
+    a3.fpart = P->fpart.as<double>(); a3.nfpart = P->k1_grid; a3.gbf = P->gbf.as<double>();
+    a3.result = P->result.as<double>();
+    k3_reduce<AT><<<P->nb + 1, 256, 0, st>>>(a3, phase);
+    CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev[3], st));
+    return 0;
+}
+
+static int launch_eval(vmat_plan* P, cudaStream_t st, int phase) {
+    DISPATCH_STORE(P->opt.store_dtype, VT, {
+        DISPATCH_ACC(P->opt.acc_dtype, AT, { return launch_eval_t<VT, AT>(P, st, phase); });
+    });
+    return 0;
+}
+
+static int capture_graph(vmat_plan* P) {
+    // warm the kernels (sets the shared-memory attributes outside capture)
+    if (int rc = launch_eval(P, P->stream, 0)) return rc;
+    CU(cudaStreamSynchronize(P->stream));
+    CU(cudaStreamBeginCapture(P->stream, cudaStreamCaptureModeThreadLocal));
+    cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream);
+    int rc = launch_eval(P, P->stream, 0);
+    cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream);
+    cudaError_t e = cudaStreamEndCapture(P->stream, &P->graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(VMAT_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    CU(cudaGraphInstantiate(&P->graph_exec, P->graph, 0));
+    return 0;
+}
+
+extern "C" int vmat_set_aperture(vmat_plan_t* P, int32_t beam, const double* w_dose, const double* w_grad) {
+    if (!P || beam < 0 || beam >= P->nb) return fail(VMAT_E_ARG, "vmat_set_aperture: bad beam");
+    CU(cudaSetDevice(P->device));
+    const int32_t lo = P->beam_ptr[beam], n = P->beam_ptr[beam + 1] - lo;
+    if (n == 0) return VMAT_OK;
+    const size_t as = P->acc_size;
+    CU(cudaStreamSynchronize(P->stream));
+    if (w_dose) {
+        if (as == 4) {
+            std::vector<float> tmp(n);
+            for (int k = 0; k < n; ++k) tmp[k] = (float)w_dose[k];
+            CU(cudaMemcpy(P->w_dose.as<char>() + (size_t)lo * 4, tmp.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        } else {
+            CU(cudaMemcpy(P->w_dose.as<char>() + (size_t)lo * 8, w_dose, (size_t)n * 8, cudaMemcpyHostToDevice));
+        }
+    } else {
+        CU(cudaMemset(P->w_dose.as<char>() + (size_t)lo * as, 0, (size_t)n * as));
+    }
+    if (w_grad) CU(cudaMemcpy(P->w_grad.as<double>() + lo, w_grad, (size_t)n * 8, cudaMemcpyHostToDevice));
+    else CU(cudaMemset(P->w_grad.as<double>() + lo, 0, (size_t)n * 8));
+    return VMAT_OK;
+}
+
+extern "C" int vmat_set_intensities(vmat_plan_t* P, const double* y) {
+    if (!P || !y) return fail(VMAT_E_ARG, "vmat_set_intensities: null");
+    CU(cudaSetDevice(P->device));
+    std::memcpy(P->h_y, y, P->nb * 8);
+    CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    return VMAT_OK;
+}
+
+extern "C" int vmat_eval(vmat_plan_t* P, const double* y, double* f, double* g) {
+    if (!P || !y) return fail(VMAT_E_ARG, "vmat_eval: null");
+    CU(cudaSetDevice(P->device));
+    std::memcpy(P->h_y, y, P->nb * 8);
+    if (P->graph_exec) {
+        CU(cudaGraphLaunch(P->graph_exec, P->stream));
+    } else {
+        CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
+        if (int rc = launch_eval(P, P->stream, 0)) return rc;
+        CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream));
+    }
+    CU(cudaStreamSynchronize(P->stream));
+    P->evaluated = true;
+    if (f) *f = P->h_res[0];
+    if (g) std::memcpy(g, P->h_res + 1, P->nb * 8);
+    return VMAT_OK;
+}
+
+extern "C" int vmat_eval_async(vmat_plan_t* P, void* stream, int phase) {
+    if (!P || phase < 0 || phase > 2) return fail(VMAT_E_ARG, "vmat_eval_async: bad argument");
+    CU(cudaSetDevice(P->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : P->stream;
+    P->evaluated = true;
+    return launch_eval(P, st, phase);
+}
+
+extern "C" int vmat_fetch_result(vmat_plan_t* P, double* f, double* g) {
+    if (!P) return fail(VMAT_E_ARG, "null plan");
+    CU(cudaSetDevice(P->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost));
+    if (f) *f = P->h_res[0];
+    if (g) std::memcpy(g, P->h_res + 1, P->nb * 8);
+    return VMAT_OK;
+}
+
+extern "C" int vmat_sync(vmat_plan_t* P) {
+    if (!P) return fail(VMAT_E_ARG, "null plan");
+    CU(cudaSetDevice(P->device));
+    CU(cudaDeviceSynchronize());
+    return VMAT_OK;
+}
+
+extern "C" int vmat_set_timing(vmat_plan_t* P, int enable) {
+    if (!P) return fail(VMAT_E_ARG, "null plan");
+    CU(cudaSetDevice(P->device));
+    if (enable && P->tev.empty()) {
+        P->tev.resize((size_t)vmat_plan::kTimingSlots * 4);
+        for (auto& e : P->tev) CU(cudaEventCreate(&e));
+    }
+    P->timing = enable != 0;
+    P->tcount = 0;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_get_timing(vmat_plan_t* P, double* ms, int32_t* n) {
+    if (!P || !ms || !n) return fail(VMAT_E_ARG, "null");
+    CU(cudaSetDevice(P->device));
+    CU(cudaDeviceSynchronize());
+    const int64_t cnt = std::min<int64_t>(P->tcount, vmat_plan::kTimingSlots);
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t k = 0; k < cnt; ++k) {
+        cudaEvent_t* ev = &P->tev[k * 4];
+        float t;
+        CU(cudaEventElapsedTime(&t, ev[0], ev[1])); acc[0] += t;
+        CU(cudaEventElapsedTime(&t, ev[1], ev[2])); acc[1] += t;
+        CU(cudaEventElapsedTime(&t, ev[2], ev[3])); acc[2] += t;
+        CU(cudaEventElapsedTime(&t, ev[0], ev[3])); acc[3] += t;
+    }
+    for (int k = 0; k < 4; ++k) ms[k] = cnt ? acc[k] / cnt : 0.0;
+    *n = (int32_t)cnt;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_reduce_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count) {
+    if (!P || !dev_ptr || !count) return fail(VMAT_E_ARG, "null");
+    *dev_ptr = P->gbf.p; *count = P->B + 1;
+    return VMAT_OK;
+}
+
+template <typename AT>
+static int fetch_as_f64(vmat_plan* P, const void* src, int64_t n, double* out) {
+    k_cast_to_f64<AT><<<(unsigned)((n + 255) / 256), 256, 0, P->stream>>>(n, static_cast<const AT*>(src), P->scratch64.as<double>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, P->scratch64.p, n * 8, cudaMemcpyDeviceToHost, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    return 0;
+}
+
+extern "C" int vmat_get_dose(vmat_plan_t* P, double* out) {
+    if (!P || !out) return fail(VMAT_E_ARG, "null");
+    CU(cudaSetDevice(P->device)); CU(cudaDeviceSynchronize());
+    DISPATCH_ACC(P->opt.acc_dtype, AT, { return fetch_as_f64<AT>(P, P->d.p, P->V, out); });
+    return 0;
+}
+extern "C" int vmat_get_voxelgrad(vmat_plan_t* P, double* out) {
+    if (!P || !out) return fail(VMAT_E_ARG, "null");
+    CU(cudaSetDevice(P->device)); CU(cudaDeviceSynchronize());
+    DISPATCH_ACC(P->opt.acc_dtype, AT, { return fetch_as_f64<AT>(P, P->vg.p, P->V, out); });
+    return 0;
+}
+extern "C" int vmat_get_beamlet_grad(vmat_plan_t* P, double* out) {
+    if (!P || !out) return fail(VMAT_E_ARG, "null");
+    CU(cudaSetDevice(P->device)); CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, P->gbf.p, P->B * 8, cudaMemcpyDeviceToHost));
+    return VMAT_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// pricing
+// ---------------------------------------------------------------------------------
+extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_beam,
+                          const vmat_price_params_t* prm, const vmat_price_row_t* rows,
+                          double* p, int32_t* l, int32_t* r) {
+    if (!P || ncand < 0 || (ncand > 0 && (!cand_beam || !prm || !rows || !p || !l || !r)))
+        return fail(VMAT_E_ARG, "vmat_price: null argument");
+    if (ncand == 0) return VMAT_OK;
+    if (!P->evaluated) return fail(VMAT_E_STATE, "vmat_price: no evaluation has produced a beamlet gradient yet");
+    const int32_t M = prm->M, N = prm->N;
+    if (M <= 0 || N <= 0 || N > 62) return fail(VMAT_E_UNSUPPORTED, "vmat_price: need 1 <= N <= 62, M >= 1");
+    for (int32_t c = 0; c < ncand; ++c)
+        if (cand_beam[c] < 0 || cand_beam[c] >= P->nb) return fail(VMAT_E_ARG, "vmat_price: bad candidate");
+    CU(cudaSetDevice(P->device));
+    const int32_t kmax = price_max_nodes(N);
+    const size_t nrow = (size_t)ncand * M;
+    if ((size_t)ncand > P->price_cap_cand || nrow * kmax > P->price_cap_dad) {
+        CU(P->price_cand.alloc(ncand * 4)); CU(P->price_p.alloc(ncand * 8));
+        CU(P->price_rows.alloc(nrow * sizeof(vmat_price_row_t)));
+        CU(P->price_l.alloc(nrow * 4)); CU(P->price_r.alloc(nrow * 4));
+        CU(P->price_dad.alloc(nrow * kmax * sizeof(int32_t) * 3));
+        P->price_cap_cand = ncand; P->price_cap_dad = nrow * kmax;
+    }
+    cudaStream_t st = P->stream;
+    CU(cudaMemcpyAsync(P->price_cand.p, cand_beam, ncand * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(P->price_rows.p, rows, nrow * sizeof(vmat_price_row_t), cudaMemcpyHostToDevice, st));
+    PriceArgs a{};
+    a.gb = P->gbf.as<double>(); a.beam_ptr = P->beam_ptr_d.as<int32_t>(); a.cand = P->price_cand.as<int32_t>();
+    a.rows = P->price_rows.as<vmat_price_row_t>(); a.C = prm->C; a.C2 = prm->C2; a.C3 = prm->C3; a.b = prm->b;
+    a.M = M; a.N = N; a.kmax = kmax; a.p = P->price_p.as<double>(); a.l = P->price_l.as<int32_t>();
+    a.r = P->price_r.as<int32_t>(); a.scratch = P->price_dad.as<int32_t>();
+    const size_t smem = price_smem_bytes(kmax);
+    if (smem > (size_t)P->smem_optin) return fail(VMAT_E_UNSUPPORTED, "vmat_price: N too large for shared memory");
+    CU(cudaFuncSetAttribute(k5_price_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_price_dp<<<ncand, kPriceThreads, smem, st>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(p, P->price_p.p, ncand * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(l, P->price_l.p, nrow * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(r, P->price_r.p, nrow * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return VMAT_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// k-medoid insertion costs
+// ---------------------------------------------------------------------------------
+extern "C" int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
+                                  const double* curmin, double* cost) {
+    if (n <= 0 || dim <= 0 || dim > 8 || !points || !curmin || !cost) return fail(VMAT_E_ARG, "vmat_kmedoid_costs: bad argument");
+    CU(cudaSetDevice(device));
+    DevBuf dp, dm, dc;
+    CU(dp.alloc(n * dim * 8)); CU(dm.alloc(n * 8)); CU(dc.alloc(n * 8));
+    CU(cudaMemcpy(dp.p, points, n * dim * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dm.p, curmin, n * 8, cudaMemcpyHostToDevice));
+    k6_kmedoid_cost<<<(unsigned)n, kKmThreads>>>(n, dim, dp.as<double>(), dm.as<double>(), dc.as<double>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(cost, dc.p, n * 8, cudaMemcpyDeviceToHost));
+    return VMAT_OK;
+}

@@ -1,0 +1,60 @@
+// K6: k-medoid insertion costs (kmedoids.py:32-60).  For every candidate point c:
+//   cost[c] = sum_j min(curmin[j], ||p_c - p_j||_2)
+// where curmin[j] is the distance from point j to its nearest already-chosen medoid.
+// This is distancemin(kappa + [c], ba) of the reference without rebuilding the full
+// pairwise distance matrix for every candidate.
+//
+// One CTA per candidate.  Up to kKmSequentialMax points the sum runs strictly left to right
+// in one thread per candidate (the reference's builtin ``sum`` order, bit-exact); beyond that
+// a fixed-shape tree (deterministic; exact whenever the distances are integers).
+#pragma once
+#include "vmat_common.cuh"
+
+namespace vmat {
+
+constexpr int kKmThreads = 256;
+constexpr int64_t kKmSequentialMax = 4096;
+
+__device__ __forceinline__ double km_dist(const double* __restrict__ P, int dim, int64_t c, int64_t j) {
+    double s = 0.0;
+    for (int d = 0; d < dim; ++d) {
+        const double df = __dsub_rn(P[c * dim + d], P[j * dim + d]);
+        s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    return __dsqrt_rn(s);
+}
+
+__global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost(int64_t n, int dim, const double* __restrict__ P,
+                                                             const double* __restrict__ curmin,
+                                                             double* __restrict__ cost) {
+    __shared__ double sh[kKmThreads];
+    const int64_t c = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (n <= kKmSequentialMax) {
+        // distances in parallel into shared memory, then one thread adds them in index order
+        double total = 0.0;
+        for (int64_t j0 = 0; j0 < n; j0 += kKmThreads) {
+            const int64_t j = j0 + tid;
+            sh[tid] = (j < n) ? fmin(curmin[j], km_dist(P, dim, c, j)) : 0.0;
+            __syncthreads();
+            if (tid == 0) {
+                const int lim = (int)min((int64_t)kKmThreads, n - j0);
+                for (int k = 0; k < lim; ++k) total = __dadd_rn(total, sh[k]);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) cost[c] = total;
+        return;
+    }
+    double v = 0.0;
+    for (int64_t j = tid; j < n; j += kKmThreads) v += fmin(curmin[j], km_dist(P, dim, c, j));
+    sh[tid] = v;
+    __syncthreads();
+    for (int o = kKmThreads / 2; o > 0; o >>= 1) {
+        if (tid < o) sh[tid] += sh[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) cost[c] = sh[0];
+}
+
+}  // namespace vmat

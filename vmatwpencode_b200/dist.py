@@ -1,0 +1,64 @@
+"""Voxel-slab sharding of one planning case across the GPUs of a node.
+
+D is partitioned by voxel rows into contiguous slabs balanced by nonzeros; rank k owns the
+slab's rows of D (in both layouts), its slice of the penalty tables, and computes a partial
+beamlet gradient and objective.  One exchange per evaluation: a sum all-reduce of the
+[gb | f] buffer (B+1 doubles) over NCCL; the aperture gradient is then formed redundantly on
+every rank.  The reference has no multi-device path (its only parallelism is a
+process pool over pricing candidates, greedyVMATsampling.py:836-841).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def partition_voxels(indptr, nparts: int):
+    """Slab boundaries [v_0=0, ..., v_nparts=V] with ~equal nonzeros per slab, multiples of 32
+    (so slabs keep whole slices) except the last."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    V = len(indptr) - 1
+    nnz = int(indptr[-1])
+    bounds = [0]
+    for k in range(1, nparts):
+        target = nnz * k // nparts
+        v = int(np.searchsorted(indptr, target, side="left"))
+        v = min(V, max(bounds[-1], (v + 16) // 32 * 32))
+        bounds.append(v)
+    bounds.append(V)
+    return bounds
+
+
+def slab_of(case, rank: int, world: int):
+    """(rows slice, D slab CSR, thr, over, under) of `rank`."""
+    D = case.D.tocsr()
+    b = partition_voxels(D.indptr, world)
+    lo, hi = b[rank], b[rank + 1]
+    return slice(lo, hi), D[lo:hi], case.thr[lo:hi], case.over[lo:hi], case.under[lo:hi]
+
+
+class ShardedEvaluator:
+    """calcObjGrad over a voxel-sharded D.  `engine` is this rank's slab evaluator with the
+    DosePlan interface (set_weights / set_intensities / eval_async(stream, phase) /
+    reduce_buffer / fetch_result); `group` a torch.distributed process group (NCCL on GPUs;
+    gloo with a host engine in the CPU tests)."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        self.engine = engine
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def eval_async(self, stream=None):
+        if self.world == 1:
+            self.engine.eval_async(stream, 0)
+            return
+        self.engine.eval_async(stream, 1)                 # local dose, penalty, partial [gb | f]
+        buf = self.engine.reduce_buffer()
+        self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.engine.eval_async(stream, 2)                 # aperture gradient from the summed gb
+
+    def eval(self, y, stream=None):
+        self.engine.set_intensities(y)
+        self.eval_async(stream)
+        return self.engine.fetch_result()

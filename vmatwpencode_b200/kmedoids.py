@@ -1,0 +1,69 @@
+"""Greedy k-medoid ordering (kmedoids.py:32-68 of the reference) with the distance pass on
+the GPU.  Same three functions; `ba` may be the reference's 1-D list of beam-angle positions
+or an (n, d) array of coordinates (the voxel-sampling use of BASELINE.json's north star).
+
+The reference rebuilds the full pairwise distance matrix for every candidate (O(n^4) for a
+whole ordering); here one kernel launch prices all candidates of an insertion step against
+the running nearest-medoid distance.  Sums run in the reference's left-to-right order for
+n <= 4096 points, so results are bit-identical there.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .plan import kmedoid_costs
+
+
+def _points(ba) -> np.ndarray:
+    P = np.asarray(ba, dtype=np.float64)
+    if P.ndim == 1:          # the reference embeds 1-D positions as [0, z]  (kmedoids.py:33-34)
+        P = np.stack([np.zeros_like(P), P], axis=1)
+    return np.ascontiguousarray(P)
+
+
+def _nearest(P: np.ndarray, kappa) -> np.ndarray:
+    """Distance of every point to its nearest medoid (column minimum of D[kappa, :], :38-41)."""
+    cur = np.full(P.shape[0], np.inf)
+    for k in kappa:
+        diff = P - P[k]
+        cur = np.minimum(cur, np.sqrt((diff * diff).sum(axis=1)))
+    return cur
+
+
+def distancemin(kappa, ba, device: int = 0):
+    """Sum over all points of the distance to the nearest medoid (kmedoids.py:32-42)."""
+    P = _points(ba)
+    *head, last = list(kappa)
+    cost = kmedoid_costs(P, _nearest(P, head), device)
+    return cost[last]
+
+
+def listdiff(a, b):
+    b = set(b)
+    return [aa for aa in a if aa not in b]
+
+
+def insertnewelement(kappa, ba, device: int = 0, _state=None):
+    """Append the candidate that minimises distancemin; the first best wins (kmedoids.py:48-60)."""
+    P = _points(ba) if _state is None else _state["P"]
+    cur = _nearest(P, kappa) if _state is None else _state["cur"]
+    cost = kmedoid_costs(P, cur, device)
+    taken = np.zeros(P.shape[0], dtype=bool)
+    taken[list(kappa)] = True
+    cost = np.where(taken, np.inf, cost)
+    best = int(np.argmin(cost))          # first minimum == strict "<" scan in candidate order
+    kappa.append(best)
+    if _state is not None:
+        diff = P - P[best]
+        _state["cur"] = np.minimum(cur, np.sqrt((diff * diff).sum(axis=1)))
+    return kappa
+
+
+def givemewholelist(kappa, ba, device: int = 0):
+    """Order all points by greedy k-medoid insertion (kmedoids.py:62-68)."""
+    kappa = list(kappa)
+    P = _points(ba)
+    state = {"P": P, "cur": _nearest(P, kappa)}
+    while len(kappa) < P.shape[0]:
+        kappa = insertnewelement(kappa, ba, device, state)
+    return kappa

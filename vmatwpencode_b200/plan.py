@@ -1,0 +1,204 @@
+"""DosePlan: host-side handle on one GPU's copy of the dose-deposition matrix.
+
+Thin Python over the C ABI (include/vmat_b200.h).  It replaces what the reference
+keeps in ``data.Dlist`` / ``DlistT`` / ``quadHelper*`` (greedyVMATsampling.py:482-483,
+524-525,564-576) and what ``calcDose`` / ``calcGradientandObjValue`` / ``PPsubroutine``
+compute with scipy.sparse (:243-272,646): one D (V x B) resident in HBM in two
+kernel-friendly layouts, and the evaluation  y -> (f, g)  as three CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Options, PriceParams, PriceRow, VmatError, check
+
+
+def _ptr(a) -> C.c_void_p:
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())          # torch tensor
+
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view a library-owned buffer."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+class DosePlan:
+    """One rank's plan: D (its voxel slab) x all beamlets, penalty tables, aperture weights."""
+
+    def __init__(self, D, beam_ptr, thr, over, under, device: int = 0, store: str = "f32",
+                 acc: str = "f32", tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0,
+                 k2_tasks: int = 0, use_graph: bool = True, Dt=None):
+        """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
+        {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
+        lib = _lib.load()
+        self._lib = lib
+        self._h = C.c_void_p(0)
+        beam_ptr = np.ascontiguousarray(beam_ptr, dtype=np.int32)
+        self.nb = len(beam_ptr) - 1
+        self.beam_ptr = beam_ptr
+        self.B = int(beam_ptr[-1])
+        opt = Options()
+        lib.vmat_default_options(C.byref(opt))
+        opt.store_dtype = _lib.DTYPE_CODES[store]
+        opt.acc_dtype = _lib.DTYPE_CODES[acc]
+        opt.tile_voxels, opt.k1_threads, opt.k2_threads, opt.k2_tasks = tile_voxels, k1_threads, k2_threads, k2_tasks
+        opt.use_graph = 1 if use_graph else 0
+        self.store, self.acc = store, acc
+        thr = np.ascontiguousarray(thr, dtype=np.float64)
+        over = np.ascontiguousarray(over, dtype=np.float64)
+        under = np.ascontiguousarray(under, dtype=np.float64)
+        if isinstance(D, dict):
+            keep = [D[k] for k in ("vrowptr", "vcol", "vval", "browptr", "bcol", "bval")]
+            self.V = int(keep[0].numel()) - 1
+            src = _lib.VMAT_F64 if str(keep[2].dtype).endswith("float64") else _lib.VMAT_F32
+            loc = _lib.VMAT_DEVICE
+        else:
+            import scipy.sparse as sp
+            Dr = sp.csr_matrix(D)
+            Dr.sort_indices()
+            Dc = Dt if Dt is not None else Dr.tocsc()
+            Dc.sort_indices()
+            self.V = Dr.shape[0]
+            if Dr.shape[1] != self.B:
+                raise VmatError(f"D has {Dr.shape[1]} columns but beam_ptr ends at {self.B}")
+            vt = np.float64 if store == "f64" else np.float32
+            keep = [np.ascontiguousarray(Dr.indptr, dtype=np.int64), np.ascontiguousarray(Dr.indices, dtype=np.int32),
+                    np.ascontiguousarray(Dr.data, dtype=vt),
+                    np.ascontiguousarray(Dc.indptr, dtype=np.int64), np.ascontiguousarray(Dc.indices, dtype=np.int32),
+                    np.ascontiguousarray(Dc.data, dtype=vt)]
+            src = _lib.VMAT_F64 if vt is np.float64 else _lib.VMAT_F32
+            loc = _lib.VMAT_HOST
+        if len(thr) != self.V:
+            raise VmatError("penalty tables must have one entry per voxel")
+        self.device = device
+        check(lib.vmat_plan_create(C.byref(self._h), device, self.V, self.B, self.nb, _ptr(beam_ptr),
+                                   *[_ptr(k) for k in keep], src, loc, _ptr(thr), _ptr(over), _ptr(under),
+                                   C.byref(opt)), "vmat_plan_create")
+        del keep
+        self._y = np.zeros(self.nb)
+        self._g = np.zeros(self.nb)
+
+    # -- lifecycle ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.vmat_plan_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        nnz, lay, alg, nl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        check(self._lib.vmat_plan_info(self._h, C.byref(nnz), C.byref(lay), C.byref(alg), C.byref(nl)), "vmat_plan_info")
+        return dict(nnz=nnz.value, layout_bytes_per_eval=lay.value, algorithmic_bytes_per_eval=alg.value,
+                    launches_per_eval=nl.value, V=self.V, B=self.B, nb=self.nb, store=self.store, acc=self.acc)
+
+    # -- aperture weights -----------------------------------------------------------
+    def set_aperture(self, beam: int, w_dose, w_grad):
+        """w_dose / w_grad: f64[B_beam] (strengths scattered over the open map / diagmaker)."""
+        n = int(self.beam_ptr[beam + 1] - self.beam_ptr[beam])
+        wd = None if w_dose is None else np.ascontiguousarray(w_dose, dtype=np.float64)
+        wg = None if w_grad is None else np.ascontiguousarray(w_grad, dtype=np.float64)
+        for w in (wd, wg):
+            if w is not None and len(w) != n:
+                raise VmatError(f"beam {beam} has {n} beamlets, got a weight vector of {len(w)}")
+        check(self._lib.vmat_set_aperture(self._h, beam, _ptr(wd), _ptr(wg)), "vmat_set_aperture")
+
+    def set_weights(self, w_dose, w_grad):
+        """All control points at once from global f64[B] vectors."""
+        for i in range(self.nb):
+            lo, hi = int(self.beam_ptr[i]), int(self.beam_ptr[i + 1])
+            self.set_aperture(i, w_dose[lo:hi], w_grad[lo:hi])
+
+    # -- evaluation -----------------------------------------------------------------
+    def eval(self, y):
+        """(f, g[nb]) for intensities y[nb]: host buffers in, host buffers out."""
+        self._y[:] = y
+        f = C.c_double()
+        check(self._lib.vmat_eval(self._h, _ptr(self._y), C.byref(f), _ptr(self._g)), "vmat_eval")
+        return f.value, self._g.copy()
+
+    def set_intensities(self, y):
+        self._y[:] = y
+        check(self._lib.vmat_set_intensities(self._h, _ptr(self._y)), "vmat_set_intensities")
+
+    def eval_async(self, stream: Optional[int] = None, phase: int = 0):
+        check(self._lib.vmat_eval_async(self._h, C.c_void_p(stream or 0), phase), "vmat_eval_async")
+
+    def fetch_result(self):
+        f = C.c_double()
+        check(self._lib.vmat_fetch_result(self._h, C.byref(f), _ptr(self._g)), "vmat_fetch_result")
+        return f.value, self._g.copy()
+
+    def sync(self):
+        check(self._lib.vmat_sync(self._h), "vmat_sync")
+
+    def set_timing(self, enable: bool = True):
+        check(self._lib.vmat_set_timing(self._h, 1 if enable else 0), "vmat_set_timing")
+
+    def get_timing(self) -> dict:
+        """Mean per-kernel milliseconds of the evaluations launched since set_timing(True)."""
+        ms = np.zeros(4)
+        n = C.c_int32()
+        check(self._lib.vmat_get_timing(self._h, _ptr(ms), C.byref(n)), "vmat_get_timing")
+        return dict(k1_ms=ms[0], k2_ms=ms[1], k3_ms=ms[2], eval_ms=ms[3], n=n.value)
+
+    def reduce_buffer(self):
+        """torch view (float64, B+1: gb then f) of the buffer to all-reduce between phases 1 and 2."""
+        import torch
+        p, n = C.c_void_p(), C.c_int64()
+        check(self._lib.vmat_reduce_buffer(self._h, C.byref(p), C.byref(n)), "vmat_reduce_buffer")
+        return torch.as_tensor(_DeviceArray(p.value, n.value), device=f"cuda:{self.device}")
+
+    def dose(self) -> np.ndarray:
+        out = np.empty(self.V)
+        check(self._lib.vmat_get_dose(self._h, _ptr(out)), "vmat_get_dose")
+        return out
+
+    def voxelgrad(self) -> np.ndarray:
+        out = np.empty(self.V)
+        check(self._lib.vmat_get_voxelgrad(self._h, _ptr(out)), "vmat_get_voxelgrad")
+        return out
+
+    def beamlet_grad(self) -> np.ndarray:
+        out = np.empty(self.B)
+        check(self._lib.vmat_get_beamlet_grad(self._h, _ptr(out)), "vmat_get_beamlet_grad")
+        return out
+
+    # -- pricing --------------------------------------------------------------------
+    def price(self, cands: Sequence[int], params: PriceParams, rows):
+        """Batched PPsubroutine: `rows` is a ctypes array of PriceRow, len(cands)*M."""
+        n = len(cands)
+        cand = np.ascontiguousarray(cands, dtype=np.int32)
+        p = np.empty(n)
+        l = np.empty((n, params.M), dtype=np.int32)
+        r = np.empty((n, params.M), dtype=np.int32)
+        check(self._lib.vmat_price(self._h, n, _ptr(cand), C.byref(params), rows, _ptr(p), _ptr(l), _ptr(r)),
+              "vmat_price")
+        return p, l, r
+
+
+def kmedoid_costs(points, curmin, device: int = 0) -> np.ndarray:
+    """cost[c] = sum_j min(curmin[j], dist(c, j))  (kmedoids.py:32-60) on the GPU."""
+    P = np.ascontiguousarray(points, dtype=np.float64)
+    if P.ndim == 1:
+        P = P.reshape(-1, 1)
+    cm = np.ascontiguousarray(curmin, dtype=np.float64)
+    out = np.empty(P.shape[0])
+    lib = _lib.load()
+    check(lib.vmat_kmedoid_costs(device, P.shape[0], P.shape[1], _ptr(P), _ptr(cm), _ptr(out)), "vmat_kmedoid_costs")
+    return out

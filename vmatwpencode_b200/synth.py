@@ -315,3 +315,28 @@ def make_config(name: str, scale: float = 1.0, **overrides) -> Case:
     cfg.update(overrides)
     cfg["V"] = max(64, int(cfg["V"] * scale))
     return make_case(**cfg)
+
+
+def case_to_arrays(case: Case, prefix: str = "case_") -> dict:
+    """Flatten a Case into plain arrays (for .npz fixtures)."""
+    D = case.D.tocsr()
+    out = dict(V=case.V, nb=case.nb, M=case.M, N=case.N, beam_ptr=case.beam_ptr,
+               angles=np.asarray(case.angles), xinter=case.xinter, yinter=case.yinter,
+               xdir=np.concatenate(case.xdirection), ydir=np.concatenate(case.ydirection),
+               indptr=D.indptr.astype(np.int64), indices=D.indices.astype(np.int32), data=D.data,
+               thr=case.thr, over=case.over, under=case.under, struct_id=case.struct_id)
+    return {prefix + k: np.asarray(v) for k, v in out.items()}
+
+
+def case_from_arrays(z, prefix: str = "case_") -> Case:
+    g = lambda k: z[prefix + k]
+    V, nb, M, N = int(g("V")), int(g("nb")), int(g("M")), int(g("N"))
+    beam_ptr = np.asarray(g("beam_ptr"), dtype=np.int32)
+    xdir, ydir = g("xdir"), g("ydir")
+    xd = [np.array(xdir[beam_ptr[i]:beam_ptr[i + 1]]) for i in range(nb)]
+    yd = [np.array(ydir[beam_ptr[i]:beam_ptr[i + 1]]) for i in range(nb)]
+    D = sp.csr_matrix((g("data"), g("indices"), g("indptr")), shape=(V, int(beam_ptr[-1])))
+    return Case(V=V, nb=nb, M=M, N=N, beam_ptr=beam_ptr, angles=[int(a) for a in g("angles")],
+                xinter=np.array(g("xinter")), yinter=np.array(g("yinter")), xdirection=xd, ydirection=yd,
+                D=D, thr=np.array(g("thr")), over=np.array(g("over")), under=np.array(g("under")),
+                struct_id=np.array(g("struct_id")))
