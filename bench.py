@@ -48,7 +48,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)],
+                                          "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -165,7 +165,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="cfg2")
@@ -205,7 +205,12 @@ def main():
     plan.set_weights(w_dose, w_grad)
     info = plan.info()
     ev = ShardedEvaluator(plan)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a side stream: the library treats stream 0 as "use the plan's own stream", and the CUDA
+    # events below must sit on the stream the kernels are launched on
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
+    assert stream != 0
     plan.set_intensities(y)
 
     def barrier():
@@ -214,12 +219,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident throughput (`value`): y already in HBM, results left in HBM ----------
-    for _ in range(W):
-        ev.eval_async(stream)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        ev.eval_async(stream)
+    barrier()
     plan.set_timing(world == 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -231,7 +236,6 @@ def main():
     ms = e0.elapsed_time(e1)
     kt = plan.get_timing() if world == 1 else None
     plan.set_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -253,6 +257,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         peak, peak_src = measured_peaks()
         value = K / (ms * 1e-3)

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Tuning sweep: build the bench workload once, then time plan variants with the library's
+per-kernel CUDA events.  Prints one line per variant (ms per kernel, GB/s per kernel)."""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+
+from bench import workload
+from vmatwpencode_b200.plan import DosePlan
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--variants", default="")
+    args = ap.parse_args()
+    case, y, w_dose, w_grad = workload(args.workload, args.scale)
+    Dt = case.D.tocsc()
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    variants = json.loads(args.variants) if args.variants else [
+        dict(), dict(k1_threads=512), dict(tile_voxels=8192), dict(tile_voxels=32768, k2_threads=512),
+        dict(tile_voxels=8192, k2_threads=128), dict(k2_threads=512), dict(k2_tasks=444), dict(k2_tasks=888),
+        dict(k2_tasks=1776), dict(store="bf16"), dict(acc="f64"),
+    ]
+    for v in variants:
+        v = dict(v)
+        store = v.pop("store", "f32"); acc = v.pop("acc", "f32")
+        plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store=store, acc=acc, Dt=Dt, **v)
+        plan.set_weights(w_dose, w_grad)
+        plan.set_intensities(y)
+        info = plan.info()
+        for _ in range(20):
+            plan.eval_async(side.cuda_stream)
+        torch.cuda.synchronize()
+        plan.set_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            plan.eval_async(side.cuda_stream)
+        e1.record()
+        torch.cuda.synchronize()
+        t = plan.get_timing()
+        ms = e0.elapsed_time(e1) / args.steps
+        sv = {"f32": 4, "bf16": 2, "f64": 8}[store]
+        kb = info["nnz"] * (sv + 4) / 1e9
+        print(json.dumps(dict(variant=dict(v, store=store, acc=acc), step_ms=round(ms, 5),
+                              k1_ms=round(t["k1_ms"], 5), k2_ms=round(t["k2_ms"], 5), k3_ms=round(t["k3_ms"], 5),
+                              k1_GBps=round(kb / t["k1_ms"] * 1e3, 1), k2_GBps=round(kb / t["k2_ms"] * 1e3, 1),
+                              eval_GBps=round(info["algorithmic_bytes_per_eval"] / ms / 1e6, 1),
+                              layout_MB=round(info["layout_bytes_per_eval"] / 1e6, 1))), flush=True)
+        plan.close()
+
+
+if __name__ == "__main__":
+    main()

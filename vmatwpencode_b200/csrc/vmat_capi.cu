@@ -390,7 +390,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     if (!P->x_in_smem) P->k1_smem = 0;
     P->k1_threads = P->opt.k1_threads > 0 ? P->opt.k1_threads : 1024;
     P->k1_grid = P->sm_count;
-    CU(P->fpart.alloc(P->k1_grid * 8)); CU(cudaMemset(P->fpart.p, 0, P->k1_grid * 8));
+    CU(P->fpart.alloc((size_t)P->nslices1 * 8)); CU(cudaMemset(P->fpart.p, 0, (size_t)P->nslices1 * 8));
     CU(cudaDeviceSynchronize());
 
     if (P->opt.use_graph) { if (int rc = capture_graph(P)) return rc; }
@@ -476,7 +476,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
     K3Args<AT> a3{};
     a3.partial = P->partial.as<AT>(); a3.ntiles = P->ntiles; a3.B = (int32_t)P->B; a3.nb = P->nb;
     a3.beam_ptr = P->beam_ptr_d.as<int32_t>(); a3.w_grad = P->w_grad.as<double>();
-    a3.fpart = P->fpart.as<double>(); a3.nfpart = P->k1_grid; a3.gbf = P->gbf.as<double>();
+    a3.fpart = P->fpart.as<double>(); a3.nfpart = P->nslices1; a3.gbf = P->gbf.as<double>();
     a3.result = P->result.as<double>();
     k3_reduce<AT><<<P->nb + 1, 256, 0, st>>>(a3, phase);
     CU(cudaGetLastError());

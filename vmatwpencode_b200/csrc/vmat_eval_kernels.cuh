@@ -88,7 +88,7 @@ struct K1Args {
     const AT* under_s;
     AT* d;                        // [V] dose, natural voxel order
     AT* vg;                       // [V] voxel gradient
-    double* fpart;                // [gridDim.x] objective partials
+    double* fpart;                // [nslices] objective partial of every slice (fixed order -> deterministic)
     unsigned int* counter;        // dynamic slice scheduler
 };
 
@@ -96,16 +96,14 @@ template <typename VT, typename AT, bool XS, int U>
 __global__ void __launch_bounds__(1024, 1) k1_dose_penalty(const K1Args<AT> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AT* xs = reinterpret_cast<AT*>(smem_raw);
-    __shared__ double red[32];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (XS) {   // x_j = y[beam(j)] * w_dose[j]   (K4 folded into the prologue)
         for (int j = tid; j < a.B; j += blockDim.x) xs[j] = mul_rn((AT)a.y[a.beam_of[j]], a.w_dose[j]);
         __syncthreads();
     }
     auto gather = [&](uint32_t j) -> AT { return XS ? xs[j] : __ldg(a.x_global + j); };
 
-    double fsum = 0.0;
     // dynamic scheduling, longest slices first; the next slice id is fetched one slice ahead
     unsigned int s = 0, s_next = 0;
     if (lane == 0) s = atomicAdd(a.counter, 1u);
@@ -118,27 +116,22 @@ __global__ void __launch_bounds__(1024, 1) k1_dose_penalty(const K1Args<AT> a) {
         const int32_t row = a.slice_rows[slot];
         const AT t = a.thr_s[slot], ov = a.over_s[slot], un = a.under_s[slot];
         const AT dose = sell_row_dot<VT, AT, U>(a.sell + off, nch, lane, gather);
+        double fterm = 0.0;
         if (row >= 0) {
             // (d-t)+ and (t-d)+, objective term, vg = 2*(2*o*over - 2*u*under)  (:255-271)
             AT o = sub_rn(dose, t);  o = o > (AT)0 ? o : (AT)0;
             AT u = sub_rn(t, dose);  u = u > (AT)0 ? u : (AT)0;
             const AT fo = mul_rn(mul_rn(o, o), ov);
             const AT fu = mul_rn(mul_rn(u, u), un);
-            fsum += (double)add_rn(fo, fu);
+            fterm = (double)add_rn(fo, fu);
             const AT go = mul_rn(mul_rn((AT)2, o), ov);
             const AT gu = mul_rn(mul_rn((AT)2, u), un);
             a.d[row] = dose;
             a.vg[row] = mul_rn((AT)2, sub_rn(go, gu));
         }
+        fterm = warp_sum(fterm);      // butterfly: same value and order in every lane, every run
+        if (lane == 0) a.fpart[s] = fterm;
         s = __shfl_sync(0xffffffffu, s_next, 0);
-    }
-    fsum = warp_sum(fsum);
-    if (lane == 0) red[warp] = fsum;
-    __syncthreads();
-    if (warp == 0) {
-        double v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
-        v = warp_sum(v);
-        if (lane == 0) a.fpart[blockIdx.x] = v;
     }
 }
 
