@@ -54,7 +54,8 @@ struct vmat_plan {
     int32_t nslices1 = 0;
     int64_t units1 = 0;
     // K2 layout
-    DevBuf sell2, off2, rows2, tasks2;
+    DevBuf sell2, off2, rows2, tasks2, cta_ptr2;
+    int k2_grid = 1;
     int32_t nslices2 = 0, ntasks2 = 0, ntiles = 0, T = 0;
     int64_t units2 = 0;
     // state
@@ -170,6 +171,21 @@ static int build_sell(vmat_plan* P, int store_dtype, int src_dtype,
     return 0;
 }
 
+template <typename VT, typename AT>
+static int k2_occupancy_t(vmat_plan* P, int* occ) {
+    auto kern = k2_beamlet_grad<VT, AT, Unroll<VT>::U>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, P->k2_threads, P->k2_smem));
+    if (*occ < 1) return fail(VMAT_E_ARG, "transposed kernel does not fit on an SM with these options");
+    return 0;
+}
+static int k2_occupancy(vmat_plan* P, int* occ) {
+    DISPATCH_STORE(P->opt.store_dtype, VT, {
+        DISPATCH_ACC(P->opt.acc_dtype, AT, { return k2_occupancy_t<VT, AT>(P, occ); });
+    });
+    return 0;
+}
+
 static int capture_graph(vmat_plan* P);
 static int launch_eval(vmat_plan* P, cudaStream_t st, int phase);
 
@@ -278,7 +294,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
     // ---- K2 layout: column tiles of T voxels; per tile, beamlet segments sorted by length
     {
-        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : (P->opt.acc_dtype == VMAT_F64 ? 8192 : 16384);
+        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : (P->opt.acc_dtype == VMAT_F64 ? 4096 : 8192);
         T = (T + 63) / 64 * 64;
         if ((size_t)T * P->acc_size > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
         const int32_t nt = (int32_t)((V + T - 1) / T);
@@ -326,32 +342,44 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             tile_sbegin[t + 1] = (int32_t)slice_chunks.size();
         }
         P->nslices2 = (int32_t)slice_chunks.size(); P->units2 = off.back();
-        // tasks: contiguous slice ranges of one tile with ~equal chunk counts
-        P->k2_threads = P->opt.k2_threads > 0 ? P->opt.k2_threads : 256;
+        // Persistent CTAs: the (tile, length)-ordered slice sequence is cut into G pieces of equal
+        // work (chunks + a per-slice constant); a piece that crosses a tile boundary becomes two
+        // tasks of the same CTA.
+        P->k2_threads = P->opt.k2_threads > 0 ? P->opt.k2_threads : 128;
         P->k2_smem = (size_t)T * P->acc_size;
-        int occ = std::max<int>(1, std::min<int>({(int)(P->smem_optin / std::max<size_t>(P->k2_smem + 1024, 1)),
-                                                  2048 / P->k2_threads, 8}));
-        int64_t target = P->opt.k2_tasks > 0 ? P->opt.k2_tasks : std::max<int64_t>((int64_t)P->sm_count * occ, 8LL * nt);
-        const int64_t total_chunks = std::accumulate(slice_chunks.begin(), slice_chunks.end(), (int64_t)0);
+        int occ = 1;
+        if (int rc = k2_occupancy(P, &occ)) return rc;
+        const int64_t G = P->opt.k2_tasks > 0 ? P->opt.k2_tasks : (int64_t)P->sm_count * occ;
+        P->k2_grid = (int)std::max<int64_t>(1, std::min<int64_t>(G, std::max<int64_t>(1, (int64_t)slice_chunks.size())));
+        std::vector<int32_t> slice_tile(slice_chunks.size());
+        for (int32_t t = 0; t < nt; ++t)
+            for (int32_t s = tile_sbegin[t]; s < tile_sbegin[t + 1]; ++s) slice_tile[s] = t;
+        int64_t total_w = 0;
+        for (int64_t c : slice_chunks) total_w += c + 1;
         std::vector<K2Task> tasks;
-        for (int32_t t = 0; t < nt; ++t) {
-            const int32_t sb = tile_sbegin[t], se = tile_sbegin[t + 1];
-            if (se == sb) continue;
-            int64_t w = 0;
-            for (int32_t s = sb; s < se; ++s) w += slice_chunks[s] + 1;
-            int64_t n_t = total_chunks > 0 ? (target * w + total_chunks / 2) / std::max<int64_t>(total_chunks, 1) : 1;
-            n_t = std::max<int64_t>(1, std::min<int64_t>(n_t, se - sb));
-            int32_t cur = sb;
+        std::vector<int32_t> cta_ptr(P->k2_grid + 1, 0);
+        {
+            int32_t cur = 0;
             int64_t acc = 0;
-            for (int64_t k = 0; k < n_t; ++k) {
-                const int64_t goal = w * (k + 1) / n_t;
+            const int32_t nsl = (int32_t)slice_chunks.size();
+            for (int c = 0; c < P->k2_grid; ++c) {
+                cta_ptr[c] = (int32_t)tasks.size();
+                const int64_t goal = total_w * (c + 1) / P->k2_grid;
                 int32_t end = cur;
-                while (end < se && (acc < goal || end == cur)) { acc += slice_chunks[end] + 1; ++end; }
-                if (k == n_t - 1) end = se;
-                if (end > cur) tasks.push_back(K2Task{t, cur, end, 0});
+                while (end < nsl && acc < goal) { acc += slice_chunks[end] + 1; ++end; }
+                if (c == P->k2_grid - 1) end = nsl;
+                int32_t b0 = cur;
+                while (b0 < end) {              // split at tile boundaries
+                    int32_t b1 = b0;
+                    while (b1 < end && slice_tile[b1] == slice_tile[b0]) ++b1;
+                    tasks.push_back(K2Task{slice_tile[b0], b0, b1, 0});
+                    b0 = b1;
+                }
                 cur = end;
             }
+            cta_ptr[P->k2_grid] = (int32_t)tasks.size();
         }
+        if (upload_vec(P->cta_ptr2, cta_ptr, st)) return VMAT_E_CUDA;
         P->ntasks2 = (int32_t)tasks.size();
         if (int rc = build_sell(P, P->opt.store_dtype, src_dtype, off, seg_start, seg_len, seg_cb,
                                 d_bcol, d_bval, P->sell2, P->off2)) return rc;
@@ -374,7 +402,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(P->w_grad.alloc(B * 8));        CU(cudaMemset(P->w_grad.p, 0, B * 8));
     CU(P->xg.alloc(B * as));           CU(cudaMemset(P->xg.p, 0, B * as));
     CU(P->d.alloc(V * as));            CU(cudaMemset(P->d.p, 0, V * as));
-    CU(P->vg.alloc(V * as));           CU(cudaMemset(P->vg.p, 0, V * as));
+    CU(P->vg.alloc((V + P->T) * as));  CU(cudaMemset(P->vg.p, 0, (V + P->T) * as));   // padded: tile copies may run past V
     CU(P->partial.alloc((size_t)P->ntiles * B * as));
     CU(cudaMemset(P->partial.p, 0, (size_t)P->ntiles * B * as));
     CU(P->gbf.alloc((B + 1) * 8));     CU(cudaMemset(P->gbf.p, 0, (B + 1) * 8));
@@ -388,7 +416,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     P->k1_smem = (size_t)B * as;
     P->x_in_smem = P->k1_smem + 2048 <= (size_t)P->smem_optin;
     if (!P->x_in_smem) P->k1_smem = 0;
-    P->k1_threads = P->opt.k1_threads > 0 ? P->opt.k1_threads : 1024;
+    P->k1_threads = P->opt.k1_threads > 0 ? P->opt.k1_threads : 512;
     P->k1_grid = P->sm_count;
     CU(P->fpart.alloc((size_t)P->nslices1 * 8)); CU(cudaMemset(P->fpart.p, 0, (size_t)P->nslices1 * 8));
     CU(cudaDeviceSynchronize());
@@ -451,23 +479,28 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
         a1.thr_s = P->thr_s.as<AT>(); a1.over_s = P->over_s.as<AT>(); a1.under_s = P->under_s.as<AT>();
         a1.d = P->d.as<AT>(); a1.vg = P->vg.as<AT>(); a1.fpart = P->fpart.as<double>();
         a1.counter = P->counter.as<unsigned int>();
-        if (P->x_in_smem) {
-            auto kern = k1_dose_penalty<VT, AT, true, U>;
+        if (P->x_in_smem && P->k1_threads <= 512) {
+            auto kern = k1_dose_penalty<VT, AT, true, U, 512>;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
+            kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
+        } else if (P->x_in_smem) {
+            auto kern = k1_dose_penalty<VT, AT, true, (U > 1 ? U / 2 : 1), 1024>;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
             kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
         } else {
-            auto kern = k1_dose_penalty<VT, AT, false, U>;
+            auto kern = k1_dose_penalty<VT, AT, false, (U > 1 ? U / 2 : 1), 1024>;
             kern<<<P->k1_grid, P->k1_threads, 0, st>>>(a1);
         }
         if (ev) CU(cudaEventRecord(ev[1], st));
         K2Args<AT> a2{};
         a2.sell = P->sell2.as<uint4>(); a2.slice_off = P->off2.as<int64_t>(); a2.slice_rows = P->rows2.as<int32_t>();
-        a2.tasks = P->tasks2.as<K2Task>(); a2.vg = P->vg.as<AT>(); a2.partial = P->partial.as<AT>();
+        a2.tasks = P->tasks2.as<K2Task>(); a2.cta_task_ptr = P->cta_ptr2.as<int32_t>();
+        a2.vg = P->vg.as<AT>(); a2.partial = P->partial.as<AT>();
         a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.k1_counter = P->counter.as<unsigned int>();
         if (P->ntasks2 > 0) {
             auto kern2 = k2_beamlet_grad<VT, AT, U>;
             CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
-            kern2<<<P->ntasks2, P->k2_threads, P->k2_smem, st>>>(a2);
+            kern2<<<P->k2_grid, P->k2_threads, P->k2_smem, st>>>(a2);
         } else {
             CU(cudaMemsetAsync(P->counter.p, 0, 4, st));
         }

@@ -20,41 +20,66 @@ namespace vmat {
 // ---------------------------------------------------------------------------------
 // generic SELL row dot product: acc = sum_k val[k] * gather(idx[k]) over `nch` chunks
 // ---------------------------------------------------------------------------------
+// Software pipelined: two register stages of U chunks each; the loads of stage k+1 are in
+// flight while stage k is consumed, so a warp keeps 2*U KB of the stream outstanding.
+template <typename VT, int U>
+struct Stage {
+    uint4 idx[U];
+    typename Store<VT>::Raw raw[U];
+};
+
+template <typename VT, int U>
+__device__ __forceinline__ void stage_load(Stage<VT, U>& st, const uint4* __restrict__ p, int lane, int nvalid) {
+    using S = Store<VT>;
+    if (nvalid >= U) {                   // warp-uniform fast path: a full stage
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            st.idx[u] = ldg_stream16(p + u * S::kUnits + lane);
+            st.raw[u] = S::load(p + u * S::kUnits, lane);
+        }
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (u < nvalid) {
+            st.idx[u] = ldg_stream16(p + u * S::kUnits + lane);
+            st.raw[u] = S::load(p + u * S::kUnits, lane);
+        } else {                         // past the end of the slice: (index 0, value 0)
+            st.idx[u] = make_uint4(0u, 0u, 0u, 0u);
+            st.raw[u] = typename S::Raw{};
+        }
+    }
+}
+
+template <typename VT, typename AT, int U, typename Gather>
+__device__ __forceinline__ void stage_fma(const Stage<VT, U>& st, AT& acc, Gather g) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        AT v[4];
+        Store<VT>::unpack(st.raw[u], v);
+        acc = fma_acc(v[0], g(st.idx[u].x), acc);
+        acc = fma_acc(v[1], g(st.idx[u].y), acc);
+        acc = fma_acc(v[2], g(st.idx[u].z), acc);
+        acc = fma_acc(v[3], g(st.idx[u].w), acc);
+    }
+}
+
 template <typename VT, typename AT, int U, typename Gather>
 __device__ __forceinline__ AT sell_row_dot(const uint4* __restrict__ p, int nch, int lane, Gather g) {
-    using S = Store<VT>;
+    constexpr int kStep = U * Store<VT>::kUnits;
     AT acc = (AT)0;
-    int c = 0;
-    for (; c + U <= nch; c += U) {
-        uint4 idx[U];
-        typename S::Raw raw[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            idx[u] = ldg_stream16(p + u * S::kUnits + lane);
-            raw[u] = S::load(p + u * S::kUnits, lane);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            AT v[4];
-            S::unpack(raw[u], v);
-            acc = fma_acc(v[0], g(idx[u].x), acc);
-            acc = fma_acc(v[1], g(idx[u].y), acc);
-            acc = fma_acc(v[2], g(idx[u].z), acc);
-            acc = fma_acc(v[3], g(idx[u].w), acc);
-        }
-        p += U * S::kUnits;
+    const int ngrp = (nch + U - 1) / U;          // the last group may be partial
+    Stage<VT, U> A, B;
+    if (ngrp > 0) stage_load<VT, U>(A, p, lane, nch);
+    int it = 0;
+    for (; it + 2 <= ngrp; it += 2) {
+        stage_load<VT, U>(B, p + kStep, lane, nch - (it + 1) * U);
+        stage_fma<VT, AT, U>(A, acc, g);
+        if (it + 2 < ngrp) stage_load<VT, U>(A, p + 2 * kStep, lane, nch - (it + 2) * U);
+        stage_fma<VT, AT, U>(B, acc, g);
+        p += 2 * kStep;
     }
-    for (; c < nch; ++c) {
-        uint4 idx = ldg_stream16(p + lane);
-        typename S::Raw raw = S::load(p, lane);
-        AT v[4];
-        S::unpack(raw, v);
-        acc = fma_acc(v[0], g(idx.x), acc);
-        acc = fma_acc(v[1], g(idx.y), acc);
-        acc = fma_acc(v[2], g(idx.z), acc);
-        acc = fma_acc(v[3], g(idx.w), acc);
-        p += S::kUnits;
-    }
+    if (it < ngrp) stage_fma<VT, AT, U>(A, acc, g);
     return acc;
 }
 
@@ -92,8 +117,8 @@ struct K1Args {
     unsigned int* counter;        // dynamic slice scheduler
 };
 
-template <typename VT, typename AT, bool XS, int U>
-__global__ void __launch_bounds__(1024, 1) k1_dose_penalty(const K1Args<AT> a) {
+template <typename VT, typename AT, bool XS, int U, int TPB>
+__global__ void __launch_bounds__(TPB, 1) k1_dose_penalty(const K1Args<AT> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AT* xs = reinterpret_cast<AT*>(smem_raw);
 
@@ -104,14 +129,20 @@ __global__ void __launch_bounds__(1024, 1) k1_dose_penalty(const K1Args<AT> a) {
     }
     auto gather = [&](uint32_t j) -> AT { return XS ? xs[j] : __ldg(a.x_global + j); };
 
-    // dynamic scheduling, longest slices first; the next slice id is fetched one slice ahead
-    unsigned int s = 0, s_next = 0;
-    if (lane == 0) s = atomicAdd(a.counter, 1u);
+    // dynamic scheduling, longest slices first.  Slice ids are claimed two slices ahead and the
+    // slice's metadata one slice ahead, so neither the atomic nor the offset loads are exposed.
+    const unsigned int ns = (unsigned)a.nslices;
+    unsigned int s = 0, s1 = 0, s2 = 0;
+    if (lane == 0) { s = atomicAdd(a.counter, 1u); s1 = atomicAdd(a.counter, 1u); }
     s = __shfl_sync(0xffffffffu, s, 0);
-    while (s < (unsigned)a.nslices) {
-        if (lane == 0) s_next = atomicAdd(a.counter, 1u);
-        const int64_t off = a.slice_off[s];
-        const int nch = (int)((a.slice_off[s + 1] - off) / Store<VT>::kUnits);
+    s1 = __shfl_sync(0xffffffffu, s1, 0);
+    int64_t off = 0, off_end = 0;
+    if (s < ns) { off = a.slice_off[s]; off_end = a.slice_off[s + 1]; }
+    while (s < ns) {
+        if (lane == 0) s2 = atomicAdd(a.counter, 1u);
+        int64_t noff = 0, noff_end = 0;
+        if (s1 < ns) { noff = a.slice_off[s1]; noff_end = a.slice_off[s1 + 1]; }
+        const int nch = (int)((off_end - off) / Store<VT>::kUnits);
         const int64_t slot = (int64_t)s * 32 + lane;
         const int32_t row = a.slice_rows[slot];
         const AT t = a.thr_s[slot], ov = a.over_s[slot], un = a.under_s[slot];
@@ -131,7 +162,8 @@ __global__ void __launch_bounds__(1024, 1) k1_dose_penalty(const K1Args<AT> a) {
         }
         fterm = warp_sum(fterm);      // butterfly: same value and order in every lane, every run
         if (lane == 0) a.fpart[s] = fterm;
-        s = __shfl_sync(0xffffffffu, s_next, 0);
+        s = s1; off = noff; off_end = noff_end;
+        s1 = __shfl_sync(0xffffffffu, s2, 0);
     }
 }
 
@@ -146,8 +178,9 @@ struct K2Args {
     const uint4* sell;            // SELL stream (beamlet-major, column-tiled)
     const int64_t* slice_off;     // [nslices+1]
     const int32_t* slice_rows;    // [nslices*32] beamlet id, -1 padding
-    const K2Task* tasks;
-    const AT* vg;                 // [V]
+    const K2Task* tasks;          // (tile, slice range), ordered by tile
+    const int32_t* cta_task_ptr;  // [gridDim.x+1]: CTA c runs tasks [ptr[c], ptr[c+1]) - equal chunk counts
+    const AT* vg;                 // [V + T] (zero padded so a tile copy may run past V)
     AT* partial;                  // [ntiles][B]
     int64_t V;
     int32_t B;
@@ -155,32 +188,44 @@ struct K2Args {
     unsigned int* k1_counter;     // reset here for the next evaluation
 };
 
+// Persistent CTAs; the host cut the (tile, length)-ordered slice sequence into gridDim.x pieces of
+// equal work, so there is no tail.  The vg tile is staged by one TMA bulk copy per tile change.
 template <typename VT, typename AT, int U>
-__global__ void __launch_bounds__(512, 1) k2_beamlet_grad(const K2Args<AT> a) {
+__global__ void __launch_bounds__(256) k2_beamlet_grad(const K2Args<AT> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AT* vt = reinterpret_cast<AT*>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (blockIdx.x == 0 && tid == 0) *a.k1_counter = 0u;
-    const K2Task task = a.tasks[blockIdx.x];
-    const int64_t base = (int64_t)task.tile * a.T;
-    const int n = (int)min((int64_t)a.T, a.V - base);
-    {   // stage the vg tile (128-bit loads; tile bases are multiples of T, so aligned)
-        constexpr int PER = 16 / sizeof(AT);
-        const uint4* src = reinterpret_cast<const uint4*>(a.vg + base);
-        uint4* dst = reinterpret_cast<uint4*>(vt);
-        const int nvec = n / PER;
-        for (int j = tid; j < nvec; j += blockDim.x) dst[j] = src[j];
-        for (int j = nvec * PER + tid; j < n; j += blockDim.x) vt[j] = a.vg[base + j];
-    }
+    if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     auto gather = [&](uint32_t j) -> AT { return vt[j]; };
-    AT* out = a.partial + (int64_t)task.tile * a.B;
-    for (int s = task.slice_begin + warp; s < task.slice_end; s += nwarps) {
-        const int64_t off = a.slice_off[s];
-        const int nch = (int)((a.slice_off[s + 1] - off) / Store<VT>::kUnits);
-        const int32_t row = a.slice_rows[(int64_t)s * 32 + lane];
-        const AT acc = sell_row_dot<VT, AT, U>(a.sell + off, nch, lane, gather);
-        if (row >= 0) out[row] = acc;
+    uint32_t parity = 0;
+    int cur_tile = -1;
+    const int t_begin = a.cta_task_ptr[blockIdx.x], t_end = a.cta_task_ptr[blockIdx.x + 1];
+    for (int ti = t_begin; ti < t_end; ++ti) {
+        const K2Task task = a.tasks[ti];
+        if (task.tile != cur_tile) {
+            __syncthreads();                         // everybody is done with the previous tile
+            if (tid == 0) {
+                const int64_t base = (int64_t)task.tile * a.T;
+                const int n = (int)min((int64_t)a.T, a.V - base);
+                const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(AT) + 15) & ~(size_t)15);
+                mbar_expect_tx(&bar, bytes);
+                tma_bulk_g2s(vt, a.vg + base, bytes, &bar);
+            }
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
+            cur_tile = task.tile;
+        }
+        AT* out = a.partial + (int64_t)task.tile * a.B;
+        for (int s = task.slice_begin + warp; s < task.slice_end; s += nwarps) {
+            const int64_t off = a.slice_off[s];
+            const int nch = (int)((a.slice_off[s + 1] - off) / Store<VT>::kUnits);
+            const int32_t row = a.slice_rows[(int64_t)s * 32 + lane];
+            const AT acc = sell_row_dot<VT, AT, U>(a.sell + off, nch, lane, gather);
+            if (row >= 0) out[row] = acc;
+        }
     }
 }
 

@@ -110,6 +110,8 @@ class DosePlan:
     # -- aperture weights -----------------------------------------------------------
     def set_aperture(self, beam: int, w_dose, w_grad):
         """w_dose / w_grad: f64[B_beam] (strengths scattered over the open map / diagmaker)."""
+        if not 0 <= beam < self.nb:
+            raise VmatError(f"no control point {beam} (numbeams = {self.nb})")
         n = int(self.beam_ptr[beam + 1] - self.beam_ptr[beam])
         wd = None if w_dose is None else np.ascontiguousarray(w_dose, dtype=np.float64)
         wg = None if w_grad is None else np.ascontiguousarray(w_grad, dtype=np.float64)
