@@ -144,6 +144,17 @@ def main():
     yC = np.zeros(6); yC[1] = 1.0; yC[4] = 2.5
     eval_and_price_fixture("evalprice_C", caseC, {1: ([0.5, 2, 2], [5.25, 5, 4]), 4: ([1, -1, 3.75], [6, 8, 5.5])},
                            yC, [(0.01, 2.25, 0.83, 0.5)])
+    # D: ragged rows + left leaves left of a row's first beamlet: the open map restarts at index 0
+    # and lists beamlets twice (duplicates are deposited twice by calcDose).
+    caseD = make_case(V=2000, nb=6, M=6, N=12, density=0.05, seed=80, gastep=2, ragged=True)
+    rngD = np.random.default_rng(0)
+    selD = {}
+    for bm in (1, 3, 4):
+        l = [int(rngD.integers(-1, caseD.N - 2)) for _ in range(caseD.M)]
+        selD[bm] = (l, [int(min(caseD.N, lv + rngD.integers(1, 6))) for lv in l])
+    yD = np.zeros(6); yD[1] = 1.2; yD[3] = 0.8; yD[4] = 1.9
+    eval_and_price_fixture("evalprice_D", caseD, selD, yD, [(0.0, 2.25, 0.83, 0.5), (1.0, 2.25, 0.83, 0.5),
+                                                            (0.05, 0.1, 0.83, 0.5)])
     colgen_fixture("colgen_A", make_case(V=2500, nb=12, M=5, N=6, density=0.04, seed=31, gastep=10), 0.02, 5, 10)
     colgen_fixture("colgen_B", make_case(V=2000, nb=18, M=4, N=7, density=0.04, seed=32, gastep=2, ragged=True), 0.0, 6, 12)
     colgen_fixture("colgen_C", make_case(V=2000, nb=36, M=3, N=5, density=0.05, seed=33, gastep=1), 0.5, 8, 14)

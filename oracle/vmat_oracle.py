@@ -107,7 +107,10 @@ class OracleState:
             lo = int(self.beam_ptr[i])
             oam = np.asarray(self.openApertureMaps[i], dtype=np.int64)
             if oam.size:
-                w_dose[lo + oam] = np.asarray(self.strengths[i], dtype=float)
+                # the open map can list a beamlet more than once (updateOpenAperture restarts a row
+                # at index 0 when its left leaf lies left of the row's first beamlet, :1089); the
+                # reference's column fancy-indexing then deposits that beamlet once per occurrence
+                np.add.at(w_dose, lo + oam, np.asarray(self.strengths[i], dtype=float))
             w_grad[lo:lo + len(self.diagmakers[i])] = self.diagmakers[i]
         return w_dose, w_grad
 

@@ -7,7 +7,7 @@ from oracle import vmat_oracle as O
 from helpers import load_golden, oracle_state_from_golden, relerr
 
 
-@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C", "evalprice_D"])
 def test_eval_matches_reference_bitwise(name):
     z, case = load_golden(name)
     st = oracle_state_from_golden(z, case)
@@ -28,7 +28,7 @@ def test_eval_matches_reference_bitwise(name):
     assert relerr(d2, z["dose"]) <= 1e-13
 
 
-@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C", "evalprice_D"])
 def test_pricing_matches_reference_bitwise(name):
     z, case = load_golden(name)
     st = oracle_state_from_golden(z, case)
@@ -101,3 +101,27 @@ def test_numpy_sum_order_restatement():
             a = rng.standard_normal(n) * 10.0 ** rng.integers(-4, 4, size=n)
             if n:
                 assert O.numpy_pairwise_sum(a) == a[np.arange(n)].sum()
+
+
+def test_global_form_equals_literal_when_open_map_has_duplicates():
+    """Ragged beamlet rows with a left leaf left of the row's first beamlet make the
+    reference's open map restart at index 0 and list beamlets twice; the global form (what the
+    kernels implement) must deposit them twice as well."""
+    from vmatwpencode_b200.synth import make_case
+    case = make_case(V=2000, nb=6, M=6, N=12, density=0.05, seed=80, gastep=2, ragged=True)
+    st = O.OracleState(case)
+    rng = np.random.default_rng(0)
+    dup = 0
+    y = np.zeros(case.nb)
+    for bm in (1, 3, 4):
+        st.caligraphicC.insertAngle(bm, case.angles[bm])
+        st.llist[bm] = [int(rng.integers(-1, case.N - 2)) for _ in range(case.M)]
+        st.rlist[bm] = [int(min(case.N, lv + rng.integers(1, 6))) for lv in st.llist[bm]]
+        st.openApertureMaps[bm], st.diagmakers[bm], st.strengths[bm] = O.update_open_aperture(st, bm)
+        dup += len(st.openApertureMaps[bm]) - len(set(st.openApertureMaps[bm].tolist()))
+        y[bm] = 0.5 + rng.random()
+    assert dup > 0, "case no longer exercises duplicate open-map entries"
+    f1, g1 = O.calc_obj_grad_literal(st, y.copy())
+    d1 = st.currentDose.copy()
+    f2, g2, d2, vg2, gb2 = O.calc_obj_grad_clean(st, y.copy())
+    assert relerr(d2, d1) <= 1e-13 and abs(f2 - f1) <= 1e-13 * abs(f1) and relerr(g2, g1) <= 1e-13

@@ -37,7 +37,7 @@ def test_native_library_is_the_in_tree_build():
 
 
 @pytest.mark.parametrize("acc", ["f64", "f32"])
-@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C", "evalprice_D"])
 def test_eval_against_reference_fixture(name, acc):
     z, case = load_golden(name)
     data = product_state_from_golden(z, case, store="f32", acc=acc)
@@ -51,7 +51,7 @@ def test_eval_against_reference_fixture(name, acc):
     data.plan.close()
 
 
-@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C", "evalprice_D"])
 def test_pricing_against_reference_fixture(name):
     z, case = load_golden(name)
     data = product_state_from_golden(z, case, store="f32", acc="f64")

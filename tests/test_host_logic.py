@@ -57,7 +57,7 @@ def test_product_does_not_import_oracle():
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
 
 
-@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C"])
+@pytest.mark.parametrize("name", ["evalprice_A", "evalprice_B", "evalprice_C", "evalprice_D"])
 def test_update_open_aperture_matches_golden(name):
     z, case = load_golden(name)
     data = vl.bind(case, gpu=False)
@@ -135,3 +135,33 @@ def test_price_row_descriptors_enumerate_the_oracle_network(name):
                 assert rows[m].vb_min == vb.min() and rows[m].vb_mask == sum(1 << int(v) for v in vb)
                 assert rows[m].grad_offset == (0 if m == 0 else offset)
                 offset = len(vb) - 1 if m == 0 else offset + len(vb)
+
+
+def test_kernel_algorithm_twin_matches_oracle_on_random_states():
+    """The pricing kernel's algorithm (tests/k5_emulator.py, fed by the product's descriptors)
+    against the oracle, on wide ragged grids with loose and tight leaf speeds."""
+    from k5_emulator import emulate_price
+    for seed, (nb, M, N, ragged, gastep) in enumerate([(10, 6, 12, True, 2), (8, 5, 9, False, 10), (9, 4, 20, True, 1)]):
+        case = make_case(V=1500, nb=nb, M=M, N=N, density=0.05, seed=80 + seed, gastep=gastep, ragged=ragged)
+        st = O.OracleState(case)
+        data = vl.bind(case, gpu=False)
+        rng = np.random.default_rng(seed)
+        for state in (st, data):
+            all_candidates(state, case)
+        y = np.zeros(nb)
+        for bm in sorted(rng.choice(nb, size=3, replace=False).tolist()):
+            l = [int(rng.integers(-1, N - 2)) for _ in range(M)]
+            r = [int(min(N, lv + rng.integers(1, 6))) for lv in l]
+            select(st, case, bm, l, r, lambda k: O.update_open_aperture(st, k))
+            select(data, case, bm, l, r, vl.updateOpenAperture)
+            y[bm] = rng.random() * 2
+        O.calc_obj_grad_literal(st, y.copy())
+        for C, vmax in [(0.0, 2.25), (0.03, 2.25), (1.0, 2.25), (0.03, 0.2), (0.2, 0.02)]:
+            for i0 in st.notinC.loc:
+                p0, l0, r0, _ = O.price_candidate(st, i0, C, 1.0, 1.0, 0.5, vmax, 0.83, N, M, 0.5)
+                predec, succ, am, ap = vl._neighbours(i0)
+                rows = (PriceRow * M)()
+                vl._fill_price_rows(rows, 0, am, ap, vmax, 0.83, predec, succ, N, M, i0, 0.5)
+                bg = st.Dlist[i0] @ st.voxelgradient
+                p, l, r = emulate_price(rows, M, C, 1.0, 1.0, 0.5, bg)
+                assert (l, r) == (l0, r0) and p == p0, (seed, C, vmax, i0)

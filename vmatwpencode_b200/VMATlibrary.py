@@ -198,7 +198,9 @@ class vmat_class:
             w_dose = np.zeros(nbl)
             oam = np.asarray(self.openApertureMaps[i], dtype=np.int64)
             if oam.size:
-                w_dose[oam] = np.asarray(self.strengths[i], dtype=float)
+                # a beamlet listed twice in the open map (:1089 restarts a row at index 0 when the
+                # left leaf is left of the row's first beamlet) is deposited twice by calcDose (:250)
+                np.add.at(w_dose, oam, np.asarray(self.strengths[i], dtype=float))
             w_grad = np.zeros(nbl)
             dm = np.asarray(self.diagmakers[i], dtype=float)
             w_grad[:len(dm)] = dm
