@@ -28,10 +28,9 @@ def main():
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     variants = json.loads(args.variants) if args.variants else [
-        dict(), dict(k1_threads=1024), dict(k1_threads=256), dict(k1_threads=384),
-        dict(tile_voxels=4096), dict(tile_voxels=16384), dict(k2_threads=64), dict(k2_threads=256),
-        dict(tile_voxels=4096, k2_threads=64), dict(tile_voxels=16384, k2_threads=256),
-        dict(k2_tasks=148 * 2), dict(k2_tasks=148 * 3), dict(k2_tasks=148 * 8),
+        dict(), dict(k1_threads=4), dict(k1_threads=6), dict(k1_threads=12),
+        dict(tile_voxels=2048), dict(tile_voxels=4096), dict(tile_voxels=16384),
+        dict(k2_tasks=148 * 2), dict(k2_tasks=148 * 4), dict(k2_tasks=148 * 6), dict(k2_tasks=148 * 12),
         dict(store="bf16"), dict(acc="f64"),
     ]
     for v in variants:

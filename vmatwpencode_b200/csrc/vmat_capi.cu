@@ -49,14 +49,14 @@ struct vmat_plan {
     int smem_optin = 0;
 
     std::vector<int32_t> beam_ptr;
-    // K1 layout
-    DevBuf sell1, off1, rows1, thr_s, over_s, under_s;
-    int32_t nslices1 = 0;
+    // K1 layout (stream of super-slices of W1 slices)
+    DevBuf sell1, off1;
+    int32_t nslices1 = 0, nss1 = 0, W1 = 16, nstages1 = 8, stage_bytes1 = 0;
     int64_t units1 = 0;
     // K2 layout
-    DevBuf sell2, off2, rows2, tasks2, cta_ptr2;
+    DevBuf sell2, off2, tasks2, cta_ptr2;
     int k2_grid = 1;
-    int32_t nslices2 = 0, ntasks2 = 0, ntiles = 0, T = 0;
+    int32_t nslices2 = 0, nss2 = 0, ntasks2 = 0, ntiles = 0, T = 0, W2 = 4, nstages2 = 8, stage_bytes2 = 0;
     int64_t units2 = 0;
     // state
     DevBuf y, beam_of, beam_ptr_d, w_dose, w_grad, xg, d, vg, fpart, partial, gbf, result, counter, scratch64;
@@ -140,42 +140,52 @@ static int upload_vec(DevBuf& dst, const std::vector<Tv>& src, cudaStream_t st) 
     return 0;
 }
 
-// Build one SELL layout from segment descriptors (already grouped in slices of 32).
-static int build_sell(vmat_plan* P, int store_dtype, int src_dtype,
-                      const std::vector<int64_t>& slice_off, const std::vector<int64_t>& seg_start,
-                      const std::vector<int32_t>& seg_len, const std::vector<int32_t>& seg_colbase,
-                      const int32_t* d_col, const void* d_val, DevBuf& sell, DevBuf& off_d) {
-    const int32_t nslices = (int32_t)slice_off.size() - 1;
-    const int64_t units = slice_off.back();
+// Build one stream layout from segment descriptors (already grouped in slices of 32, W slices per
+// super-slice).  `tables` (thr/over/under in slice order, element size es) go into the headers.
+static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W, int32_t HU,
+                        const std::vector<int64_t>& ss_off, const std::vector<int64_t>& seg_start,
+                        const std::vector<int32_t>& seg_len, const std::vector<int32_t>& seg_colbase,
+                        const std::vector<int32_t>& rows, const DevBuf* thr, const DevBuf* over, const DevBuf* under,
+                        int32_t es, const int32_t* d_col, const void* d_val, DevBuf& sell, DevBuf& off_d) {
+    const int32_t nslices = (int32_t)(rows.size() / 32);
+    const int64_t units = ss_off.back();
     CU(sell.alloc((size_t)units * 16));
-    if (upload_vec(off_d, slice_off, P->stream)) return VMAT_E_CUDA;
+    CU(cudaMemsetAsync(sell.p, 0, (size_t)units * 16, P->stream));
+    if (upload_vec(off_d, ss_off, P->stream)) return VMAT_E_CUDA;
     if (nslices == 0) return 0;
-    DevBuf dstart, dlen, dcb;
+    DevBuf dstart, dlen, dcb, drows;
     if (upload_vec(dstart, seg_start, P->stream)) return VMAT_E_CUDA;
     if (upload_vec(dlen, seg_len, P->stream)) return VMAT_E_CUDA;
     if (upload_vec(dcb, seg_colbase, P->stream)) return VMAT_E_CUDA;
+    if (upload_vec(drows, rows, P->stream)) return VMAT_E_CUDA;
     const int threads = 256;
     const int64_t blocks = ((int64_t)nslices * 32 + threads - 1) / threads;
+    const unsigned char* t0 = thr ? thr->as<unsigned char>() : nullptr;
+    const unsigned char* t1 = over ? over->as<unsigned char>() : nullptr;
+    const unsigned char* t2 = under ? under->as<unsigned char>() : nullptr;
     DISPATCH_STORE(store_dtype, VT, {
         if (src_dtype == VMAT_F32)
-            k_fill_sell<VT, float><<<(unsigned)blocks, threads, 0, P->stream>>>(
-                nslices, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
-                d_col, static_cast<const float*>(d_val), sell.as<uint4>());
+            k_fill_stream<VT, float><<<(unsigned)blocks, threads, 0, P->stream>>>(
+                nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
+                drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const float*>(d_val), sell.as<uint4>());
         else
-            k_fill_sell<VT, double><<<(unsigned)blocks, threads, 0, P->stream>>>(
-                nslices, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
-                d_col, static_cast<const double*>(d_val), sell.as<uint4>());
+            k_fill_stream<VT, double><<<(unsigned)blocks, threads, 0, P->stream>>>(
+                nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
+                drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const double*>(d_val), sell.as<uint4>());
     });
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(P->stream));
     return 0;
 }
 
+constexpr int kW1 = 16;     // consumer warps (slices per super-slice) of the dose kernel
+constexpr int kW2 = 4;      // ... of the transposed kernel
+
 template <typename VT, typename AT>
 static int k2_occupancy_t(vmat_plan* P, int* occ) {
-    auto kern = k2_beamlet_grad<VT, AT, Unroll<VT>::U>;
+    auto kern = k2_beamlet_grad<VT, AT, kW2>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, P->k2_threads, P->k2_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, (kW2 + 1) * 32, P->k2_smem));
     if (*occ < 1) return fail(VMAT_E_ARG, "transposed kernel does not fit on an SM with these options");
     return 0;
 }
@@ -242,6 +252,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     }
 
     // ---- K1 layout: voxels sorted by row length (descending, stable) ----------------
+    const int units = store_units(P->opt.store_dtype);
+    const int es = (int)P->acc_size;
     {
         std::vector<int32_t> order(V);
         {
@@ -252,35 +264,35 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
             for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - (h_vrow[v + 1] - h_vrow[v])]++] = (int32_t)v;
         }
-        const int32_t ns = (int32_t)((V + 31) / 32);
-        const int units = store_units(P->opt.store_dtype);
-        std::vector<int64_t> off(ns + 1, 0), seg_start((size_t)ns * 32, 0);
+        const int32_t W = kW1, HU = 8 + 3 * (32 * es / 16);
+        const int32_t nss = (int32_t)((V + 32 * W - 1) / (32 * W));
+        const int32_t ns = nss * W;
+        std::vector<int64_t> off(nss + 1, 0), seg_start((size_t)ns * 32, 0);
         std::vector<int32_t> seg_len((size_t)ns * 32, 0), seg_cb((size_t)ns * 32, 0), rows((size_t)ns * 32, -1);
         std::vector<double> t_s((size_t)ns * 32, 0.0), o_s((size_t)ns * 32, 0.0), u_s((size_t)ns * 32, 0.0);
-        for (int32_t s = 0; s < ns; ++s) {
+        for (int32_t ss = 0; ss < nss; ++ss) {
             int64_t mx = 0;
-            for (int k = 0; k < 32; ++k) {
-                const int64_t pos = (int64_t)s * 32 + k;
-                if (pos >= V) break;
+            for (int64_t pos = (int64_t)ss * W * 32; pos < (int64_t)(ss + 1) * W * 32 && pos < V; ++pos) {
                 const int32_t v = order[pos];
                 const int64_t len = h_vrow[v + 1] - h_vrow[v];
                 seg_start[pos] = h_vrow[v]; seg_len[pos] = (int32_t)len; rows[pos] = v;
                 t_s[pos] = thr[v]; o_s[pos] = over[v]; u_s[pos] = under[v];
                 mx = std::max(mx, len);
             }
-            off[s + 1] = off[s] + (mx + 3) / 4 * units;
+            off[ss + 1] = off[ss] + (int64_t)W * HU + (mx + 3) / 4 * (int64_t)W * units;
         }
-        P->nslices1 = ns; P->units1 = off[ns];
-        if (int rc = build_sell(P, P->opt.store_dtype, src_dtype, off, seg_start, seg_len, seg_cb,
-                                d_vcol, d_vval, P->sell1, P->off1)) return rc;
-        if (upload_vec(P->rows1, rows, st)) return VMAT_E_CUDA;
+        P->nslices1 = ns; P->nss1 = nss; P->W1 = W; P->units1 = off[nss];
+        DevBuf thr_s, over_s, under_s;
         int rc = 0;
         DISPATCH_ACC(P->opt.acc_dtype, AT, {
-            rc |= upload_cast<AT>(P->thr_s, t_s, st);
-            rc |= upload_cast<AT>(P->over_s, o_s, st);
-            rc |= upload_cast<AT>(P->under_s, u_s, st);
+            rc |= upload_cast<AT>(thr_s, t_s, st);
+            rc |= upload_cast<AT>(over_s, o_s, st);
+            rc |= upload_cast<AT>(under_s, u_s, st);
         });
         if (rc) return VMAT_E_CUDA;
+        if (int rc2 = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, off, seg_start, seg_len, seg_cb, rows,
+                                   &thr_s, &over_s, &under_s, es, d_vcol, d_vval, P->sell1, P->off1)) return rc2;
+        P->stage_bytes1 = W * std::max<int>(units, HU) * 16;
     }
     up_vcol.alloc(0); up_vval.alloc(0);   // release the voxel-major CSR copy
 
@@ -296,7 +308,13 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     {
         int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : (P->opt.acc_dtype == VMAT_F64 ? 4096 : 8192);
         T = (T + 63) / 64 * 64;
-        if ((size_t)T * P->acc_size > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
+        const int32_t W = kW2, HU = 8;
+        P->W2 = W;
+        P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
+        P->nstages2 = 8;
+        const size_t tile_bytes = ((size_t)T * P->acc_size + 127) & ~(size_t)127;
+        P->k2_smem = tile_bytes + (size_t)P->nstages2 * P->stage_bytes2;
+        if (P->k2_smem + 2048 > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
         const int32_t nt = (int32_t)((V + T - 1) / T);
         P->T = T; P->ntiles = nt;
         DevBuf d_seg;
@@ -309,11 +327,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         CU(cudaStreamSynchronize(st));
         d_seg.alloc(0);
 
-        const int units = store_units(P->opt.store_dtype);
         std::vector<int64_t> off(1, 0), seg_start;
-        std::vector<int32_t> seg_len, seg_cb, rows;
-        std::vector<int32_t> tile_sbegin(nt + 1, 0);
-        std::vector<int64_t> slice_chunks;
+        std::vector<int32_t> seg_len, seg_cb, rows, ss_tile;
+        std::vector<int64_t> ss_cost;                      // stages (header + chunks) of each super-slice
         std::vector<std::pair<int32_t, int32_t>> items;   // (len, beamlet)
         for (int32_t t = 0; t < nt; ++t) {
             items.clear();
@@ -323,9 +339,10 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             }
             std::stable_sort(items.begin(), items.end(),
                              [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first > b.first; });
-            for (size_t i0 = 0; i0 < items.size(); i0 += 32) {
+            const size_t per_ss = (size_t)32 * W;
+            for (size_t i0 = 0; i0 < items.size(); i0 += per_ss) {
                 int32_t mx = 0;
-                for (int k = 0; k < 32; ++k) {
+                for (size_t k = 0; k < per_ss; ++k) {
                     if (i0 + k < items.size()) {
                         const int32_t len = items[i0 + k].first, b = items[i0 + k].second;
                         seg_start.push_back(segstart[(int64_t)b * (nt + 1) + t]);
@@ -336,43 +353,37 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
                     }
                 }
                 const int64_t nch = (mx + 3) / 4;
-                slice_chunks.push_back(nch);
-                off.push_back(off.back() + nch * units);
+                ss_cost.push_back(nch + 1);
+                ss_tile.push_back(t);
+                off.push_back(off.back() + (int64_t)W * HU + nch * (int64_t)W * units);
             }
-            tile_sbegin[t + 1] = (int32_t)slice_chunks.size();
         }
-        P->nslices2 = (int32_t)slice_chunks.size(); P->units2 = off.back();
-        // Persistent CTAs: the (tile, length)-ordered slice sequence is cut into G pieces of equal
-        // work (chunks + a per-slice constant); a piece that crosses a tile boundary becomes two
-        // tasks of the same CTA.
-        P->k2_threads = P->opt.k2_threads > 0 ? P->opt.k2_threads : 128;
-        P->k2_smem = (size_t)T * P->acc_size;
+        P->nss2 = (int32_t)ss_cost.size(); P->nslices2 = P->nss2 * W; P->units2 = off.back();
+        // Persistent CTAs: the (tile, length)-ordered super-slice sequence is cut into G pieces of
+        // equal work; a piece that crosses a tile boundary becomes two tasks of the same CTA.
         int occ = 1;
         if (int rc = k2_occupancy(P, &occ)) return rc;
         const int64_t G = P->opt.k2_tasks > 0 ? P->opt.k2_tasks : (int64_t)P->sm_count * occ;
-        P->k2_grid = (int)std::max<int64_t>(1, std::min<int64_t>(G, std::max<int64_t>(1, (int64_t)slice_chunks.size())));
-        std::vector<int32_t> slice_tile(slice_chunks.size());
-        for (int32_t t = 0; t < nt; ++t)
-            for (int32_t s = tile_sbegin[t]; s < tile_sbegin[t + 1]; ++s) slice_tile[s] = t;
+        P->k2_grid = (int)std::max<int64_t>(1, std::min<int64_t>(G, std::max<int64_t>(1, (int64_t)P->nss2)));
         int64_t total_w = 0;
-        for (int64_t c : slice_chunks) total_w += c + 1;
+        for (int64_t c : ss_cost) total_w += c;
         std::vector<K2Task> tasks;
         std::vector<int32_t> cta_ptr(P->k2_grid + 1, 0);
         {
             int32_t cur = 0;
             int64_t acc = 0;
-            const int32_t nsl = (int32_t)slice_chunks.size();
+            const int32_t nss = P->nss2;
             for (int c = 0; c < P->k2_grid; ++c) {
                 cta_ptr[c] = (int32_t)tasks.size();
                 const int64_t goal = total_w * (c + 1) / P->k2_grid;
                 int32_t end = cur;
-                while (end < nsl && acc < goal) { acc += slice_chunks[end] + 1; ++end; }
-                if (c == P->k2_grid - 1) end = nsl;
+                while (end < nss && acc < goal) { acc += ss_cost[end]; ++end; }
+                if (c == P->k2_grid - 1) end = nss;
                 int32_t b0 = cur;
                 while (b0 < end) {              // split at tile boundaries
                     int32_t b1 = b0;
-                    while (b1 < end && slice_tile[b1] == slice_tile[b0]) ++b1;
-                    tasks.push_back(K2Task{slice_tile[b0], b0, b1, 0});
+                    while (b1 < end && ss_tile[b1] == ss_tile[b0]) ++b1;
+                    tasks.push_back(K2Task{ss_tile[b0], b0, b1, 0});
                     b0 = b1;
                 }
                 cur = end;
@@ -381,9 +392,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         }
         if (upload_vec(P->cta_ptr2, cta_ptr, st)) return VMAT_E_CUDA;
         P->ntasks2 = (int32_t)tasks.size();
-        if (int rc = build_sell(P, P->opt.store_dtype, src_dtype, off, seg_start, seg_len, seg_cb,
-                                d_bcol, d_bval, P->sell2, P->off2)) return rc;
-        if (upload_vec(P->rows2, rows, st)) return VMAT_E_CUDA;
+        if (int rc = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, off, seg_start, seg_len, seg_cb, rows,
+                                  nullptr, nullptr, nullptr, 0, d_bcol, d_bval, P->sell2, P->off2)) return rc;
         if (upload_vec(P->tasks2, tasks, st)) return VMAT_E_CUDA;
     }
     up_bcol.alloc(0); up_bval.alloc(0); up_brow.alloc(0);
@@ -412,12 +422,18 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaMallocHost(&P->h_y, nb * 8));
     CU(cudaMallocHost(&P->h_res, (nb + 1) * 8));
 
-    // K1 launch shape: one CTA per SM, x staged once per SM
-    P->k1_smem = (size_t)B * as;
-    P->x_in_smem = P->k1_smem + 2048 <= (size_t)P->smem_optin;
-    if (!P->x_in_smem) P->k1_smem = 0;
-    P->k1_threads = P->opt.k1_threads > 0 ? P->opt.k1_threads : 512;
-    P->k1_grid = P->sm_count;
+    // K1 launch shape: one CTA per SM (W1 consumer warps + producer), x staged once per SM,
+    // the rest of shared memory is the TMA ring (at most 16 stages)
+    {
+        const size_t xbytes = ((size_t)B * as + 127) & ~(size_t)127;
+        P->x_in_smem = xbytes + 2 * (size_t)P->stage_bytes1 + 4096 <= (size_t)P->smem_optin;
+        const size_t avail = (size_t)P->smem_optin - 4096 - (P->x_in_smem ? xbytes : 0);
+        P->nstages1 = (int)std::max<size_t>(2, std::min<size_t>(16, avail / P->stage_bytes1));
+        if (P->opt.k1_threads > 0) P->nstages1 = std::max(2, std::min(P->nstages1, P->opt.k1_threads));   // reused as a ring-depth knob
+        P->k1_smem = (P->x_in_smem ? xbytes : 0) + (size_t)P->nstages1 * P->stage_bytes1;
+        P->k1_threads = (kW1 + 1) * 32;
+        P->k1_grid = P->sm_count;
+    }
     CU(P->fpart.alloc((size_t)P->nslices1 * 8)); CU(cudaMemset(P->fpart.p, 0, (size_t)P->nslices1 * 8));
     CU(cudaDeviceSynchronize());
 
@@ -444,8 +460,8 @@ extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layou
         // what the three kernels stream: both SELL layouts (padding included), slice metadata,
         // penalty tables, d/vg writes, vg tile reads, tile partials (write + read), x inputs, gb.
         int64_t b = (P->units1 + P->units2) * 16;
-        b += (int64_t)P->nslices1 * (8 + 32 * 4) + (int64_t)P->nslices2 * (8 + 32 * 4);
-        b += 3 * P->V * as + 2 * P->V * as + P->V * as;
+        b += (int64_t)(P->nss1 + P->nss2) * 8;            // super-slice offsets (headers are inside the streams)
+        b += 2 * P->V * as + P->V * as;                     // d, vg written; vg read
         b += 2 * (int64_t)P->ntiles * P->B * as;
         b += P->B * (as + 4) + P->B * 8 * 2;
         *layout_bytes = b;
@@ -460,7 +476,6 @@ extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layou
 // ---------------------------------------------------------------------------------
 template <typename VT, typename AT>
 static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
-    constexpr int U = Unroll<VT>::U;
     cudaEvent_t* ev = nullptr;
     if (P->timing && phase == 0) {
         ev = &P->tev[(P->tcount % vmat_plan::kTimingSlots) * 4];
@@ -473,34 +488,32 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
                 (int32_t)P->B, P->y.as<double>(), P->beam_of.as<int32_t>(), P->w_dose.as<AT>(), P->xg.as<AT>());
         }
         K1Args<AT> a1{};
-        a1.sell = P->sell1.as<uint4>(); a1.slice_off = P->off1.as<int64_t>(); a1.slice_rows = P->rows1.as<int32_t>();
-        a1.nslices = P->nslices1; a1.B = (int32_t)P->B; a1.y = P->y.as<double>(); a1.beam_of = P->beam_of.as<int32_t>();
+        a1.sell = P->sell1.as<uint4>(); a1.ss_off = P->off1.as<int64_t>(); a1.nss = P->nss1;
+        a1.nstages = P->nstages1; a1.stage_bytes = P->stage_bytes1;
+        a1.B = (int32_t)P->B; a1.y = P->y.as<double>(); a1.beam_of = P->beam_of.as<int32_t>();
         a1.w_dose = P->w_dose.as<AT>(); a1.x_global = P->xg.as<AT>();
-        a1.thr_s = P->thr_s.as<AT>(); a1.over_s = P->over_s.as<AT>(); a1.under_s = P->under_s.as<AT>();
         a1.d = P->d.as<AT>(); a1.vg = P->vg.as<AT>(); a1.fpart = P->fpart.as<double>();
         a1.counter = P->counter.as<unsigned int>();
-        if (P->x_in_smem && P->k1_threads <= 512) {
-            auto kern = k1_dose_penalty<VT, AT, true, U, 512>;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
-            kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
-        } else if (P->x_in_smem) {
-            auto kern = k1_dose_penalty<VT, AT, true, (U > 1 ? U / 2 : 1), 1024>;
+        if (P->x_in_smem) {
+            auto kern = k1_dose_penalty<VT, AT, true, kW1>;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
             kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
         } else {
-            auto kern = k1_dose_penalty<VT, AT, false, (U > 1 ? U / 2 : 1), 1024>;
-            kern<<<P->k1_grid, P->k1_threads, 0, st>>>(a1);
+            auto kern = k1_dose_penalty<VT, AT, false, kW1>;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
+            kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
         }
         if (ev) CU(cudaEventRecord(ev[1], st));
         K2Args<AT> a2{};
-        a2.sell = P->sell2.as<uint4>(); a2.slice_off = P->off2.as<int64_t>(); a2.slice_rows = P->rows2.as<int32_t>();
+        a2.sell = P->sell2.as<uint4>(); a2.ss_off = P->off2.as<int64_t>();
         a2.tasks = P->tasks2.as<K2Task>(); a2.cta_task_ptr = P->cta_ptr2.as<int32_t>();
         a2.vg = P->vg.as<AT>(); a2.partial = P->partial.as<AT>();
-        a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.k1_counter = P->counter.as<unsigned int>();
+        a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.nstages = P->nstages2; a2.stage_bytes = P->stage_bytes2;
+        a2.k1_counter = P->counter.as<unsigned int>();
         if (P->ntasks2 > 0) {
-            auto kern2 = k2_beamlet_grad<VT, AT, U>;
+            auto kern2 = k2_beamlet_grad<VT, AT, kW2>;
             CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
-            kern2<<<P->k2_grid, P->k2_threads, P->k2_smem, st>>>(a2);
+            kern2<<<P->k2_grid, (kW2 + 1) * 32, P->k2_smem, st>>>(a2);
         } else {
             CU(cudaMemsetAsync(P->counter.p, 0, 4, st));
         }

@@ -1,15 +1,19 @@
 // Evaluation kernels of libvmat_b200 (sm_100a): dose + penalty (K1), transposed
 // product (K2), deterministic reductions (K3), layout construction.
 //
-// Data layout in HBM ("row-sorted sliced ELL", SELL-32-4):
-//   * rows (voxels for K1, (tile, beamlet) segments for K2) are sorted by length and cut
-//     into slices of 32; lane i of a warp owns row i of its slice;
-//   * a slice is a run of chunks; a chunk holds 4 nonzeros of each of the 32 rows: first
-//     the 32 int4 index vectors, then the 32 value vectors (vmat_common.cuh: Store<>), so
-//     every warp load is one fully coalesced 128-bit-per-lane transaction and the whole
-//     slice is one contiguous stream;
-//   * the vector being gathered (x for K1, a tile of vg for K2) is staged in shared memory
-//     so the irregular accesses never leave the SM.
+// Data layout in HBM ("row-sorted sliced ELL stream"):
+//   * rows (voxels for K1, (tile, beamlet) segments for K2) are sorted by length and cut into
+//     slices of 32 (lane i of a warp owns row i); W consecutive slices form a super-slice that
+//     one CTA processes with W consumer warps in lock step;
+//   * a super-slice is one contiguous run of the stream: a header (per warp: the 32 row ids and,
+//     for K1, the rows' penalty tables) followed by nch stages; stage c holds chunk c of every
+//     warp; a chunk is 4 nonzeros of each of the warp's 32 rows: 32 int4 index vectors, then
+//     the 32 value vectors (vmat_common.cuh: Store<>);
+//   * a producer thread streams the CTA's super-slices with TMA bulk copies into a shared-memory
+//     ring (full/empty mbarriers); consumers read their chunk with conflict-free 128-bit shared
+//     loads.  The stream is never touched by the LSU global path and no slice boundary stalls it;
+//   * the vector being gathered (x for K1, a tile of vg for K2) is staged in shared memory so
+//     the irregular accesses never leave the SM.
 // Each lane accumulates its row sequentially in storage order: no shuffles, no atomics,
 // bit-reproducible.
 #pragma once
@@ -17,70 +21,58 @@
 
 namespace vmat {
 
-// ---------------------------------------------------------------------------------
-// generic SELL row dot product: acc = sum_k val[k] * gather(idx[k]) over `nch` chunks
-// ---------------------------------------------------------------------------------
-// Software pipelined: two register stages of U chunks each; the loads of stage k+1 are in
-// flight while stage k is consumed, so a warp keeps 2*U KB of the stream outstanding.
-template <typename VT, int U>
-struct Stage {
-    uint4 idx[U];
-    typename Store<VT>::Raw raw[U];
+constexpr int kStageHeader = 1;     // stage carries the super-slice header
+constexpr int kStageLast = 2;       // last stage of the super-slice: run the epilogue
+struct StageInfo { int32_t ss, flags, tile, pad; };
+
+// header units (16 B) per warp: 32 row ids (+ thr, over, under as AT for K1)
+template <typename AT> __host__ __device__ constexpr int header_units_k1() { return 8 + 3 * (32 * (int)sizeof(AT) / 16); }
+constexpr int kHeaderUnitsK2 = 8;
+
+// one chunk of one warp from the ring: acc += sum_k val[k] * gather(idx[k])
+template <typename VT, typename AT, typename Gather>
+__device__ __forceinline__ void chunk_fma(const unsigned char* __restrict__ cp, int lane, AT& acc, Gather g) {
+    const uint4 idx = *reinterpret_cast<const uint4*>(cp + lane * 16);
+    AT v[4];
+    if constexpr (sizeof(VT) == 4) {
+        const uint4 r = *reinterpret_cast<const uint4*>(cp + 512 + lane * 16);
+        v[0] = (AT)__uint_as_float(r.x); v[1] = (AT)__uint_as_float(r.y);
+        v[2] = (AT)__uint_as_float(r.z); v[3] = (AT)__uint_as_float(r.w);
+    } else if constexpr (sizeof(VT) == 2) {
+        const uint2 r = *reinterpret_cast<const uint2*>(cp + 512 + lane * 8);
+        v[0] = (AT)__uint_as_float(r.x << 16); v[1] = (AT)__uint_as_float(r.x & 0xffff0000u);
+        v[2] = (AT)__uint_as_float(r.y << 16); v[3] = (AT)__uint_as_float(r.y & 0xffff0000u);
+    } else {
+        const double2 a = *reinterpret_cast<const double2*>(cp + 512 + lane * 16);
+        const double2 b = *reinterpret_cast<const double2*>(cp + 1024 + lane * 16);
+        v[0] = (AT)a.x; v[1] = (AT)a.y; v[2] = (AT)b.x; v[3] = (AT)b.y;
+    }
+    acc = fma_acc(v[0], g(idx.x), acc);
+    acc = fma_acc(v[1], g(idx.y), acc);
+    acc = fma_acc(v[2], g(idx.z), acc);
+    acc = fma_acc(v[3], g(idx.w), acc);
+}
+
+// ring bookkeeping shared by producer and consumers
+struct RingPos {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int nstages) { if (++stage == nstages) { stage = 0; phase ^= 1u; } }
 };
 
-template <typename VT, int U>
-__device__ __forceinline__ void stage_load(Stage<VT, U>& st, const uint4* __restrict__ p, int lane, int nvalid) {
-    using S = Store<VT>;
-    if (nvalid >= U) {                   // warp-uniform fast path: a full stage
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            st.idx[u] = ldg_stream16(p + u * S::kUnits + lane);
-            st.raw[u] = S::load(p + u * S::kUnits, lane);
-        }
-        return;
+// producer side: publish one stage (header or data) of `bytes` from `src`
+__device__ __forceinline__ void ring_push(unsigned char* ring, int stage_bytes, uint64_t* full, uint64_t* empty,
+                                          StageInfo* sinfo, RingPos& pos, int nstages, const StageInfo& info,
+                                          const void* src, uint32_t bytes, uint64_t policy) {
+    mbar_wait(&empty[pos.stage], pos.phase ^ 1u);
+    sinfo[pos.stage] = info;
+    if (bytes) {
+        mbar_expect_tx(&full[pos.stage], bytes);
+        tma_bulk_g2s_hint(ring + (size_t)pos.stage * stage_bytes, src, bytes, &full[pos.stage], policy);
+    } else {
+        mbar_arrive(&full[pos.stage]);
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if (u < nvalid) {
-            st.idx[u] = ldg_stream16(p + u * S::kUnits + lane);
-            st.raw[u] = S::load(p + u * S::kUnits, lane);
-        } else {                         // past the end of the slice: (index 0, value 0)
-            st.idx[u] = make_uint4(0u, 0u, 0u, 0u);
-            st.raw[u] = typename S::Raw{};
-        }
-    }
-}
-
-template <typename VT, typename AT, int U, typename Gather>
-__device__ __forceinline__ void stage_fma(const Stage<VT, U>& st, AT& acc, Gather g) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        AT v[4];
-        Store<VT>::unpack(st.raw[u], v);
-        acc = fma_acc(v[0], g(st.idx[u].x), acc);
-        acc = fma_acc(v[1], g(st.idx[u].y), acc);
-        acc = fma_acc(v[2], g(st.idx[u].z), acc);
-        acc = fma_acc(v[3], g(st.idx[u].w), acc);
-    }
-}
-
-template <typename VT, typename AT, int U, typename Gather>
-__device__ __forceinline__ AT sell_row_dot(const uint4* __restrict__ p, int nch, int lane, Gather g) {
-    constexpr int kStep = U * Store<VT>::kUnits;
-    AT acc = (AT)0;
-    const int ngrp = (nch + U - 1) / U;          // the last group may be partial
-    Stage<VT, U> A, B;
-    if (ngrp > 0) stage_load<VT, U>(A, p, lane, nch);
-    int it = 0;
-    for (; it + 2 <= ngrp; it += 2) {
-        stage_load<VT, U>(B, p + kStep, lane, nch - (it + 1) * U);
-        stage_fma<VT, AT, U>(A, acc, g);
-        if (it + 2 < ngrp) stage_load<VT, U>(A, p + 2 * kStep, lane, nch - (it + 2) * U);
-        stage_fma<VT, AT, U>(B, acc, g);
-        p += 2 * kStep;
-    }
-    if (it < ngrp) stage_fma<VT, AT, U>(A, acc, g);
-    return acc;
+    pos.advance(nstages);
 }
 
 // ---------------------------------------------------------------------------------
@@ -96,136 +88,226 @@ __global__ void k4_expand_x(int32_t B, const double* __restrict__ y, const int32
 // ---------------------------------------------------------------------------------
 // K1: d = D x, fused penalty epilogue (objective partials, voxel gradient)
 //     replaces calcDose + calcGradientandObjValue (greedyVMATsampling.py:243-271)
+// CTA = W consumer warps + 1 producer warp; persistent, one CTA per SM; super-slices are
+// claimed from an atomic counter, longest first.
 // ---------------------------------------------------------------------------------
 template <typename AT>
 struct K1Args {
-    const uint4* sell;            // SELL stream (voxel-major)
-    const int64_t* slice_off;     // [nslices+1] in 16-byte units
-    const int32_t* slice_rows;    // [nslices*32] voxel id of each lane, -1 = padding lane
-    int32_t nslices;
+    const uint4* sell;            // stream (voxel-major)
+    const int64_t* ss_off;        // [nss+1] in 16-byte units
+    int32_t nss;
+    int32_t nstages;              // ring depth
+    int32_t stage_bytes;          // ring slot size
     int32_t B;
     const double* y;              // [nb] intensities
     const int32_t* beam_of;       // [B]
     const AT* w_dose;             // [B]
     const AT* x_global;           // [B] (only read when XS == false)
-    const AT* thr_s;              // penalty tables in slice order [nslices*32]
-    const AT* over_s;
-    const AT* under_s;
     AT* d;                        // [V] dose, natural voxel order
     AT* vg;                       // [V] voxel gradient
-    double* fpart;                // [nslices] objective partial of every slice (fixed order -> deterministic)
-    unsigned int* counter;        // dynamic slice scheduler
+    double* fpart;                // [nss*W] objective partial of every slice (fixed order -> deterministic)
+    unsigned int* counter;        // dynamic super-slice scheduler
 };
 
-template <typename VT, typename AT, bool XS, int U, int TPB>
-__global__ void __launch_bounds__(TPB, 1) k1_dose_penalty(const K1Args<AT> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <typename VT, typename AT, bool XS, int W>
+__global__ void __launch_bounds__((W + 1) * 32, 1) k1_dose_penalty(const K1Args<AT> a) {
+    constexpr int KU = Store<VT>::kUnits, HU = header_units_k1<AT>();
+    constexpr int kMaxStages = 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages];
+    __shared__ StageInfo sinfo[kMaxStages];
+    const int xbytes = XS ? ((a.B * (int)sizeof(AT) + 127) & ~127) : 0;
     AT* xs = reinterpret_cast<AT*>(smem_raw);
+    unsigned char* ring = smem_raw + xbytes;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nst = a.nstages, SB = a.stage_bytes;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
+        fence_barrier_init();
+    }
     if (XS) {   // x_j = y[beam(j)] * w_dose[j]   (K4 folded into the prologue)
         for (int j = tid; j < a.B; j += blockDim.x) xs[j] = mul_rn((AT)a.y[a.beam_of[j]], a.w_dose[j]);
-        __syncthreads();
     }
-    auto gather = [&](uint32_t j) -> AT { return XS ? xs[j] : __ldg(a.x_global + j); };
+    __syncthreads();
 
-    // dynamic scheduling, longest slices first.  Slice ids are claimed two slices ahead and the
-    // slice's metadata one slice ahead, so neither the atomic nor the offset loads are exposed.
-    const unsigned int ns = (unsigned)a.nslices;
-    unsigned int s = 0, s1 = 0, s2 = 0;
-    if (lane == 0) { s = atomicAdd(a.counter, 1u); s1 = atomicAdd(a.counter, 1u); }
-    s = __shfl_sync(0xffffffffu, s, 0);
-    s1 = __shfl_sync(0xffffffffu, s1, 0);
-    int64_t off = 0, off_end = 0;
-    if (s < ns) { off = a.slice_off[s]; off_end = a.slice_off[s + 1]; }
-    while (s < ns) {
-        if (lane == 0) s2 = atomicAdd(a.counter, 1u);
-        int64_t noff = 0, noff_end = 0;
-        if (s1 < ns) { noff = a.slice_off[s1]; noff_end = a.slice_off[s1 + 1]; }
-        const int nch = (int)((off_end - off) / Store<VT>::kUnits);
-        const int64_t slot = (int64_t)s * 32 + lane;
-        const int32_t row = a.slice_rows[slot];
-        const AT t = a.thr_s[slot], ov = a.over_s[slot], un = a.under_s[slot];
-        const AT dose = sell_row_dot<VT, AT, U>(a.sell + off, nch, lane, gather);
-        double fterm = 0.0;
-        if (row >= 0) {
-            // (d-t)+ and (t-d)+, objective term, vg = 2*(2*o*over - 2*u*under)  (:255-271)
-            AT o = sub_rn(dose, t);  o = o > (AT)0 ? o : (AT)0;
-            AT u = sub_rn(t, dose);  u = u > (AT)0 ? u : (AT)0;
-            const AT fo = mul_rn(mul_rn(o, o), ov);
-            const AT fu = mul_rn(mul_rn(u, u), un);
-            fterm = (double)add_rn(fo, fu);
-            const AT go = mul_rn(mul_rn((AT)2, o), ov);
-            const AT gu = mul_rn(mul_rn((AT)2, u), un);
-            a.d[row] = dose;
-            a.vg[row] = mul_rn((AT)2, sub_rn(go, gu));
+    if (warp == W) {
+        // ---------------- producer: one thread streams super-slices into the ring ----------
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            RingPos pos;
+            const unsigned int ns = (unsigned)a.nss;
+            unsigned int cur = atomicAdd(a.counter, 1u), nxt = atomicAdd(a.counter, 1u);
+            int64_t o0 = 0, o1 = 0;
+            if (cur < ns) { o0 = a.ss_off[cur]; o1 = a.ss_off[cur + 1]; }
+            while (cur < ns) {
+                const unsigned int nn = atomicAdd(a.counter, 1u);
+                int64_t n0 = 0, n1 = 0;
+                if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; }
+                const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
+                ring_push(ring, SB, full, empty, sinfo, pos, nst,
+                          StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0), 0, 0},
+                          a.sell + o0, W * HU * 16, pol);
+                const uint4* data = a.sell + o0 + W * HU;
+                for (int c = 0; c < nch; ++c)
+                    ring_push(ring, SB, full, empty, sinfo, pos, nst,
+                              StageInfo{(int32_t)cur, c == nch - 1 ? kStageLast : 0, 0, 0},
+                              data + (int64_t)c * W * KU, W * KU * 16, pol);
+                cur = nxt; nxt = nn; o0 = n0; o1 = n1;
+            }
+            ring_push(ring, SB, full, empty, sinfo, pos, nst, StageInfo{-1, 0, 0, 0}, nullptr, 0, pol);
         }
-        fterm = warp_sum(fterm);      // butterfly: same value and order in every lane, every run
-        if (lane == 0) a.fpart[s] = fterm;
-        s = s1; off = noff; off_end = noff_end;
-        s1 = __shfl_sync(0xffffffffu, s2, 0);
+        return;
+    }
+
+    // ---------------- consumers: warp w owns slice w of every super-slice -------------------
+    auto gather = [&](uint32_t j) -> AT { return XS ? xs[j] : __ldg(a.x_global + j); };
+    RingPos pos;
+    AT acc = (AT)0, t = (AT)0, ov = (AT)0, un = (AT)0;
+    int32_t row = -1;
+    while (true) {
+        mbar_wait(&full[pos.stage], pos.phase);
+        const StageInfo info = sinfo[pos.stage];
+        if (info.ss < 0) break;
+        const unsigned char* sp = ring + (size_t)pos.stage * SB;
+        if (info.flags & kStageHeader) {
+            const unsigned char* hp = sp + warp * (HU * 16);
+            row = reinterpret_cast<const int32_t*>(hp)[lane];
+            t  = reinterpret_cast<const AT*>(hp + 128)[lane];
+            ov = reinterpret_cast<const AT*>(hp + 128 + 32 * sizeof(AT))[lane];
+            un = reinterpret_cast<const AT*>(hp + 128 + 64 * sizeof(AT))[lane];
+            acc = (AT)0;
+        } else {
+            chunk_fma<VT, AT>(sp + warp * (KU * 16), lane, acc, gather);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[pos.stage]);
+        if (info.flags & kStageLast) {
+            double fterm = 0.0;
+            if (row >= 0) {
+                // (d-t)+ and (t-d)+, objective term, vg = 2*(2*o*over - 2*u*under)  (:255-271)
+                AT o = sub_rn(acc, t);  o = o > (AT)0 ? o : (AT)0;
+                AT u = sub_rn(t, acc);  u = u > (AT)0 ? u : (AT)0;
+                const AT fo = mul_rn(mul_rn(o, o), ov);
+                const AT fu = mul_rn(mul_rn(u, u), un);
+                fterm = (double)add_rn(fo, fu);
+                const AT go = mul_rn(mul_rn((AT)2, o), ov);
+                const AT gu = mul_rn(mul_rn((AT)2, u), un);
+                a.d[row] = acc;
+                a.vg[row] = mul_rn((AT)2, sub_rn(go, gu));
+            }
+            fterm = warp_sum(fterm);      // butterfly: same value and order in every lane, every run
+            if (lane == 0) a.fpart[(int64_t)info.ss * W + warp] = fterm;
+        }
+        pos.advance(nst);
     }
 }
 
 // ---------------------------------------------------------------------------------
 // K2: partial[tile][beamlet] = sum over the tile's voxels of D[v, beamlet] * vg[v]
 //     (transposed product over the pre-built beamlet-major layout; PPsubroutine :646)
+// Persistent CTAs (W consumer warps + producer); the host cut the (tile, length)-ordered
+// super-slice sequence into gridDim.x pieces of equal work, so there is no tail.  The vg tile
+// is staged by one TMA bulk copy per tile change.
 // ---------------------------------------------------------------------------------
-struct K2Task { int32_t tile, slice_begin, slice_end, pad; };
+struct K2Task { int32_t tile, ss_begin, ss_end, pad; };
 
 template <typename AT>
 struct K2Args {
-    const uint4* sell;            // SELL stream (beamlet-major, column-tiled)
-    const int64_t* slice_off;     // [nslices+1]
-    const int32_t* slice_rows;    // [nslices*32] beamlet id, -1 padding
-    const K2Task* tasks;          // (tile, slice range), ordered by tile
-    const int32_t* cta_task_ptr;  // [gridDim.x+1]: CTA c runs tasks [ptr[c], ptr[c+1]) - equal chunk counts
+    const uint4* sell;            // stream (beamlet-major, column-tiled)
+    const int64_t* ss_off;        // [nss+1]
+    const K2Task* tasks;          // (tile, super-slice range), ordered by tile
+    const int32_t* cta_task_ptr;  // [gridDim.x+1]: CTA c runs tasks [ptr[c], ptr[c+1])
     const AT* vg;                 // [V + T] (zero padded so a tile copy may run past V)
     AT* partial;                  // [ntiles][B]
     int64_t V;
     int32_t B;
     int32_t T;                    // voxels per tile
+    int32_t nstages, stage_bytes;
     unsigned int* k1_counter;     // reset here for the next evaluation
 };
 
-// Persistent CTAs; the host cut the (tile, length)-ordered slice sequence into gridDim.x pieces of
-// equal work, so there is no tail.  The vg tile is staged by one TMA bulk copy per tile change.
-template <typename VT, typename AT, int U>
-__global__ void __launch_bounds__(256) k2_beamlet_grad(const K2Args<AT> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <typename VT, typename AT, int W>
+__global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT> a) {
+    constexpr int KU = Store<VT>::kUnits, HU = kHeaderUnitsK2;
+    constexpr int kMaxStages = 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tilebar;
+    __shared__ StageInfo sinfo[kMaxStages];
+    const int tbytes = (a.T * (int)sizeof(AT) + 127) & ~127;
     AT* vt = reinterpret_cast<AT*>(smem_raw);
-    __shared__ __align__(8) uint64_t bar;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    unsigned char* ring = smem_raw + tbytes;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nst = a.nstages, SB = a.stage_bytes;
     if (blockIdx.x == 0 && tid == 0) *a.k1_counter = 0u;
-    if (tid == 0) mbar_init(&bar, 1);
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
+        mbar_init(&tilebar, 1);
+        fence_barrier_init();
+    }
     __syncthreads();
-    auto gather = [&](uint32_t j) -> AT { return vt[j]; };
-    uint32_t parity = 0;
-    int cur_tile = -1;
     const int t_begin = a.cta_task_ptr[blockIdx.x], t_end = a.cta_task_ptr[blockIdx.x + 1];
-    for (int ti = t_begin; ti < t_end; ++ti) {
-        const K2Task task = a.tasks[ti];
-        if (task.tile != cur_tile) {
-            __syncthreads();                         // everybody is done with the previous tile
-            if (tid == 0) {
-                const int64_t base = (int64_t)task.tile * a.T;
-                const int n = (int)min((int64_t)a.T, a.V - base);
-                const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(AT) + 15) & ~(size_t)15);
-                mbar_expect_tx(&bar, bytes);
-                tma_bulk_g2s(vt, a.vg + base, bytes, &bar);
+
+    if (warp == W) {
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            RingPos pos;
+            for (int ti = t_begin; ti < t_end; ++ti) {
+                const K2Task task = a.tasks[ti];
+                int64_t o0 = a.ss_off[task.ss_begin];
+                for (int ss = task.ss_begin; ss < task.ss_end; ++ss) {
+                    const int64_t o1 = a.ss_off[ss + 1];
+                    const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
+                    ring_push(ring, SB, full, empty, sinfo, pos, nst,
+                              StageInfo{ss, kStageHeader | (nch == 0 ? kStageLast : 0), task.tile, 0},
+                              a.sell + o0, W * HU * 16, pol);
+                    const uint4* data = a.sell + o0 + W * HU;
+                    for (int c = 0; c < nch; ++c)
+                        ring_push(ring, SB, full, empty, sinfo, pos, nst,
+                                  StageInfo{ss, c == nch - 1 ? kStageLast : 0, task.tile, 0},
+                                  data + (int64_t)c * W * KU, W * KU * 16, pol);
+                    o0 = o1;
+                }
             }
-            mbar_wait(&bar, parity);
-            parity ^= 1u;
-            cur_tile = task.tile;
+            ring_push(ring, SB, full, empty, sinfo, pos, nst, StageInfo{-1, 0, 0, 0}, nullptr, 0, pol);
         }
-        AT* out = a.partial + (int64_t)task.tile * a.B;
-        for (int s = task.slice_begin + warp; s < task.slice_end; s += nwarps) {
-            const int64_t off = a.slice_off[s];
-            const int nch = (int)((a.slice_off[s + 1] - off) / Store<VT>::kUnits);
-            const int32_t row = a.slice_rows[(int64_t)s * 32 + lane];
-            const AT acc = sell_row_dot<VT, AT, U>(a.sell + off, nch, lane, gather);
-            if (row >= 0) out[row] = acc;
+        return;
+    }
+
+    auto gather = [&](uint32_t j) -> AT { return vt[j]; };
+    RingPos pos;
+    AT acc = (AT)0;
+    int32_t row = -1;
+    int cur_tile = -1;
+    uint32_t tparity = 0;
+    while (true) {
+        mbar_wait(&full[pos.stage], pos.phase);
+        const StageInfo info = sinfo[pos.stage];
+        if (info.ss < 0) break;
+        const unsigned char* sp = ring + (size_t)pos.stage * SB;
+        if (info.flags & kStageHeader) {
+            if (info.tile != cur_tile) {
+                named_bar_sync(1, W * 32);            // all consumers are done with the previous tile
+                if (tid == 0) {
+                    const int64_t base = (int64_t)info.tile * a.T;
+                    const int n = (int)min((int64_t)a.T, a.V - base);
+                    const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(AT) + 15) & ~(size_t)15);
+                    mbar_expect_tx(&tilebar, bytes);
+                    tma_bulk_g2s(vt, a.vg + base, bytes, &tilebar);
+                }
+                mbar_wait(&tilebar, tparity);
+                tparity ^= 1u;
+                cur_tile = info.tile;
+            }
+            row = reinterpret_cast<const int32_t*>(sp + warp * (HU * 16))[lane];
+            acc = (AT)0;
+        } else {
+            chunk_fma<VT, AT>(sp + warp * (KU * 16), lane, acc, gather);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[pos.stage]);
+        if ((info.flags & kStageLast) && row >= 0) a.partial[(int64_t)cur_tile * a.B + row] = acc;
+        pos.advance(nst);
     }
 }
 
@@ -327,25 +409,40 @@ template <> struct StoreCvt<__nv_bfloat16> {
     template <typename S> __device__ static __nv_bfloat16 cvt(S v) { return __float2bfloat16_rn((float)v); }
 };
 
-// one warp per slice: lane copies its segment (CSR positions seg_start .. +seg_len) into
-// the chunked layout, indices rebased by seg_colbase; padding = (index 0, value 0)
+// one warp per slice s = ss*W + w: writes the warp's part of the super-slice header (row ids and,
+// when `tables` is set, thr/over/under of elem size `es`) and copies the lane's segment (CSR
+// positions seg_start .. +seg_len) into the chunked stages; padding = (index 0, value 0)
 template <typename VT, typename ST>
-__global__ void k_fill_sell(int32_t nslices, const int64_t* __restrict__ slice_off,
-                            const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_len,
-                            const int32_t* __restrict__ seg_colbase,
-                            const int32_t* __restrict__ col, const ST* __restrict__ val,
-                            uint4* __restrict__ sell) {
+__global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int64_t* __restrict__ ss_off,
+                              const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_len,
+                              const int32_t* __restrict__ seg_colbase, const int32_t* __restrict__ rows,
+                              const unsigned char* __restrict__ thr, const unsigned char* __restrict__ over,
+                              const unsigned char* __restrict__ under, int32_t es,
+                              const int32_t* __restrict__ col, const ST* __restrict__ val,
+                              uint4* __restrict__ sell) {
     using S = Store<VT>;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= nslices) return;
-    const int64_t off = slice_off[gw];
-    const int nch = (int)((slice_off[gw + 1] - off) / S::kUnits);
+    const int64_t ss = gw / W;
+    const int w = (int)(gw % W);
+    const int64_t off = ss_off[ss];
+    const int nch = (int)((ss_off[ss + 1] - off - (int64_t)W * HU) / ((int64_t)W * S::kUnits));
     const int64_t slot = gw * 32 + lane;
+    unsigned char* hp = reinterpret_cast<unsigned char*>(sell + off + (int64_t)w * HU);
+    reinterpret_cast<int32_t*>(hp)[lane] = rows[slot];
+    if (thr) {
+        for (int k = 0; k < es; ++k) {
+            hp[128 + lane * es + k] = thr[slot * es + k];
+            hp[128 + 32 * es + lane * es + k] = over[slot * es + k];
+            hp[128 + 64 * es + lane * es + k] = under[slot * es + k];
+        }
+    }
     const int64_t st = seg_start[slot];
     const int32_t len = seg_len[slot], cb = seg_colbase[slot];
+    uint4* data = sell + off + (int64_t)W * HU;
     for (int c = 0; c < nch; ++c) {
-        uint4* chunk = sell + off + (int64_t)c * S::kUnits;
+        uint4* chunk = data + ((int64_t)c * W + w) * S::kUnits;
         int32_t ix[4];
         VT vv[4];
 #pragma unroll

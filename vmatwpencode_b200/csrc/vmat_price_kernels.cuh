@@ -68,7 +68,7 @@ __device__ __forceinline__ double numpy_order_sum(const double* __restrict__ bg,
 }
 
 __global__ void __launch_bounds__(kPriceThreads) k5_price_dp(const PriceArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int kmax = a.kmax;
     double* dbl = reinterpret_cast<double*>(smem_raw);
     PriceNodeSmem S;
