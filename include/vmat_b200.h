@@ -43,7 +43,7 @@ typedef struct vmat_options {
     int32_t k2_threads;     /* threads per CTA of the transposed kernel (0 = default)          */
     int32_t k2_tasks;       /* CTAs of the transposed kernel (0 = default)                     */
     int32_t use_graph;      /* 1: replay the three-kernel evaluation as one CUDA graph         */
-    int32_t reserved[9];
+    int32_t reserved[9];    /* [2]: chunk cap per slice (longer rows get several lanes); 0 = default */
 } vmat_options_t;
 
 /* Library / build identification. */

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvmat_b200.so")
+# VMAT_B200_LIB overrides the library path (A/B comparisons of kernel builds only)
+LIB_PATH = os.environ.get("VMAT_B200_LIB") or os.path.join(_HERE, "libvmat_b200.so")
 
 VMAT_F32, VMAT_BF16, VMAT_F64 = 0, 1, 2
 VMAT_HOST, VMAT_DEVICE = 0, 1

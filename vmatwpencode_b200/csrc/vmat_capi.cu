@@ -50,11 +50,11 @@ struct vmat_plan {
 
     std::vector<int32_t> beam_ptr;
     // K1 layout (stream of super-slices of W1 slices)
-    DevBuf sell1, off1;
+    DevBuf sell1, off1, tpr1;
     int32_t nslices1 = 0, nss1 = 0, W1 = 16, nstages1 = 8, stage_bytes1 = 0;
     int64_t units1 = 0;
     // K2 layout
-    DevBuf sell2, off2, tasks2, cta_ptr2;
+    DevBuf sell2, off2, tpr2, tasks2, cta_ptr2;
     int k2_grid = 1;
     int32_t nslices2 = 0, nss2 = 0, ntasks2 = 0, ntiles = 0, T = 0, W2 = 4, nstages2 = 8, stage_bytes2 = 0;
     int64_t units2 = 0;
@@ -143,15 +143,17 @@ static int upload_vec(DevBuf& dst, const std::vector<Tv>& src, cudaStream_t st) 
 // Build one stream layout from segment descriptors (already grouped in slices of 32, W slices per
 // super-slice).  `tables` (thr/over/under in slice order, element size es) go into the headers.
 static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W, int32_t HU,
-                        const std::vector<int64_t>& ss_off, const std::vector<int64_t>& seg_start,
+                        const std::vector<int64_t>& ss_off, const std::vector<uint8_t>& ss_tpr,
+                        const std::vector<int64_t>& seg_start,
                         const std::vector<int32_t>& seg_len, const std::vector<int32_t>& seg_colbase,
                         const std::vector<int32_t>& rows, const DevBuf* thr, const DevBuf* over, const DevBuf* under,
-                        int32_t es, const int32_t* d_col, const void* d_val, DevBuf& sell, DevBuf& off_d) {
+                        int32_t es, const int32_t* d_col, const void* d_val, DevBuf& sell, DevBuf& off_d, DevBuf& tpr_d) {
     const int32_t nslices = (int32_t)(rows.size() / 32);
     const int64_t units = ss_off.back();
     CU(sell.alloc((size_t)units * 16));
     CU(cudaMemsetAsync(sell.p, 0, (size_t)units * 16, P->stream));
     if (upload_vec(off_d, ss_off, P->stream)) return VMAT_E_CUDA;
+    if (upload_vec(tpr_d, ss_tpr, P->stream)) return VMAT_E_CUDA;
     if (nslices == 0) return 0;
     DevBuf dstart, dlen, dcb, drows;
     if (upload_vec(dstart, seg_start, P->stream)) return VMAT_E_CUDA;
@@ -167,16 +169,63 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
         if (src_dtype == VMAT_F32)
             k_fill_stream<VT, float><<<(unsigned)blocks, threads, 0, P->stream>>>(
                 nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
-                drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const float*>(d_val), sell.as<uint4>());
+                tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const float*>(d_val), sell.as<uint4>());
         else
             k_fill_stream<VT, double><<<(unsigned)blocks, threads, 0, P->stream>>>(
                 nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
-                drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const double*>(d_val), sell.as<uint4>());
+                tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const double*>(d_val), sell.as<uint4>());
     });
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(P->stream));
     return 0;
 }
+
+// Host-side description of a stream: super-slices of W slices; a slice holds 32/tpr rows with tpr
+// lanes per row, where tpr is the smallest power of two that keeps the slice within `cap` chunks.
+struct StreamDesc {
+    int32_t W, HU, units, cap;
+    std::vector<int64_t> ss_off{0}, seg_start;
+    std::vector<uint8_t> ss_tpr;
+    std::vector<int32_t> seg_len, seg_cb, rows, ss_tile;
+    std::vector<int64_t> ss_cost;                 // ring stages (header + chunks) of each super-slice
+    std::vector<double> t_s, o_s, u_s;            // penalty tables in slot order (K1 only)
+    struct Item { int32_t len, id; int64_t start; };
+    // `items` sorted by len descending; appends the super-slices of one group (all voxels / one tile)
+    void add_group(const std::vector<Item>& items, int32_t colbase, int32_t tile,
+                   const double* thr, const double* over, const double* under) {
+        size_t pos = 0;
+        while (pos < items.size()) {
+            const int32_t maxlen = items[pos].len;
+            const int64_t nch1 = (maxlen + 3) / 4;
+            int tpr = 1;
+            while ((nch1 + tpr - 1) / tpr > cap && tpr < 32) tpr *= 2;
+            const int64_t nch = (nch1 + tpr - 1) / tpr;
+            const size_t rows_per_slice = 32 / tpr, rows_per_ss = rows_per_slice * W;
+            const size_t base_slot = seg_start.size();
+            seg_start.resize(base_slot + (size_t)32 * W, 0);
+            seg_len.resize(base_slot + (size_t)32 * W, 0);
+            seg_cb.resize(base_slot + (size_t)32 * W, 0);
+            rows.resize(base_slot + (size_t)32 * W, -1);
+            if (thr) { t_s.resize(base_slot + (size_t)32 * W, 0.0); o_s.resize(base_slot + (size_t)32 * W, 0.0); u_s.resize(base_slot + (size_t)32 * W, 0.0); }
+            for (size_t r = 0; r < rows_per_ss && pos < items.size(); ++r, ++pos) {
+                const Item& it = items[pos];
+                const size_t w = r / rows_per_slice, q = r % rows_per_slice;
+                for (int part = 0; part < tpr; ++part) {
+                    const size_t slot = base_slot + w * 32 + q * tpr + part;
+                    seg_start[slot] = it.start; seg_len[slot] = it.len; seg_cb[slot] = colbase;
+                    if (part == 0) {
+                        rows[slot] = it.id;
+                        if (thr) { t_s[slot] = thr[it.id]; o_s[slot] = over[it.id]; u_s[slot] = under[it.id]; }
+                    }
+                }
+            }
+            ss_tpr.push_back((uint8_t)tpr);
+            ss_tile.push_back(tile);
+            ss_cost.push_back(nch + 1);
+            ss_off.push_back(ss_off.back() + (int64_t)W * HU + nch * (int64_t)W * units);
+        }
+    }
+};
 
 constexpr int kW1 = 16;     // consumer warps (slices per super-slice) of the dose kernel
 constexpr int kW2 = 4;      // ... of the transposed kernel
@@ -265,33 +314,27 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - (h_vrow[v + 1] - h_vrow[v])]++] = (int32_t)v;
         }
         const int32_t W = kW1, HU = 8 + 3 * (32 * es / 16);
-        const int32_t nss = (int32_t)((V + 32 * W - 1) / (32 * W));
-        const int32_t ns = nss * W;
-        std::vector<int64_t> off(nss + 1, 0), seg_start((size_t)ns * 32, 0);
-        std::vector<int32_t> seg_len((size_t)ns * 32, 0), seg_cb((size_t)ns * 32, 0), rows((size_t)ns * 32, -1);
-        std::vector<double> t_s((size_t)ns * 32, 0.0), o_s((size_t)ns * 32, 0.0), u_s((size_t)ns * 32, 0.0);
-        for (int32_t ss = 0; ss < nss; ++ss) {
-            int64_t mx = 0;
-            for (int64_t pos = (int64_t)ss * W * 32; pos < (int64_t)(ss + 1) * W * 32 && pos < V; ++pos) {
-                const int32_t v = order[pos];
-                const int64_t len = h_vrow[v + 1] - h_vrow[v];
-                seg_start[pos] = h_vrow[v]; seg_len[pos] = (int32_t)len; rows[pos] = v;
-                t_s[pos] = thr[v]; o_s[pos] = over[v]; u_s[pos] = under[v];
-                mx = std::max(mx, len);
-            }
-            off[ss + 1] = off[ss] + (int64_t)W * HU + (mx + 3) / 4 * (int64_t)W * units;
+        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2] : 24;
+        StreamDesc sd{W, HU, units, cap};
+        std::vector<StreamDesc::Item> items(V);
+        for (int64_t pos = 0; pos < V; ++pos) {
+            const int32_t v = order[pos];
+            items[pos] = StreamDesc::Item{(int32_t)(h_vrow[v + 1] - h_vrow[v]), v, h_vrow[v]};
         }
-        P->nslices1 = ns; P->nss1 = nss; P->W1 = W; P->units1 = off[nss];
+        sd.add_group(items, 0, 0, thr, over, under);
+        const int32_t nss = (int32_t)sd.ss_tpr.size();
+        P->nslices1 = nss * W; P->nss1 = nss; P->W1 = W; P->units1 = sd.ss_off.back();
         DevBuf thr_s, over_s, under_s;
         int rc = 0;
         DISPATCH_ACC(P->opt.acc_dtype, AT, {
-            rc |= upload_cast<AT>(thr_s, t_s, st);
-            rc |= upload_cast<AT>(over_s, o_s, st);
-            rc |= upload_cast<AT>(under_s, u_s, st);
+            rc |= upload_cast<AT>(thr_s, sd.t_s, st);
+            rc |= upload_cast<AT>(over_s, sd.o_s, st);
+            rc |= upload_cast<AT>(under_s, sd.u_s, st);
         });
         if (rc) return VMAT_E_CUDA;
-        if (int rc2 = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, off, seg_start, seg_len, seg_cb, rows,
-                                   &thr_s, &over_s, &under_s, es, d_vcol, d_vval, P->sell1, P->off1)) return rc2;
+        if (int rc2 = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, sd.ss_off, sd.ss_tpr, sd.seg_start, sd.seg_len,
+                                   sd.seg_cb, sd.rows, &thr_s, &over_s, &under_s, es, d_vcol, d_vval,
+                                   P->sell1, P->off1, P->tpr1)) return rc2;
         P->stage_bytes1 = W * std::max<int>(units, HU) * 16;
     }
     up_vcol.alloc(0); up_vval.alloc(0);   // release the voxel-major CSR copy
@@ -327,38 +370,22 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         CU(cudaStreamSynchronize(st));
         d_seg.alloc(0);
 
-        std::vector<int64_t> off(1, 0), seg_start;
-        std::vector<int32_t> seg_len, seg_cb, rows, ss_tile;
-        std::vector<int64_t> ss_cost;                      // stages (header + chunks) of each super-slice
-        std::vector<std::pair<int32_t, int32_t>> items;   // (len, beamlet)
+        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2] : 24;
+        StreamDesc sd{W, HU, units, cap};
+        std::vector<StreamDesc::Item> items;
         for (int32_t t = 0; t < nt; ++t) {
             items.clear();
             for (int32_t b = 0; b < (int32_t)B; ++b) {
                 const int64_t s0 = segstart[(int64_t)b * (nt + 1) + t], s1 = segstart[(int64_t)b * (nt + 1) + t + 1];
-                if (s1 > s0) items.emplace_back((int32_t)(s1 - s0), b);
+                if (s1 > s0) items.push_back(StreamDesc::Item{(int32_t)(s1 - s0), b, s0});
             }
             std::stable_sort(items.begin(), items.end(),
-                             [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first > b.first; });
-            const size_t per_ss = (size_t)32 * W;
-            for (size_t i0 = 0; i0 < items.size(); i0 += per_ss) {
-                int32_t mx = 0;
-                for (size_t k = 0; k < per_ss; ++k) {
-                    if (i0 + k < items.size()) {
-                        const int32_t len = items[i0 + k].first, b = items[i0 + k].second;
-                        seg_start.push_back(segstart[(int64_t)b * (nt + 1) + t]);
-                        seg_len.push_back(len); seg_cb.push_back(t * T); rows.push_back(b);
-                        mx = std::max(mx, len);
-                    } else {
-                        seg_start.push_back(0); seg_len.push_back(0); seg_cb.push_back(0); rows.push_back(-1);
-                    }
-                }
-                const int64_t nch = (mx + 3) / 4;
-                ss_cost.push_back(nch + 1);
-                ss_tile.push_back(t);
-                off.push_back(off.back() + (int64_t)W * HU + nch * (int64_t)W * units);
-            }
+                             [](const StreamDesc::Item& a, const StreamDesc::Item& b) { return a.len > b.len; });
+            sd.add_group(items, t * T, t, nullptr, nullptr, nullptr);
         }
-        P->nss2 = (int32_t)ss_cost.size(); P->nslices2 = P->nss2 * W; P->units2 = off.back();
+        const std::vector<int64_t>& ss_cost = sd.ss_cost;
+        const std::vector<int32_t>& ss_tile = sd.ss_tile;
+        P->nss2 = (int32_t)ss_cost.size(); P->nslices2 = P->nss2 * W; P->units2 = sd.ss_off.back();
         // Persistent CTAs: the (tile, length)-ordered super-slice sequence is cut into G pieces of
         // equal work; a piece that crosses a tile boundary becomes two tasks of the same CTA.
         int occ = 1;
@@ -392,8 +419,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         }
         if (upload_vec(P->cta_ptr2, cta_ptr, st)) return VMAT_E_CUDA;
         P->ntasks2 = (int32_t)tasks.size();
-        if (int rc = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, off, seg_start, seg_len, seg_cb, rows,
-                                  nullptr, nullptr, nullptr, 0, d_bcol, d_bval, P->sell2, P->off2)) return rc;
+        if (int rc = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, sd.ss_off, sd.ss_tpr, sd.seg_start, sd.seg_len,
+                                  sd.seg_cb, sd.rows, nullptr, nullptr, nullptr, 0, d_bcol, d_bval,
+                                  P->sell2, P->off2, P->tpr2)) return rc;
         if (upload_vec(P->tasks2, tasks, st)) return VMAT_E_CUDA;
     }
     up_bcol.alloc(0); up_bval.alloc(0); up_brow.alloc(0);
@@ -488,7 +516,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
                 (int32_t)P->B, P->y.as<double>(), P->beam_of.as<int32_t>(), P->w_dose.as<AT>(), P->xg.as<AT>());
         }
         K1Args<AT> a1{};
-        a1.sell = P->sell1.as<uint4>(); a1.ss_off = P->off1.as<int64_t>(); a1.nss = P->nss1;
+        a1.sell = P->sell1.as<uint4>(); a1.ss_off = P->off1.as<int64_t>(); a1.ss_tpr = P->tpr1.as<uint8_t>(); a1.nss = P->nss1;
         a1.nstages = P->nstages1; a1.stage_bytes = P->stage_bytes1;
         a1.B = (int32_t)P->B; a1.y = P->y.as<double>(); a1.beam_of = P->beam_of.as<int32_t>();
         a1.w_dose = P->w_dose.as<AT>(); a1.x_global = P->xg.as<AT>();
@@ -505,7 +533,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
         }
         if (ev) CU(cudaEventRecord(ev[1], st));
         K2Args<AT> a2{};
-        a2.sell = P->sell2.as<uint4>(); a2.ss_off = P->off2.as<int64_t>();
+        a2.sell = P->sell2.as<uint4>(); a2.ss_off = P->off2.as<int64_t>(); a2.ss_tpr = P->tpr2.as<uint8_t>();
         a2.tasks = P->tasks2.as<K2Task>(); a2.cta_task_ptr = P->cta_ptr2.as<int32_t>();
         a2.vg = P->vg.as<AT>(); a2.partial = P->partial.as<AT>();
         a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.nstages = P->nstages2; a2.stage_bytes = P->stage_bytes2;

@@ -3,8 +3,10 @@
 //
 // Data layout in HBM ("row-sorted sliced ELL stream"):
 //   * rows (voxels for K1, (tile, beamlet) segments for K2) are sorted by length and cut into
-//     slices of 32 (lane i of a warp owns row i); W consecutive slices form a super-slice that
-//     one CTA processes with W consumer warps in lock step;
+//     slices that one warp processes: 32/tpr rows with tpr lanes per row (tpr = 1 for short rows,
+//     a power of two for long ones, so that no slice is longer than kChunkCap chunks and work
+//     items stay small against an SM's share); W consecutive slices form a super-slice that one
+//     CTA processes with W consumer warps in lock step;
 //   * a super-slice is one contiguous run of the stream: a header (per warp: the 32 row ids and,
 //     for K1, the rows' penalty tables) followed by nch stages; stage c holds chunk c of every
 //     warp; a chunk is 4 nonzeros of each of the warp's 32 rows: 32 int4 index vectors, then
@@ -14,8 +16,8 @@
 //     loads.  The stream is never touched by the LSU global path and no slice boundary stalls it;
 //   * the vector being gathered (x for K1, a tile of vg for K2) is staged in shared memory so
 //     the irregular accesses never leave the SM.
-// Each lane accumulates its row sequentially in storage order: no shuffles, no atomics,
-// bit-reproducible.
+// Each lane accumulates its share of a row sequentially in storage order; the tpr lanes of a row
+// are combined by a fixed butterfly.  No atomics anywhere: bit-reproducible.
 #pragma once
 #include "vmat_common.cuh"
 
@@ -23,7 +25,7 @@ namespace vmat {
 
 constexpr int kStageHeader = 1;     // stage carries the super-slice header
 constexpr int kStageLast = 2;       // last stage of the super-slice: run the epilogue
-struct StageInfo { int32_t ss, flags, tile, pad; };
+struct StageInfo { int32_t ss, flags, tile, tpr; };
 
 // header units (16 B) per warp: 32 row ids (+ thr, over, under as AT for K1)
 template <typename AT> __host__ __device__ constexpr int header_units_k1() { return 8 + 3 * (32 * (int)sizeof(AT) / 16); }
@@ -95,6 +97,7 @@ template <typename AT>
 struct K1Args {
     const uint4* sell;            // stream (voxel-major)
     const int64_t* ss_off;        // [nss+1] in 16-byte units
+    const uint8_t* ss_tpr;        // [nss] lanes per row in this super-slice
     int32_t nss;
     int32_t nstages;              // ring depth
     int32_t stage_bytes;          // ring slot size
@@ -145,13 +148,14 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k1_dose_penalty(const K1Args<
                 int64_t n0 = 0, n1 = 0;
                 if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; }
                 const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
+                const int tpr = a.ss_tpr[cur];
                 ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                          StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0), 0, 0},
+                          StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0), 0, tpr},
                           a.sell + o0, W * HU * 16, pol);
                 const uint4* data = a.sell + o0 + W * HU;
                 for (int c = 0; c < nch; ++c)
                     ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                              StageInfo{(int32_t)cur, c == nch - 1 ? kStageLast : 0, 0, 0},
+                              StageInfo{(int32_t)cur, c == nch - 1 ? kStageLast : 0, 0, tpr},
                               data + (int64_t)c * W * KU, W * KU * 16, pol);
                 cur = nxt; nxt = nn; o0 = n0; o1 = n1;
             }
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k1_dose_penalty(const K1Args<
     AT acc = (AT)0, t = (AT)0, ov = (AT)0, un = (AT)0;
     int32_t row = -1;
     while (true) {
-        mbar_wait(&full[pos.stage], pos.phase);
+        mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
         const StageInfo info = sinfo[pos.stage];
         if (info.ss < 0) break;
         const unsigned char* sp = ring + (size_t)pos.stage * SB;
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k1_dose_penalty(const K1Args<
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[pos.stage]);
         if (info.flags & kStageLast) {
+            for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // tpr lanes of a row
             double fterm = 0.0;
             if (row >= 0) {
                 // (d-t)+ and (t-d)+, objective term, vg = 2*(2*o*over - 2*u*under)  (:255-271)
@@ -216,6 +221,7 @@ template <typename AT>
 struct K2Args {
     const uint4* sell;            // stream (beamlet-major, column-tiled)
     const int64_t* ss_off;        // [nss+1]
+    const uint8_t* ss_tpr;        // [nss]
     const K2Task* tasks;          // (tile, super-slice range), ordered by tile
     const int32_t* cta_task_ptr;  // [gridDim.x+1]: CTA c runs tasks [ptr[c], ptr[c+1])
     const AT* vg;                 // [V + T] (zero padded so a tile copy may run past V)
@@ -258,13 +264,14 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
                 for (int ss = task.ss_begin; ss < task.ss_end; ++ss) {
                     const int64_t o1 = a.ss_off[ss + 1];
                     const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
+                    const int tpr = a.ss_tpr[ss];
                     ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                              StageInfo{ss, kStageHeader | (nch == 0 ? kStageLast : 0), task.tile, 0},
+                              StageInfo{ss, kStageHeader | (nch == 0 ? kStageLast : 0), task.tile, tpr},
                               a.sell + o0, W * HU * 16, pol);
                     const uint4* data = a.sell + o0 + W * HU;
                     for (int c = 0; c < nch; ++c)
                         ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                                  StageInfo{ss, c == nch - 1 ? kStageLast : 0, task.tile, 0},
+                                  StageInfo{ss, c == nch - 1 ? kStageLast : 0, task.tile, tpr},
                                   data + (int64_t)c * W * KU, W * KU * 16, pol);
                     o0 = o1;
                 }
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     int cur_tile = -1;
     uint32_t tparity = 0;
     while (true) {
-        mbar_wait(&full[pos.stage], pos.phase);
+        mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
         const StageInfo info = sinfo[pos.stage];
         if (info.ss < 0) break;
         const unsigned char* sp = ring + (size_t)pos.stage * SB;
@@ -306,7 +313,10 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[pos.stage]);
-        if ((info.flags & kStageLast) && row >= 0) a.partial[(int64_t)cur_tile * a.B + row] = acc;
+        if (info.flags & kStageLast) {
+            for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (row >= 0) a.partial[(int64_t)cur_tile * a.B + row] = acc;
+        }
         pos.advance(nst);
     }
 }
@@ -415,7 +425,8 @@ template <> struct StoreCvt<__nv_bfloat16> {
 template <typename VT, typename ST>
 __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int64_t* __restrict__ ss_off,
                               const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_len,
-                              const int32_t* __restrict__ seg_colbase, const int32_t* __restrict__ rows,
+                              const int32_t* __restrict__ seg_colbase, const uint8_t* __restrict__ ss_tpr,
+                              const int32_t* __restrict__ rows,
                               const unsigned char* __restrict__ thr, const unsigned char* __restrict__ over,
                               const unsigned char* __restrict__ under, int32_t es,
                               const int32_t* __restrict__ col, const ST* __restrict__ val,
@@ -440,6 +451,7 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
     }
     const int64_t st = seg_start[slot];
     const int32_t len = seg_len[slot], cb = seg_colbase[slot];
+    const int tpr = ss_tpr[ss], part = lane % tpr;      // the row's nonzeros go round-robin (4 at a time) over its lanes
     uint4* data = sell + off + (int64_t)W * HU;
     for (int c = 0; c < nch; ++c) {
         uint4* chunk = data + ((int64_t)c * W + w) * S::kUnits;
@@ -447,7 +459,7 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
         VT vv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int e = c * 4 + k;
+            const int e = (c * tpr + part) * 4 + k;
             if (e < len) { ix[k] = col[st + e] - cb; vv[k] = StoreCvt<VT>::cvt(val[st + e]); }
             else         { ix[k] = 0;                vv[k] = StoreCvt<VT>::cvt(0.0f); }
         }
