@@ -225,7 +225,6 @@ def main():
     for _ in range(W):
         ev.eval_async(stream)
     barrier()
-    plan.set_timing(world == 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -234,8 +233,17 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    kt = plan.get_timing() if world == 1 else None
-    plan.set_timing(False)
+    # second pass of the same K steps with a CUDA event after every kernel: the per-kernel
+    # durations behind `roofline` (events between kernels serialise the launches, so this pass
+    # is a little slower than the one `value` comes from)
+    kt = None
+    if world == 1:
+        plan.set_timing(True)
+        for _ in range(K):
+            ev.eval_async(stream)
+        barrier()
+        kt = plan.get_timing()
+        plan.set_timing(False)
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -114,6 +114,11 @@ int vmat_get_timing(vmat_plan_t* plan, double* ms /* 4 */, int32_t* n);
  * caller must sum across ranks between phase 1 and phase 2. */
 int vmat_reduce_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);
 
+/* Device buffers for callers that keep the optimisation loop on the GPU: the intensities the
+ * next vmat_eval_async reads (f64[nb]) and the result the last one wrote (f64[nb+1]: f then g). */
+int vmat_intensities_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);
+int vmat_result_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);
+
 /* Read back state of the last evaluation as f64: data.currentDose (:244-250),
  * data.voxelgradient (:271), and beamGrad of every control point (:646) concatenated. */
 int vmat_get_dose(vmat_plan_t* plan, double* d_out /* V */);

@@ -130,7 +130,8 @@ def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol):
 
 
 @pytest.mark.parametrize("opts", [dict(use_graph=False), dict(tile_voxels=128), dict(tile_voxels=64, k2_tasks=7),
-                                  dict(k1_threads=256), dict(k2_threads=128, k2_tasks=1000)])
+                                  dict(k1_threads=256), dict(k2_threads=128, k2_tasks=1000), dict(pdl=False),
+                                  dict(chunk_cap=2), dict(chunk_cap=1000), dict(tile_voxels=64, chunk_cap=1)])
 def test_plan_options_do_not_change_results(opts):
     case = make_case(V=9000, nb=8, M=4, N=6, density=0.02, seed=71)
     st = O.OracleState(case)
@@ -276,3 +277,45 @@ def test_full_size_config2_properties(acc):
     # aperture gradient is the w_grad-weighted beamlet gradient
     assert relerr(g, np.add.reduceat(w_grad * gb, case.beam_ptr[:-1].astype(np.int64))) <= tol
     plan.close()
+
+
+def test_back_to_back_evaluations_do_not_race():
+    """Evaluations enqueued back to back overlap through programmatic dependent launch (the next
+    kernel's prologue runs while the previous kernel drains).  Alternate two intensity vectors
+    without any host synchronisation and check every result against the single-shot values."""
+    import torch
+    case = make_case(V=60_000, nb=24, M=6, N=8, density=0.01, seed=75)
+    rng = np.random.default_rng(5)
+    y0, w_dose, w_grad = random_weights(case, rng, 0.8)
+    ys = [y0, y0 * 0.37 + 0.2, y0 * 1.9]
+    for acc in ("f32", "f64"):
+        plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc=acc)
+        plan.set_weights(w_dose, w_grad)
+        want = []
+        for y in ys:
+            f, g = plan.eval(y)
+            want.append(np.concatenate([[f], g]))
+        side = torch.cuda.Stream()
+        ydev = [torch.tensor(y, dtype=torch.float64, device="cuda") for y in ys]
+        ybuf, rbuf = plan.intensities_buffer(), plan.result_buffer()
+        n = 90
+        out = torch.zeros((n, case.nb + 1), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            for k in range(n):
+                ybuf.copy_(ydev[k % 3], non_blocking=True)
+                plan.eval_async(side.cuda_stream)
+                out[k].copy_(rbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for k in range(n):
+            assert np.array_equal(got[k], want[k % 3]), (acc, k)
+        # and with nothing between the evaluations at all
+        with torch.cuda.stream(side):
+            ybuf.copy_(ydev[1], non_blocking=True)
+            for k in range(50):
+                plan.eval_async(side.cuda_stream)
+        torch.cuda.synchronize()
+        f, g = plan.fetch_result()
+        assert np.array_equal(np.concatenate([[f], g]), want[1])
+        plan.close()

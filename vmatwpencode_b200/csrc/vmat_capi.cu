@@ -59,10 +59,11 @@ struct vmat_plan {
     int32_t nslices2 = 0, nss2 = 0, ntasks2 = 0, ntiles = 0, T = 0, W2 = 4, nstages2 = 8, stage_bytes2 = 0;
     int64_t units2 = 0;
     // state
-    DevBuf y, beam_of, beam_ptr_d, w_dose, w_grad, xg, d, vg, fpart, partial, gbf, result, counter, scratch64;
+    DevBuf y, beam_of, beam_ptr_d, w_dose, w_grad, xg, d, vg, fpart, fblock, partial, gbf, result, counter, scratch64;
     double* h_y = nullptr;       // pinned
     double* h_res = nullptr;     // pinned
     bool x_in_smem = true;
+    bool pdl = true;               // programmatic dependent launch between the evaluation kernels
     int k1_threads = 1024, k1_grid = 148, k2_threads = 256;
     size_t k1_smem = 0, k2_smem = 0;
     bool evaluated = false;
@@ -245,6 +246,20 @@ static int k2_occupancy(vmat_plan* P, int* occ) {
     return 0;
 }
 
+// launch with programmatic stream serialization: the kernel may begin (prologue up to its
+// griddepcontrol.wait) while its predecessor in the stream is still draining
+template <typename Kern, typename Arg, typename... Rest>
+static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, bool pdl, Arg arg, Rest... rest) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, arg, rest...);
+}
+
 static int capture_graph(vmat_plan* P);
 static int launch_eval(vmat_plan* P, cudaStream_t st, int phase);
 
@@ -273,6 +288,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     if (P->opt.acc_dtype != VMAT_F32 && P->opt.acc_dtype != VMAT_F64) return fail(VMAT_E_ARG, "bad acc_dtype");
     if (P->opt.store_dtype < 0 || P->opt.store_dtype > 2) return fail(VMAT_E_ARG, "bad store_dtype");
     P->acc_size = P->opt.acc_dtype == VMAT_F64 ? 8 : 4;
+    P->pdl = P->opt.reserved[3] == 0;      // reserved[3] = 1 disables programmatic dependent launch
     P->beam_ptr.assign(beam_ptr, beam_ptr + nb + 1);
     CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -446,6 +462,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(P->gbf.alloc((B + 1) * 8));     CU(cudaMemset(P->gbf.p, 0, (B + 1) * 8));
     CU(P->result.alloc((nb + 1) * 8)); CU(cudaMemset(P->result.p, 0, (nb + 1) * 8));
     CU(P->counter.alloc(64));          CU(cudaMemset(P->counter.p, 0, 64));
+    CU(P->fblock.alloc((size_t)std::max(1, P->k2_grid) * 8)); CU(cudaMemset(P->fblock.p, 0, (size_t)std::max(1, P->k2_grid) * 8));
     CU(P->scratch64.alloc(std::max<int64_t>(V, B) * 8));
     CU(cudaMallocHost(&P->h_y, nb * 8));
     CU(cudaMallocHost(&P->h_res, (nb + 1) * 8));
@@ -525,11 +542,11 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
         if (P->x_in_smem) {
             auto kern = k1_dose_penalty<VT, AT, true, kW1>;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
-            kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
+            CU(launch_pdl(kern, P->k1_grid, P->k1_threads, P->k1_smem, st, P->pdl, a1));
         } else {
             auto kern = k1_dose_penalty<VT, AT, false, kW1>;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
-            kern<<<P->k1_grid, P->k1_threads, P->k1_smem, st>>>(a1);
+            CU(launch_pdl(kern, P->k1_grid, P->k1_threads, P->k1_smem, st, P->pdl, a1));
         }
         if (ev) CU(cudaEventRecord(ev[1], st));
         K2Args<AT> a2{};
@@ -538,12 +555,11 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
         a2.vg = P->vg.as<AT>(); a2.partial = P->partial.as<AT>();
         a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.nstages = P->nstages2; a2.stage_bytes = P->stage_bytes2;
         a2.k1_counter = P->counter.as<unsigned int>();
-        if (P->ntasks2 > 0) {
+        a2.fpart = P->fpart.as<double>(); a2.fblock = P->fblock.as<double>(); a2.nfpart = P->nslices1;
+        {   // always launched (even with an empty task list): it also folds the objective partials
             auto kern2 = k2_beamlet_grad<VT, AT, kW2>;
             CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
-            kern2<<<P->k2_grid, (kW2 + 1) * 32, P->k2_smem, st>>>(a2);
-        } else {
-            CU(cudaMemsetAsync(P->counter.p, 0, 4, st));
+            CU(launch_pdl(kern2, P->k2_grid, (kW2 + 1) * 32, P->k2_smem, st, P->pdl, a2));
         }
     }
     if (ev) CU(cudaEventRecord(ev[2], st));
@@ -552,7 +568,8 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase) {
     a3.beam_ptr = P->beam_ptr_d.as<int32_t>(); a3.w_grad = P->w_grad.as<double>();
     a3.fpart = P->fpart.as<double>(); a3.nfpart = P->nslices1; a3.gbf = P->gbf.as<double>();
     a3.result = P->result.as<double>();
-    k3_reduce<AT><<<P->nb + 1, 256, 0, st>>>(a3, phase);
+    a3.fblock = P->fblock.as<double>(); a3.nfblock = P->k2_grid;
+    CU(launch_pdl(k3_reduce<AT>, P->nb, 256, 0, st, P->pdl, a3, phase));
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[3], st));
     return 0;
@@ -689,6 +706,17 @@ extern "C" int vmat_get_timing(vmat_plan_t* P, double* ms, int32_t* n) {
 extern "C" int vmat_reduce_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count) {
     if (!P || !dev_ptr || !count) return fail(VMAT_E_ARG, "null");
     *dev_ptr = P->gbf.p; *count = P->B + 1;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_intensities_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count) {
+    if (!P || !dev_ptr || !count) return fail(VMAT_E_ARG, "null");
+    *dev_ptr = P->y.p; *count = P->nb;
+    return VMAT_OK;
+}
+extern "C" int vmat_result_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count) {
+    if (!P || !dev_ptr || !count) return fail(VMAT_E_ARG, "null");
+    *dev_ptr = P->result.p; *count = P->nb + 1;
     return VMAT_OK;
 }
 

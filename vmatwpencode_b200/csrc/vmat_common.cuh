@@ -66,6 +66,10 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* sr
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  :: "r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
 }
+// programmatic dependent launch: the next kernel of the stream may start its prologue while this
+// one drains; it must wait here before touching anything the previous kernel wrote
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }

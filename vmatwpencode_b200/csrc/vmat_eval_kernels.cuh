@@ -129,10 +129,12 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k1_dose_penalty(const K1Args<
         for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (XS) {   // x_j = y[beam(j)] * w_dose[j]   (K4 folded into the prologue)
         for (int j = tid; j < a.B; j += blockDim.x) xs[j] = mul_rn((AT)a.y[a.beam_of[j]], a.w_dose[j]);
     }
     __syncthreads();
+    pdl_wait();     // d, vg, fpart and the slice counter belong to the previous evaluation until here
 
     if (warp == W) {
         // ---------------- producer: one thread streams super-slices into the ring ----------
@@ -231,6 +233,9 @@ struct K2Args {
     int32_t T;                    // voxels per tile
     int32_t nstages, stage_bytes;
     unsigned int* k1_counter;     // reset here for the next evaluation
+    const double* fpart;          // [nfpart] K1's per-slice objective partials ...
+    double* fblock;               // [gridDim.x] ... folded here into one fixed-order sum per CTA
+    int32_t nfpart;
 };
 
 template <typename VT, typename AT, int W>
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     unsigned char* ring = smem_raw + tbytes;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nst = a.nstages, SB = a.stage_bytes;
-    if (blockIdx.x == 0 && tid == 0) *a.k1_counter = 0u;
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
         mbar_init(&tilebar, 1);
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     __syncthreads();
     const int t_begin = a.cta_task_ptr[blockIdx.x], t_end = a.cta_task_ptr[blockIdx.x + 1];
 
-    if (warp == W) {
+    if (warp == W) {     // the producer streams D (static data) right away; only consumers need K1's vg
         if (lane == 0) {
             const uint64_t pol = l2_evict_first_policy();
             RingPos pos;
@@ -281,6 +286,16 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
         return;
     }
 
+    pdl_wait();          // vg is complete, the previous K3 has consumed `partial`
+    if (blockIdx.x == 0 && tid == 0) *a.k1_counter = 0u;
+    if (warp == 0) {     // objective: this CTA's fixed share of the per-slice partials (order fixed -> reproducible)
+        const int per = (a.nfpart + gridDim.x - 1) / gridDim.x;
+        const int f0 = blockIdx.x * per, f1 = min(a.nfpart, f0 + per);
+        double v = 0.0;
+        for (int k = f0 + lane; k < f1; k += 32) v += a.fpart[k];
+        v = warp_sum(v);
+        if (lane == 0) a.fblock[blockIdx.x] = v;
+    }
     auto gather = [&](uint32_t j) -> AT { return vt[j]; };
     RingPos pos;
     AT acc = (AT)0;
@@ -337,6 +352,8 @@ struct K3Args {
     int32_t nfpart;
     double* gbf;                  // [B+1]: gb then f
     double* result;               // [nb+1]: f then g
+    const double* fblock;         // [nfblock] objective sums of K2's CTAs
+    int32_t nfblock;
 };
 
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
@@ -354,42 +371,67 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
     return r;
 }
 
+// sum of src[first], src[first+stride], ... (< n) in that order; loads are issued in batches of 8
+// so the chain costs one memory round trip per 8 terms instead of one per term
+template <typename T>
+__device__ __forceinline__ double strided_sum(const T* __restrict__ src, int64_t first, int64_t stride, int64_t n) {
+    double s = 0.0;
+    int64_t k = first;
+    for (; k + 7 * stride < n; k += 8 * stride) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[k + u * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    {   // tail (< 8 terms): one more batch of predicated loads instead of a chain of single loads
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (k + u * stride < n) ? src[k + u * stride] : (T)0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (k + u * stride < n) s += (double)v[u];
+    }
+    return s;
+}
+
 template <typename AT>
 __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) {
     __shared__ double sh[256];
     const int tid = threadIdx.x;
-    if ((int)blockIdx.x == a.nb) {      // objective
-        if (phase != 2) {
-            double v = 0.0;
-            for (int k = tid; k < a.nfpart; k += 256) v += a.fpart[k];
-            v = block_sum_256(v, sh);
-            if (tid == 0) a.gbf[a.B] = v;
-            if (tid == 0 && phase == 0) a.result[0] = v;
-        } else if (tid == 0) {
-            a.result[0] = a.gbf[a.B];
-        }
-        return;
-    }
+    pdl_launch_dependents();
     const int lo = a.beam_ptr[blockIdx.x], hi = a.beam_ptr[blockIdx.x + 1];
+    pdl_wait();
+    // objective (block 0): the per-CTA sums K2 left in fblock, added in index order; the loads are
+    // issued before the beamlet loop so that they share its memory round trip
+    double fv = 0.0;
+    if (blockIdx.x == 0 && phase != 2) fv = strided_sum(a.fblock, tid, 256, a.nfblock);
     double contrib = 0.0;
     for (int j0 = lo; j0 < hi; j0 += 64) {
         // 4 threads per beamlet: thread q sums tiles t = q, q+4, ...; combined (q0+q1)+(q2+q3)
         const int j = j0 + (tid >> 2), q = tid & 3;
         double s = 0.0;
+        const double wg = (phase != 1 && j < hi && q == 0) ? a.w_grad[j] : 0.0;
         if (phase != 2) {
-            if (j < hi)
-                for (int t = q; t < a.ntiles; t += 4) s += (double)a.partial[(int64_t)t * a.B + j];
+            if (j < hi) s = strided_sum(a.partial + j, (int64_t)q * a.B, (int64_t)4 * a.B, (int64_t)a.ntiles * a.B);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             if (j < hi && q == 0) a.gbf[j] = s;
         } else if (j < hi) {
             s = a.gbf[j];
         }
-        if (phase != 1 && j < hi && q == 0) contrib += a.w_grad[j] * s;
+        contrib += wg * s;
     }
     if (phase != 1) {
         const double g = block_sum_256(contrib, sh);
         if (tid == 0) a.result[1 + blockIdx.x] = g;
+    }
+    if (blockIdx.x == 0) {
+        if (phase == 2) {
+            if (tid == 0) a.result[0] = a.gbf[a.B];
+        } else {
+            fv = block_sum_256(fv, sh);
+            if (tid == 0) { a.gbf[a.B] = fv; if (phase == 0) a.result[0] = fv; }
+        }
     }
 }
 

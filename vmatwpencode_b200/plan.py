@@ -38,7 +38,7 @@ class DosePlan:
 
     def __init__(self, D, beam_ptr, thr, over, under, device: int = 0, store: str = "f32",
                  acc: str = "f32", tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0,
-                 k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0):
+                 k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True):
         """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
         {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
         lib = _lib.load()
@@ -55,6 +55,7 @@ class DosePlan:
         opt.tile_voxels, opt.k1_threads, opt.k2_threads, opt.k2_tasks = tile_voxels, k1_threads, k2_threads, k2_tasks
         opt.use_graph = 1 if use_graph else 0
         opt.reserved[2] = chunk_cap
+        opt.reserved[3] = 0 if pdl else 1
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         over = np.ascontiguousarray(over, dtype=np.float64)
@@ -166,6 +167,20 @@ class DosePlan:
         p, n = C.c_void_p(), C.c_int64()
         check(self._lib.vmat_reduce_buffer(self._h, C.byref(p), C.byref(n)), "vmat_reduce_buffer")
         return torch.as_tensor(_DeviceArray(p.value, n.value), device=f"cuda:{self.device}")
+
+    def _device_view(self, fn):
+        import torch
+        p, n = C.c_void_p(), C.c_int64()
+        check(fn(self._h, C.byref(p), C.byref(n)), "device buffer")
+        return torch.as_tensor(_DeviceArray(p.value, n.value), device=f"cuda:{self.device}")
+
+    def intensities_buffer(self):
+        """torch view (float64[nb]) of the intensities the next eval_async reads."""
+        return self._device_view(self._lib.vmat_intensities_buffer)
+
+    def result_buffer(self):
+        """torch view (float64[nb+1]: f then g) of what the last eval_async wrote."""
+        return self._device_view(self._lib.vmat_result_buffer)
 
     def dose(self) -> np.ndarray:
         out = np.empty(self.V)
