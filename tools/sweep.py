@@ -28,9 +28,8 @@ def main():
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     variants = json.loads(args.variants) if args.variants else [
-        dict(), dict(chunk_cap=8), dict(chunk_cap=12), dict(chunk_cap=16), dict(chunk_cap=48), dict(chunk_cap=1000),
-        dict(tile_voxels=4096), dict(tile_voxels=4096, chunk_cap=12), dict(tile_voxels=2048),
-        dict(k2_tasks=148 * 2), dict(k2_tasks=148 * 6),
+        dict(), dict(k1_threads=512), dict(chunk_cap=12), dict(chunk_cap=48), dict(tile_voxels=4096),
+        dict(tile_voxels=16384), dict(k2_tasks=148 * 2), dict(k2_tasks=148 * 6),
         dict(store="bf16"), dict(acc="f64"),
     ]
     for v in variants:

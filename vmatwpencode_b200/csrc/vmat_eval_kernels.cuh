@@ -110,18 +110,25 @@ struct K1Args {
     AT* vg;                       // [V] voxel gradient
     double* fpart;                // [nss*W] objective partial of every slice (fixed order -> deterministic)
     unsigned int* counter;        // dynamic super-slice scheduler
+    // host-buffer path (vmat_eval): y is read straight from mapped pinned host memory, mirrored
+    // into the device copy, and the evaluation sequence number is bumped for K3's completion tags
+    double* y_mirror;             // [nb] or nullptr
+    int32_t nb;
+    unsigned long long* seq;      // nullptr on the resident path
 };
 
 template <typename VT, typename AT, bool XS, int W>
-__global__ void __launch_bounds__((W + 1) * 32, 1) k1_dose_penalty(const K1Args<AT> a) {
+__global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT> a) {
     constexpr int KU = Store<VT>::kUnits, HU = header_units_k1<AT>();
     constexpr int kMaxStages = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages];
     __shared__ StageInfo sinfo[kMaxStages];
     const int xbytes = XS ? ((a.B * (int)sizeof(AT) + 127) & ~127) : 0;
+    const int ybytes = XS ? ((a.nb * 8 + 127) & ~127) : 0;
     AT* xs = reinterpret_cast<AT*>(smem_raw);
-    unsigned char* ring = smem_raw + xbytes;
+    double* ys = reinterpret_cast<double*>(smem_raw + xbytes);
+    unsigned char* ring = smem_raw + xbytes + ybytes;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nst = a.nstages, SB = a.stage_bytes;
 
@@ -130,11 +137,22 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k1_dose_penalty(const K1Args<
         fence_barrier_init();
     }
     pdl_launch_dependents();
-    if (XS) {   // x_j = y[beam(j)] * w_dose[j]   (K4 folded into the prologue)
-        for (int j = tid; j < a.B; j += blockDim.x) xs[j] = mul_rn((AT)a.y[a.beam_of[j]], a.w_dose[j]);
+    __syncthreads();                                   // barriers initialised
+    if (warp < W) {
+        if (XS) {   // x_j = y[beam(j)] * w_dose[j]   (K4 folded into the prologue; consumers only -
+                    // the producer is already streaming D meanwhile)
+            // y (possibly in mapped host memory) is read once per CTA into shared memory
+            for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y[j];
+            named_bar_sync(1, W * 32);
+            for (int j = tid; j < a.B; j += W * 32) xs[j] = mul_rn((AT)ys[a.beam_of[j]], a.w_dose[j]);
+            named_bar_sync(1, W * 32);
+        }
     }
-    __syncthreads();
     pdl_wait();     // d, vg, fpart and the slice counter belong to the previous evaluation until here
+    if (a.seq != nullptr && blockIdx.x == 0 && warp < W) {
+        if (XS) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
+        if (tid == 0) atomicAdd(a.seq, 1ull);
+    }
 
     if (warp == W) {
         // ---------------- producer: one thread streams super-slices into the ring ----------
@@ -354,6 +372,11 @@ struct K3Args {
     double* result;               // [nb+1]: f then g
     const double* fblock;         // [nfblock] objective sums of K2's CTAs
     int32_t nfblock;
+    // host-buffer path: results also go to mapped pinned host memory, each slot followed by a tag
+    // (the evaluation sequence number) that the host polls instead of synchronising the stream
+    double* host_result;          // [nb+1] or nullptr
+    volatile unsigned long long* host_tags;   // [nb+1]
+    const unsigned long long* seq;
 };
 
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
@@ -421,16 +444,26 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
         }
         contrib += wg * s;
     }
+    const bool to_host = a.host_result != nullptr && phase == 0;
+    unsigned long long seq = 0;
+    if (to_host && tid == 0) seq = *a.seq;
     if (phase != 1) {
         const double g = block_sum_256(contrib, sh);
-        if (tid == 0) a.result[1 + blockIdx.x] = g;
+        if (tid == 0) {
+            a.result[1 + blockIdx.x] = g;
+            if (to_host) { a.host_result[1 + blockIdx.x] = g; __threadfence_system(); a.host_tags[1 + blockIdx.x] = seq; }
+        }
     }
     if (blockIdx.x == 0) {
         if (phase == 2) {
             if (tid == 0) a.result[0] = a.gbf[a.B];
         } else {
             fv = block_sum_256(fv, sh);
-            if (tid == 0) { a.gbf[a.B] = fv; if (phase == 0) a.result[0] = fv; }
+            if (tid == 0) {
+                a.gbf[a.B] = fv;
+                if (phase == 0) a.result[0] = fv;
+                if (to_host) { a.host_result[0] = fv; __threadfence_system(); a.host_tags[0] = seq; }
+            }
         }
     }
 }
