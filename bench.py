@@ -295,8 +295,12 @@ def main():
             name, kms, kb = ("k2_beamlet_grad", kt["k2_ms"], k2_bytes) if kt["k2_ms"] >= kt["k1_ms"] else \
                             ("k1_dose_penalty", kt["k1_ms"], k1_bytes)
             ach = kb / (kms * 1e-3) / 1e9
+            traffic = None      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
+            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if os.path.isfile(tpath) and args.workload == "cfg2" and args.scale == 1.0 and (args.store, args.acc) == ("f32", "f32"):
+                traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(name)
             line["roofline"] = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                                 "algorithmic_bytes_per_launch": kb, "launch_ms": kms}
             line["kernels_ms"] = {k: kt[k] for k in ("k1_ms", "k2_ms", "k3_ms", "eval_ms")}
             ach_eval = algo / (ms / K * 1e-3) / 1e9
