@@ -283,7 +283,7 @@ def main():
                        "scale": args.scale},
             "e2e": {"value": K / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": case.nb * 8,
                     "d2h_bytes_per_step": (case.nb + 1) * 8, "ms_per_step": 1e3 * e2e_s / K},
-            "gpu_launches": info["launches_per_eval"] * K,
+            "gpu_launches": (info["launches_per_eval"] + (1 if world > 1 else 0)) * K,
             "clocks": clocks,
             "check": {"f": f_res, "g_norm": float(np.linalg.norm(g_res))},
         }
