@@ -319,3 +319,31 @@ def test_back_to_back_evaluations_do_not_race():
         f, g = plan.fetch_result()
         assert np.array_equal(np.concatenate([[f], g]), want[1])
         plan.close()
+
+
+def test_device_generated_case_matches_host_generated_case():
+    """The on-GPU generator + device-CSR plan construction against the host (scipy) route."""
+    import torch
+    from vmatwpencode_b200.synth import make_device_case
+    kw = dict(V=40_000, nb=12, M=5, N=6, density=0.01, seed=77)
+    host = make_case(**kw)
+    dev = make_device_case(**kw)
+    assert dev.nnz == host.nnz
+    D = host.D.tocsr(); D.sort_indices()
+    assert np.array_equal(dev.csr["vrowptr"].cpu().numpy(), D.indptr)
+    assert np.array_equal(dev.csr["vcol"].cpu().numpy(), D.indices)
+    # values agree to the last float32 bit or two (exp/sin/cos differ between CPU and GPU libms)
+    assert np.allclose(dev.csr["vval"].cpu().numpy(), D.data, rtol=3e-7, atol=0)
+    rng = np.random.default_rng(1)
+    y, w_dose, w_grad = random_weights(host, rng, 0.7)
+    Dd = __import__("scipy.sparse", fromlist=["csr_matrix"]).csr_matrix(
+        (dev.csr["vval"].cpu().numpy().astype(np.float64), D.indices, D.indptr), shape=D.shape)
+    host.D = Dd
+    st = O.OracleState(host)
+    f0, g0, d0, vg0, gb0 = O.calc_obj_grad_clean(st, y, w_dose, w_grad)
+    plan = DosePlan(dev.csr, dev.beam_ptr, dev.thr, dev.over, dev.under, store="f32", acc="f64")
+    plan.set_weights(w_dose, w_grad)
+    f, g = plan.eval(y)
+    assert abs(f - f0) <= 1e-11 * abs(f0) and relerr(g, g0) <= 1e-11
+    assert relerr(plan.dose(), d0) <= 1e-11 and relerr(plan.beamlet_grad(), gb0) <= 1e-11
+    plan.close()

@@ -62,3 +62,26 @@ class ShardedEvaluator:
         self.engine.set_intensities(y)
         self.eval_async(stream)
         return self.engine.fetch_result()
+
+
+def slab_of_device(case, rank: int, world: int):
+    """Slab of a DeviceCase (synth.make_device_case): (csr dict of CUDA tensors, thr, over, under)."""
+    import torch
+    c = case.csr
+    if world == 1:
+        return c, case.thr, case.over, case.under
+    b = partition_voxels(c["vrowptr"].cpu().numpy(), world)
+    lo, hi = b[rank], b[rank + 1]
+    vr = c["vrowptr"]
+    p0, p1 = int(vr[lo].item()), int(vr[hi].item())
+    vrowptr = (vr[lo:hi + 1] - vr[lo]).contiguous()
+    vcol, vval = c["vcol"][p0:p1].contiguous(), c["vval"][p0:p1].contiguous()
+    keep = (c["bcol"] >= lo) & (c["bcol"] < hi)
+    B = case.B
+    rows_of = torch.repeat_interleave(torch.arange(B, device=keep.device), torch.diff(c["browptr"]))
+    browptr = torch.zeros(B + 1, dtype=torch.int64, device=keep.device)
+    browptr[1:] = torch.cumsum(torch.bincount(rows_of[keep], minlength=B), 0)
+    bcol = (c["bcol"][keep] - lo).to(torch.int32).contiguous()
+    bval = c["bval"][keep].contiguous()
+    slab = dict(vrowptr=vrowptr, vcol=vcol, vval=vval, browptr=browptr, bcol=bcol, bval=bval)
+    return slab, case.thr[lo:hi], case.over[lo:hi], case.under[lo:hi]

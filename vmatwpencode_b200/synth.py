@@ -340,3 +340,91 @@ def case_from_arrays(z, prefix: str = "case_") -> Case:
                 xinter=np.array(g("xinter")), yinter=np.array(g("yinter")), xdirection=xd, ydirection=yd,
                 D=D, thr=np.array(g("thr")), over=np.array(g("over")), under=np.array(g("under")),
                 struct_id=np.array(g("struct_id")))
+
+
+@dataclass
+class DeviceCase:
+    """A synthetic case whose D lives on the GPU only (both CSR orientations as CUDA tensors);
+    for configurations too large to build through scipy on the host (configs 3-5)."""
+    V: int
+    nb: int
+    M: int
+    N: int
+    beam_ptr: np.ndarray
+    angles: List[int]
+    thr: np.ndarray
+    over: np.ndarray
+    under: np.ndarray
+    csr: dict                   # vrowptr, vcol, vval, browptr, bcol, bval (torch, on device)
+    nnz: int
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def B(self) -> int:
+        return int(self.beam_ptr[-1])
+
+
+def make_device_case(V: int, nb: int, M: int, N: int, density: float = 0.01, seed: int = 0,
+                     model: str = "geometric", val_dtype: str = "f32", gastep: Optional[int] = None,
+                     rich_structures: bool = False, device: str = "cuda", **_ignored) -> DeviceCase:
+    """Same cases as make_case (full M x N beamlet rectangles), generated and sorted on the GPU."""
+    if gastep is None:
+        gastep = max(1, 360 // nb)
+    angles = [gastep * i for i in range(nb)]
+    B = nb * M * N
+    beam_ptr = (np.arange(nb + 1, dtype=np.int64) * (M * N)).astype(np.int32)
+    keys, vals = [], []
+    if model == "geometric":
+        per_hit = 2.0 - 1.0 / (2 * N)
+        frac = min(density * M * N / per_hit, 0.7)
+        for i in range(nb):
+            rows, mrow, ncol, v = beam_entries(i, angles[i], V, M, N, frac, seed, device)
+            col = i * M * N + mrow * N + ncol
+            keys.append(rows * B + col)
+            vals.append(_round_to(v, val_dtype).to(torch.float32 if val_dtype != "f64" else torch.float64))
+        key = torch.cat(keys); val = torch.cat(vals)
+        del keys, vals
+    elif model == "uniform":
+        nnz_target = int(round(density * V * B))
+        k = torch.arange(nnz_target, dtype=torch.int64, device=device)
+        rows_t = (_hash01(k, k * 0 + 11, seed) * V).to(torch.int64).clamp_(max=V - 1)
+        cols_t = (_hash01(k, k * 0 + 13, seed + 1) * B).to(torch.int64).clamp_(max=B - 1)
+        key = torch.unique(rows_t * B + cols_t)
+        del rows_t, cols_t, k
+        val = _round_to(0.05 + _hash01(key // B, key % B, seed + 2), val_dtype).to(
+            torch.float32 if val_dtype != "f64" else torch.float64)
+    else:
+        raise ValueError(model)
+    # voxel-major: sort by (row, col)
+    key, order = torch.sort(key)
+    vval = val[order]
+    del order, val
+    rows = key // B
+    vcol = (key - rows * B).to(torch.int32)
+    vrowptr = torch.zeros(V + 1, dtype=torch.int64, device=device)
+    vrowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=V), 0)
+    # beamlet-major: sort by (col, row)
+    key2 = vcol.to(torch.int64) * V + rows
+    del key, rows
+    key2, order = torch.sort(key2)
+    bval = vval[order]
+    del order
+    cols = key2 // V
+    bcol = (key2 - cols * V).to(torch.int32)
+    browptr = torch.zeros(B + 1, dtype=torch.int64, device=device)
+    browptr[1:] = torch.cumsum(torch.bincount(cols, minlength=B), 0)
+    del key2, cols
+    sid, table = structures(V, M, device=device, rich=rich_structures)
+    thr, over, under = penalty_tables(sid, table)
+    nnz = int(vcol.numel())
+    return DeviceCase(V=V, nb=nb, M=M, N=N, beam_ptr=beam_ptr, angles=angles,
+                      thr=thr.cpu().numpy(), over=over.cpu().numpy(), under=under.cpu().numpy(),
+                      csr=dict(vrowptr=vrowptr, vcol=vcol, vval=vval, browptr=browptr, bcol=bcol, bval=bval),
+                      nnz=nnz, meta=dict(model=model, density=nnz / (V * B), seed=seed, gastep=gastep))
+
+
+def make_device_config(name: str, scale: float = 1.0, **overrides) -> DeviceCase:
+    cfg = dict(CONFIGS[name])
+    cfg.update(overrides)
+    cfg["V"] = max(64, int(cfg["V"] * scale))
+    return make_device_case(**cfg)
