@@ -114,6 +114,16 @@ int vmat_get_timing(vmat_plan_t* plan, double* ms /* 4 */, int32_t* n);
  * caller must sum across ranks between phase 1 and phase 2. */
 int vmat_reduce_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);
 
+/*
+ * Multi-GPU exchange without NCCL: every rank exports the CUDA IPC handle of its comm buffer
+ * (vmat_comm_handle, 64 bytes), the caller gathers the handles of all ranks (any transport) and
+ * hands them to vmat_comm_attach.  From then on vmat_eval_async(phase 0) / vmat_eval run the
+ * reduction kernel fused with a one-shot all-reduce over peer memory (NVLink), summing the ranks
+ * in rank order, and phases 1/2 are not needed.  All ranks must evaluate in lock step.
+ */
+int vmat_comm_handle(vmat_plan_t* plan, void* handle_out /* 64 bytes */);
+int vmat_comm_attach(vmat_plan_t* plan, int32_t rank, int32_t nranks, const void* handles /* nranks*64 bytes */);
+
 /* Device buffers for callers that keep the optimisation loop on the GPU: the intensities the
  * next vmat_eval_async reads (f64[nb]) and the result the last one wrote (f64[nb+1]: f then g). */
 int vmat_intensities_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);

@@ -66,6 +66,10 @@ struct vmat_plan {
     double *d_hy = nullptr, *d_hres = nullptr;          // device views of the mapped host buffers
     unsigned long long* d_htags = nullptr;
     unsigned long long host_seq = 0;
+    // fused cross-GPU exchange (vmat_comm_attach)
+    DevBuf comm_buf, comm_ptrs, comm_state;
+    std::vector<void*> comm_peers;        // opened IPC mappings (own slot = nullptr)
+    int comm_rank = 0, comm_nranks = 1;
     int host_path = 2;             // bit0: K1 reads y from mapped host memory; bit1: K3 publishes results + tags to host memory
     bool x_in_smem = true;
     bool pdl = true;               // programmatic dependent launch between the evaluation kernels
@@ -87,6 +91,7 @@ struct vmat_plan {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
         for (auto e : tev) cudaEventDestroy(e);
+        for (void* q : comm_peers) if (q) cudaIpcCloseMemHandle(q);
         if (h_y) cudaFreeHost(h_y);
         if (h_res) cudaFreeHost(h_res);
         if (h_tags) cudaFreeHost(h_tags);
@@ -506,6 +511,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(P->counter.alloc(64));          CU(cudaMemset(P->counter.p, 0, 64));
     CU(P->fblock.alloc((size_t)std::max(1, P->k2_grid) * 8)); CU(cudaMemset(P->fblock.p, 0, (size_t)std::max(1, P->k2_grid) * 8));
     CU(P->scratch64.alloc(std::max<int64_t>(V, B) * 8));
+    CU(P->comm_buf.alloc((2 * (size_t)(B + 1) + 64) * 8));  CU(cudaMemset(P->comm_buf.p, 0, (2 * (size_t)(B + 1) + 64) * 8));
+    CU(P->comm_state.alloc(64));         CU(cudaMemset(P->comm_state.p, 0, 64));
     CU(cudaHostAlloc(&P->h_y, nb * 8, cudaHostAllocMapped));
     CU(cudaHostAlloc(&P->h_res, (nb + 1) * 8, cudaHostAllocMapped));
     CU(cudaHostAlloc(&P->h_tags, (nb + 1) * 8, cudaHostAllocMapped));
@@ -624,6 +631,16 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
     a3.fpart = P->fpart.as<double>(); a3.nfpart = P->nslices1; a3.gbf = P->gbf.as<double>();
     a3.result = P->result.as<double>();
     a3.fblock = P->fblock.as<double>(); a3.nfblock = P->k2_grid;
+    if (P->comm_nranks > 1 && phase == 0) {
+        CommArgs c{};
+        c.peer_bufs = P->comm_ptrs.as<double*>(); c.rank = P->comm_rank; c.nranks = P->comm_nranks;
+        c.epoch = P->comm_state.as<unsigned long long>(); c.done = P->comm_state.as<unsigned int>() + 4;
+        c.error = P->comm_state.as<int32_t>() + 8;
+        CU(launch_pdl(k3_reduce_exchange<AT>, P->nb, 256, 0, st, P->pdl, a3, c));
+        CU(cudaGetLastError());
+        if (ev) CU(cudaEventRecord(ev[3], st));
+        return 0;
+    }
     if (host_mode && (P->host_path & 2)) { a3.host_result = P->d_hres; a3.host_tags = P->d_htags; a3.seq = P->counter.as<unsigned long long>() + 4; }
     CU(launch_pdl(k3_reduce<AT>, P->nb, 256, 0, st, P->pdl, a3, phase));
     CU(cudaGetLastError());
@@ -685,20 +702,31 @@ extern "C" int vmat_set_intensities(vmat_plan_t* P, const double* y) {
     return VMAT_OK;
 }
 
+static int check_comm(vmat_plan* P) {
+    if (P->comm_nranks <= 1) return 0;
+    int32_t st[16];
+    CU(cudaMemcpy(st, P->comm_state.p, 64, cudaMemcpyDeviceToHost));
+    if (st[8] != 0) return fail(VMAT_E_CUDA, "multi-GPU exchange timed out: a peer rank did not evaluate in lock step");
+    return 0;
+}
+
 extern "C" int vmat_eval(vmat_plan_t* P, const double* y, double* f, double* g) {
     if (!P || !y) return fail(VMAT_E_ARG, "vmat_eval: null");
     CU(cudaSetDevice(P->device));
     std::memcpy(P->h_y, y, P->nb * 8);
+    const bool multi = P->comm_nranks > 1;            // fused exchange: plain copies, no host tags
+    const bool zc_y = (P->host_path & 1) && !multi, zc_res = (P->host_path & 2) && !multi;
     const unsigned long long expect = ++P->host_seq;
-    if (P->graph_exec) {
+    if (P->graph_exec && !multi) {
         CU(cudaGraphLaunch(P->graph_exec, P->stream));
     } else {
-        if (!(P->host_path & 1)) CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
-        if (int rc = launch_eval(P, P->stream, 0, true)) return rc;
-        if (!(P->host_path & 2)) CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream));
+        if (!zc_y) CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
+        if (int rc = launch_eval(P, P->stream, 0, !multi)) return rc;
+        if (!zc_res) CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream));
     }
-    if (!(P->host_path & 2)) {
+    if (!zc_res) {
         CU(cudaStreamSynchronize(P->stream));
+        if (int rc = check_comm(P)) return rc;
         P->evaluated = true;
         if (f) *f = P->h_res[0];
         if (g) std::memcpy(g, P->h_res + 1, P->nb * 8);
@@ -741,6 +769,7 @@ extern "C" int vmat_fetch_result(vmat_plan_t* P, double* f, double* g) {
     CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost));
+    if (int rc = check_comm(P)) return rc;
     if (f) *f = P->h_res[0];
     if (g) std::memcpy(g, P->h_res + 1, P->nb * 8);
     return VMAT_OK;
@@ -787,6 +816,43 @@ extern "C" int vmat_get_timing(vmat_plan_t* P, double* ms, int32_t* n) {
 extern "C" int vmat_reduce_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count) {
     if (!P || !dev_ptr || !count) return fail(VMAT_E_ARG, "null");
     *dev_ptr = P->gbf.p; *count = P->B + 1;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_comm_handle(vmat_plan_t* P, void* handle_out) {
+    if (!P || !handle_out) return fail(VMAT_E_ARG, "null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(P->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, P->comm_buf.p));
+    std::memcpy(handle_out, &h, 64);
+    return VMAT_OK;
+}
+
+extern "C" int vmat_comm_attach(vmat_plan_t* P, int32_t rank, int32_t nranks, const void* handles) {
+    if (!P || !handles || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return fail(VMAT_E_ARG, "vmat_comm_attach: bad argument");
+    CU(cudaSetDevice(P->device));
+    CU(cudaDeviceSynchronize());
+    for (void* q : P->comm_peers) if (q) cudaIpcCloseMemHandle(q);
+    P->comm_peers.assign(nranks, nullptr);
+    std::vector<double*> ptrs(nranks, nullptr);
+    for (int q = 0; q < nranks; ++q) {
+        if (q == rank) { ptrs[q] = P->comm_buf.as<double>(); continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + (size_t)q * 64, 64);
+        void* mapped = nullptr;
+        CU(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+        P->comm_peers[q] = mapped;
+        ptrs[q] = static_cast<double*>(mapped);
+    }
+    if (upload_vec(P->comm_ptrs, ptrs, P->stream)) return VMAT_E_CUDA;
+    CU(cudaMemset(P->comm_buf.p, 0, P->comm_buf.bytes));
+    CU(cudaMemset(P->comm_state.p, 0, 64));
+    P->comm_rank = rank; P->comm_nranks = nranks;
+    // the captured graph (if any) holds the single-GPU reduction: rebuild it
+    if (P->graph_exec) { cudaGraphExecDestroy(P->graph_exec); P->graph_exec = nullptr; }
+    if (P->graph) { cudaGraphDestroy(P->graph); P->graph = nullptr; }
+    CU(cudaDeviceSynchronize());
     return VMAT_OK;
 }
 

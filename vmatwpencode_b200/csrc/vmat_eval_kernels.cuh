@@ -469,6 +469,116 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
 }
 
 // ---------------------------------------------------------------------------------
+// K3 fused with the cross-GPU exchange (multi-GPU, one rank per GPU).  Every rank owns a
+// "comm buffer" in its HBM that all peers have mapped (CUDA IPC over NVLink):
+//     [parity 0: gb partial (B) | f partial] [parity 1: ...] [flags: one epoch counter per rank]
+// Each rank writes its local [gb | f] partial into its own buffer, publishes the evaluation's
+// epoch to every peer's flag slot (system-scope release), waits until all peers have published,
+// then every CTA reads the partials of all ranks for its beamlets straight from peer memory and
+// adds them in rank order - a one-shot all-reduce inside the reduction kernel: no NCCL launch,
+// identical bits on every rank.  Two parities make the buffer safe to rewrite in the next
+// evaluation while a slow peer may still be reading this one.
+// ---------------------------------------------------------------------------------
+struct CommArgs {
+    double* const* peer_bufs;     // [nranks] device pointers to every rank's comm buffer (own included)
+    int32_t rank, nranks;
+    unsigned long long* epoch;    // completed evaluations on this rank
+    unsigned int* done;           // [2] block counters (reset by the last block)
+    int32_t* error;               // set when a peer did not show up within the time-out
+};
+
+__device__ __forceinline__ double ld_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <typename AT>
+__global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, const CommArgs c) {
+    __shared__ double sh[256];
+    __shared__ int ok_s;
+    const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    const int lo = a.beam_ptr[blockIdx.x], hi = a.beam_ptr[blockIdx.x + 1];
+    pdl_wait();
+    const unsigned long long e = *c.epoch + 1;
+    const size_t stride = (size_t)a.B + 1;
+    const size_t par_off = (size_t)(e & 1ull) * stride;
+    double* mine = c.peer_bufs[c.rank] + par_off;
+    // ---- A: this rank's partial for my beamlets (and the objective) into my comm buffer
+    if (blockIdx.x == 0) {
+        double fv = strided_sum(a.fblock, tid, 256, a.nfblock);
+        fv = block_sum_256(fv, sh);
+        if (tid == 0) mine[a.B] = fv;
+    }
+    for (int j0 = lo; j0 < hi; j0 += 64) {
+        const int j = j0 + (tid >> 2), q = tid & 3;
+        double s = 0.0;
+        if (j < hi) s = strided_sum(a.partial + j, (int64_t)q * a.B, (int64_t)4 * a.B, (int64_t)a.ntiles * a.B);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (j < hi && q == 0) mine[j] = s;
+    }
+    __syncthreads();
+    // ---- B: the last CTA publishes this rank's epoch to every peer; everybody waits for all peers
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&c.done[0], 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            for (int q = 0; q < c.nranks; ++q) {
+                unsigned long long* flags = reinterpret_cast<unsigned long long*>(c.peer_bufs[q] + 2 * stride);
+                st_release_sys_u64(flags + c.rank, e);
+            }
+        }
+        const unsigned long long* myflags = reinterpret_cast<const unsigned long long*>(c.peer_bufs[c.rank] + 2 * stride);
+        int ok = 1;
+        const long long t0 = clock64();
+        for (int q = 0; q < c.nranks && ok; ++q) {
+            while (ld_acquire_sys_u64(myflags + q) < e) {
+                if (clock64() - t0 > 4000000000ll) { ok = 0; break; }      // ~2 s: a peer is gone
+            }
+        }
+        if (!ok) *c.error = 1;
+        ok_s = ok;
+    }
+    __syncthreads();
+    // ---- C: sum the partials of all ranks, in rank order, straight from peer memory
+    double contrib = 0.0;
+    if (ok_s) {
+        for (int j = lo + tid; j < hi; j += 256) {
+            double s = 0.0;
+            for (int q = 0; q < c.nranks; ++q) s += ld_sys_f64(c.peer_bufs[q] + par_off + j);
+            a.gbf[j] = s;
+            contrib += a.w_grad[j] * s;
+        }
+    }
+    const double g = block_sum_256(contrib, sh);
+    if (tid == 0) a.result[1 + blockIdx.x] = ok_s ? g : nan("");
+    if (blockIdx.x == 0 && tid == 0) {
+        double f = 0.0;
+        for (int q = 0; q < c.nranks; ++q) f += ld_sys_f64(c.peer_bufs[q] + par_off + a.B);
+        a.gbf[a.B] = f;
+        a.result[0] = ok_s ? f : nan("");
+    }
+    // ---- the last CTA to leave closes the evaluation
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&c.done[1], 1u) == gridDim.x - 1) {
+            *c.epoch = e;
+            c.done[0] = 0u; c.done[1] = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // layout construction (plan build time)
 // ---------------------------------------------------------------------------------
 // first position in each beamlet row whose voxel id is >= t*T, for t = 0..ntiles

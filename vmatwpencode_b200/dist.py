@@ -42,15 +42,27 @@ class ShardedEvaluator:
     reduce_buffer / fetch_result); `group` a torch.distributed process group (NCCL on GPUs;
     gloo with a host engine in the CPU tests)."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, fused: bool = True):
+        """`fused=True` (GPU engines only): exchange over peer memory inside the reduction kernel
+        (vmat_comm_attach) instead of an NCCL all-reduce between two kernel phases."""
         import torch.distributed as dist
         self.engine = engine
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.fused = False
+        if fused and self.world > 1 and hasattr(engine, "comm_handle"):
+            import torch
+            rank = dist.get_rank(group)
+            mine = torch.tensor(list(engine.comm_handle()), dtype=torch.uint8, device=f"cuda:{engine.device}")
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine, group=group)
+            engine.comm_attach(rank, self.world, b"".join(bytes(h.cpu().tolist()) for h in allh))
+            dist.barrier(group)
+            self.fused = True
 
     def eval_async(self, stream=None):
-        if self.world == 1:
+        if self.world == 1 or self.fused:
             self.engine.eval_async(stream, 0)
             return
         self.engine.eval_async(stream, 1)                 # local dose, penalty, partial [gb | f]

@@ -169,6 +169,21 @@ class DosePlan:
         check(self._lib.vmat_reduce_buffer(self._h, C.byref(p), C.byref(n)), "vmat_reduce_buffer")
         return torch.as_tensor(_DeviceArray(p.value, n.value), device=f"cuda:{self.device}")
 
+    def comm_handle(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's exchange buffer."""
+        buf = (C.c_ubyte * 64)()
+        check(self._lib.vmat_comm_handle(self._h, buf), "vmat_comm_handle")
+        return bytes(buf)
+
+    def comm_attach(self, rank: int, nranks: int, handles: bytes):
+        """Map every rank's exchange buffer; from now on evaluations all-reduce over peer memory
+        inside the reduction kernel.  Every rank must attach before any rank evaluates."""
+        if len(handles) != 64 * nranks:
+            raise VmatError("need one 64-byte IPC handle per rank")
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        check(self._lib.vmat_comm_attach(self._h, rank, nranks, buf), "vmat_comm_attach")
+        self.fused_exchange = nranks > 1
+
     def _device_view(self, fn):
         import torch
         p, n = C.c_void_p(), C.c_int64()
