@@ -351,3 +351,85 @@ def test_device_generated_case_matches_host_generated_case():
     assert abs(f - f0) <= 1e-11 * abs(f0) and relerr(g, g0) <= 1e-11
     assert relerr(plan.dose(), d0) <= 1e-11 and relerr(plan.beamlet_grad(), gb0) <= 1e-11
     plan.close()
+
+
+def test_all_zero_matrix_and_single_row_grid():
+    """Degenerate inputs: D without any nonzero, and a 2 x 1 beamlet grid (the smallest the
+    reference can price: with one beamlet per control point its DoseSide index runs off beamGrad)."""
+    import scipy.sparse as sp
+    case = make_case(V=700, nb=3, M=2, N=1, density=0.3, seed=76)
+    Z = sp.csr_matrix((case.V, case.B))
+    plan = DosePlan(Z, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc="f64")
+    plan.set_weights(np.ones(case.B), np.ones(case.B))
+    f, g = plan.eval(np.ones(case.nb))
+    assert abs(f - float(np.sum(case.under * case.thr ** 2))) <= 1e-12 * max(f, 1e-300) and np.all(g == 0)
+    plan.close()
+    st = O.OracleState(case)
+    data = vl.bind(case, store="f32", acc="f64")
+    for state in (st, data):
+        all_candidates(state, case)
+    O.calc_obj_grad_literal(st, np.zeros(case.nb))
+    vl.calcObjGrad(np.zeros(case.nb))
+    got = vl.PricingProblem(0.1, 1.0, 1.0, 0.5, 2.25, 0.83, case.N, case.M, 0.5)
+    want = O.pricing_problem(st, 0.1, 1.0, 1.0, 0.5, 2.25, 0.83, case.N, case.M, 0.5)
+    assert got[3] == want[3] and [int(v) for v in got[1]] == want[1] and [int(v) for v in got[2]] == want[2]
+    data.plan.close()
+
+
+@pytest.mark.parametrize("acc,nb", [("f32", 460), ("f64", 230)])
+def test_beamlet_vector_larger_than_shared_memory(acc, nb):
+    """With enough beamlets x no longer fits next to the ring in shared memory: the dose kernel
+    falls back to gathering x from global memory (a separate expansion kernel writes it)."""
+    case = make_case(V=3000, nb=nb, M=8, N=16, density=0.002, seed=78, gastep=1)
+    assert case.B * (4 if acc == "f32" else 8) > 227 * 1024
+    st = O.OracleState(case)
+    y, w_dose, w_grad = random_weights(case, np.random.default_rng(3), 0.6)
+    f0, g0, d0, vg0, gb0 = O.calc_obj_grad_clean(st, y, w_dose, w_grad)
+    plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc=acc)
+    assert plan.info()["launches_per_eval"] == 4
+    plan.set_weights(w_dose, w_grad)
+    f, g = plan.eval(y)
+    tol = TOL[acc]
+    assert abs(f - f0) <= tol * abs(f0) and relerr(g, g0) <= tol
+    assert relerr(plan.dose(), d0) <= tol and relerr(plan.beamlet_grad(), gb0) <= tol
+    plan.close()
+
+
+def test_pricing_wide_rows():
+    """40 beamlets per leaf row: 861 nodes per network row, dose sums in the pairwise regime."""
+    case = make_case(V=5000, nb=4, M=4, N=40, density=0.02, seed=79, gastep=10)
+    st = O.OracleState(case)
+    data = vl.bind(case, store="f32", acc="f64")
+    for state in (st, data):
+        all_candidates(state, case)
+    select(st, case, 1, [3, 5, 10, 2], [30, 25, 33, 18], lambda k: O.update_open_aperture(st, k))
+    select(data, case, 1, [3, 5, 10, 2], [30, 25, 33, 18], vl.updateOpenAperture)
+    y = np.zeros(case.nb); y[1] = 1.0
+    O.calc_obj_grad_literal(st, y.copy())
+    vl.calcObjGrad(y.copy())
+    for C, vmax in [(0.0, 2.25), (0.05, 2.25), (0.05, 0.6)]:
+        for i0 in st.notinC.loc:
+            p0, l0, r0, _ = O.price_candidate(st, i0, C, 1.0, 1.0, 0.5, vmax, 0.83, case.N, case.M, 0.5)
+            p, l, r, _ = vl.parallelizationPricingProblem(i0, C, 1.0, 1.0, 0.5, vmax, 0.83, case.N, case.M, 0.5)
+            assert [int(v) for v in l] == l0 and [int(v) for v in r] == r0, (C, vmax, i0)
+            assert abs(p - p0) <= 1e-10 * max(1.0, abs(p0))
+    data.plan.close()
+
+
+def test_kmedoid_costs_tree_path_and_voxel_points():
+    """More than 4096 points takes the fixed-shape tree; with integer coordinates on a line the
+    distances are integers, so the result is exact whatever the order."""
+    from vmatwpencode_b200.plan import kmedoid_costs
+    n = 5000
+    pts = np.arange(n, dtype=float)
+    cur = np.abs(pts - 1234.0)
+    cost = kmedoid_costs(pts.reshape(-1, 1), cur)
+    for c in (0, 17, 2500, 4999):
+        assert cost[c] == float(np.minimum(cur, np.abs(pts - pts[c])).sum())
+    rng = np.random.default_rng(8)
+    P = rng.random((6000, 3))
+    cur = np.sqrt(((P - P[5]) ** 2).sum(axis=1))
+    cost = kmedoid_costs(P, cur)
+    for c in (1, 3000):
+        want = np.minimum(cur, np.sqrt(((P - P[c]) ** 2).sum(axis=1))).sum()
+        assert abs(cost[c] - want) <= 1e-12 * want
