@@ -80,9 +80,9 @@ def eval_and_price_fixture(name, case, selected, y, price_settings):
     print(name, "f =", float(f), "candidates", len(data.notinC.loc))
 
 
-def colgen_fixture(name, case, C, kappasize, max_iter):
-    ns = R.reference_namespace(case)
-    hist = R.ref_colgen(ns, case, C=C, kappasize=kappasize, max_iter=max_iter)
+def colgen_fixture(name, case, C, kappasize, max_iter, elimination=False, module="greedyVMATsampling"):
+    ns = R.reference_namespace(case, module)
+    hist = R.ref_colgen(ns, case, C=C, kappasize=kappasize, max_iter=max_iter, elimination=elimination)
     out = case_to_arrays(case)
     out["C"] = np.float64(C)
     out["kappasize"] = np.int64(kappasize)
@@ -93,6 +93,13 @@ def colgen_fixture(name, case, C, kappasize, max_iter):
     out["pstar"] = np.asarray([h["pstar"] for h in hist])
     out["x"] = np.asarray([h["x"] for h in hist])
     out["fun"] = np.asarray([h["fun"] for h in hist])
+    out["elimination"] = np.bool_(elimination)
+    out["removed_flat"] = np.asarray([k for h in hist for k in h["removed"]], dtype=np.int64)
+    out["removed_count"] = np.asarray([len(h["removed"]) for h in hist], dtype=np.int64)
+    if module.endswith("Laptop"):      # Kelly measure the reference stored for the control points still selected
+        pw = ns["penalizationweights"]
+        out["kelly_idx"] = np.asarray([k for k, v in enumerate(pw) if v is not None], dtype=np.int64)
+        out["kelly"] = np.asarray([float(v) for v in pw if v is not None])
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
     print(name, "iterations", len(hist), "sequence", [h["idx"] for h in hist])
 
@@ -158,6 +165,8 @@ def main():
     colgen_fixture("colgen_A", make_case(V=2500, nb=12, M=5, N=6, density=0.04, seed=31, gastep=10), 0.02, 5, 10)
     colgen_fixture("colgen_B", make_case(V=2000, nb=18, M=4, N=7, density=0.04, seed=32, gastep=2, ragged=True), 0.0, 6, 12)
     colgen_fixture("colgen_C", make_case(V=2000, nb=36, M=3, N=5, density=0.05, seed=33, gastep=1), 0.5, 8, 14)
+    colgen_fixture("colgen_E", make_case(V=2500, nb=14, M=4, N=6, density=0.04, seed=35, gastep=10), 0.01, 5, 14,
+                   elimination=True, module="greedyVMATsamplingLaptop")
     kmedoids_fixture()
 
 

@@ -27,10 +27,11 @@ from scipy.optimize import minimize
 
 REFERENCE_ROOT = os.environ.get("VMAT_REFERENCE_ROOT", "/root/reference")
 
+_HOT = ["region", "apertureList", "vmat_class", "calcObjGrad", "fvalidbeamlets", "PPsubroutine",
+        "parallelizationPricingProblem", "PricingProblem", "solveRMC", "updateOpenAperture"]
 WANTED = {
-    "greedyVMATsampling": ["region", "apertureList", "vmat_class", "calcObjGrad", "fvalidbeamlets",
-                           "PPsubroutine", "parallelizationPricingProblem", "solveRMC",
-                           "updateOpenAperture"],
+    "greedyVMATsampling": _HOT,
+    "greedyVMATsamplingLaptop": _HOT,
     "kmedoids": ["distancemin", "listdiff", "insertnewelement", "givemewholelist"],
 }
 
@@ -59,8 +60,27 @@ def extract(module: str, names=None) -> dict:
             if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
     if module == "kmedoids":
         keep = [n for n in tree.body if isinstance(n, ast.ImportFrom) and n.module == "scipy.spatial"] + keep
+    from functools import partial
+
+    class SerialPool:
+        """Stand-in for multiprocessing.Pool so that the reference's own PricingProblem runs here
+        (its pool is created under ``if __name__ == '__main__'``, hence __name__ below)."""
+
+        def __init__(self, processes=None):
+            pass
+
+        def map(self, fn, it):
+            return [fn(x) for x in it]
+
+        def close(self):
+            pass
+
+        def join(self):
+            pass
+
     ns = {"np": _numpy_shim(), "sparse": sparse, "math": math, "time": time, "random": random,
-          "sys": sys, "minimize": minimize, "__name__": "reference_extract"}
+          "sys": sys, "minimize": minimize, "__name__": "__main__", "Pool": SerialPool, "partial": partial,
+          "numcores": 1}
     exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
     return ns
 
@@ -101,6 +121,7 @@ def reference_namespace(case, module: str = "greedyVMATsampling") -> dict:
     ns["quadHelperUnder"] = np.array(case.under)
     ns["N"] = case.N
     ns["M"] = case.M
+    ns["penalizationweights"] = [None] * case.nb      # Laptop variant: Kelly measure per control point
     return ns
 
 
@@ -118,7 +139,7 @@ def ref_pricing_problem(ns, C, C2, C3, b, vmax, speedlim, N, M, bw):
 
 
 def ref_colgen(ns, case, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vmax=2.25,
-               speedlim=0.83, bw=0.5, RU=10.0):
+               speedlim=0.83, bw=0.5, RU=10.0, elimination=False, threshold=10E-3):
     """The reference's colGen loop (greedyVMATsampling.py:937-1046) driven over the
     reference's own functions, without its plotting / pickle side effects.
     Returns the list of (bestApertureIndex, l, r, pstar, rmp.x copy, rmp.fun)."""
@@ -136,7 +157,8 @@ def ref_colgen(ns, case, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vma
     while (pstar < 0) and (data.notinC.len() > 0):
         data.calcDose()
         data.calcGradientandObjValue()
-        pstar, lm, rm, best, _ = ref_pricing_problem(ns, C, C2, C3, b, vmax, speedlim, case.N, case.M, bw)
+        with quiet():      # the reference's own PricingProblem, its Pool replaced by a serial map
+            pstar, lm, rm, best = ns["PricingProblem"](C, C2, C3, b, vmax, speedlim, case.N, case.M, bw)
         if pstar >= 0:
             break
         data.caligraphicC.insertAngle(best, data.notinC(best))
@@ -152,9 +174,24 @@ def ref_colgen(ns, case, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vma
                 warnings.simplefilter("ignore")
                 res = ns["solveRMC"](YU)
         data.rmpres = res
+        removed = []                                   # elimination phase (:1007-1033)
+        for k in range(case.nb):
+            if k in data.caligraphicC.loc and (res.x[k] < threshold) and elimination:
+                data.entryCounter += 1
+                removed.append(k)
+                data.notinC.insertAngle(k, data.pointtoAngle[k])
+                data.caligraphicC.removeIndex(k)
+        stop = False
+        prev = data.listIndexofAperturesRemovedEachStep
+        if len(prev) > 1 and (np.any(np.isin(removed, prev[-1])) or np.any(np.isin(removed, prev[-2]))):
+            stop = True
+        if not stop:
+            prev.append(removed)
         history.append(dict(idx=int(best), l=[int(v) for v in lm], r=[int(v) for v in rm],
                             pstar=float(pstar), x=np.array(res.x, dtype=float), fun=float(res.fun),
-                            nit=int(res.nit), nfev=int(res.nfev)))
+                            nit=int(res.nit), nfev=int(res.nfev), removed=list(removed)))
+        if stop:
+            break
         while not data.notinC.isEmpty():
             kappa.append(data.notinC.loc[0])
             data.notinC.removeIndex(data.notinC.loc[0])

@@ -94,6 +94,7 @@ class OracleState:
         self.objectiveValue = float("inf")
         self.notinC = ApertureSet()
         self.caligraphicC = ApertureSet()
+        self.removed_each_step = []                    # listIndexofAperturesRemovedEachStep
         # global ("clean") form: one V x B matrix and two beamlet weight vectors
         self.D = case.D
         self.beam_ptr = np.asarray(case.beam_ptr, dtype=np.int64)
@@ -113,6 +114,26 @@ class OracleState:
                 np.add.at(w_dose, lo + oam, np.asarray(self.strengths[i], dtype=float))
             w_grad[lo:lo + len(self.diagmakers[i])] = self.diagmakers[i]
         return w_dose, w_grad
+
+
+def quad_helpers(functionData, regions, numvoxels, priority=None):
+    """quadHelperThresh/Over/Under as the reference builds them at load time
+    (greedyVMATsampling.py:554-576): per structure s (after the priority reordering) the
+    weights are divided by the structure size, then written voxel by voxel."""
+    fd = np.array([float(v) for v in np.ravel(functionData)]).reshape(3, -1)
+    if priority is not None:
+        fd = fd[:, priority]
+    for s in range(fd.shape[1]):
+        if regions[s].sizeInVoxels > 0:
+            fd[1, s] = fd[1, s] * 1 / regions[s].sizeInVoxels
+            fd[2, s] = fd[2, s] * 1 / regions[s].sizeInVoxels
+    thr, over, under = np.zeros(numvoxels), np.zeros(numvoxels), np.zeros(numvoxels)
+    for s in range(fd.shape[1]):
+        for j in range(regions[s].sizeInVoxels):
+            thr[int(regions[s].indices[j])] = fd[0][s]
+            over[int(regions[s].indices[j])] = fd[1][s]
+            under[int(regions[s].indices[j])] = fd[2][s]
+    return thr, over, under
 
 
 # --------------------------------------------------------------------------
@@ -412,8 +433,24 @@ def solve_rmc(st: OracleState, YU, evaluator=None):
                         options={"ftol": 1e-1, "maxiter": 200})
 
 
+def kelly_measure(l, r):
+    """Aperture complexity (perimeter / area) of leaf vectors l, r
+    (greedyVMATsamplingLaptop.py:850-862, inside its PricingProblem)."""
+    area = 0.0
+    perimeter = r[0] - l[0] + np.sign(r[0] - l[0])
+    for n in range(len(l)):
+        area += 0.5 * (r[n] - l[n]) * 0.5
+    for n in range(1, len(l)):
+        area += 0.5 * (r[n] - l[n]) * 0.5
+        perimeter += np.sign(r[n] - l[n])
+        perimeter += (np.abs(l[n] - l[n - 1]) + np.abs(r[n] - r[n - 1]) - 2 * np.maximum(0, l[n - 1] - r[n])
+                      - 2 * np.maximum(0, l[n] - r[n - 1]))
+    perimeter += r[len(r) - 1] - l[len(l) - 1] + np.sign(r[len(r) - 1] - l[len(l) - 1])
+    return perimeter / area
+
+
 def col_gen(st: OracleState, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vmax=2.25,
-            speedlim=0.83, bw=0.5, RU=10.0, clean=False):
+            speedlim=0.83, bw=0.5, RU=10.0, clean=False, elimination=False, threshold=10E-3):
     """colGen (greedyVMATsampling.py:937-1046, non-WholeCircle branch) without plots/pickle.
     Returns the greedy history: per iteration idx, l, r, pstar, x, fun."""
     YU = RU / speedlim
@@ -442,9 +479,22 @@ def col_gen(st: OracleState, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5,
         st.llist[best], st.rlist[best] = lm, rm
         st.openApertureMaps[best], st.diagmakers[best], st.strengths[best] = update_open_aperture(st, best)
         res = solve_rmc(st, YU, evaluator)
+        removed = []                                                               # :1007-1033
+        for k in range(st.numbeams):
+            if k in st.caligraphicC.loc and (res.x[k] < threshold) and elimination:
+                removed.append(k)
+                st.notinC.insertAngle(k, st.pointtoAngle[k])
+                st.caligraphicC.removeIndex(k)
+        prev = st.removed_each_step
+        stop = len(prev) > 1 and bool(np.any(np.isin(removed, prev[-1])) or np.any(np.isin(removed, prev[-2])))
+        if not stop:
+            prev.append(removed)
         history.append(dict(idx=int(best), l=list(lm), r=list(rm), pstar=float(pstar),
                             x=np.array(res.x, dtype=float), fun=float(res.fun),
-                            nit=int(res.nit), nfev=int(res.nfev)))
+                            nit=int(res.nit), nfev=int(res.nfev), removed=list(removed),
+                            kelly=float(kelly_measure(lm, rm))))
+        if stop:
+            break
         while not st.notinC.isEmpty():                                             # :1037-1039
             kappa.append(st.notinC.loc[0])
             st.notinC.removeIndex(st.notinC.loc[0])

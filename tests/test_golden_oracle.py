@@ -63,19 +63,35 @@ def test_fallback_midpoints_are_exercised():
     assert hit > 0
 
 
-@pytest.mark.parametrize("name", ["colgen_A", "colgen_B", "colgen_C"])
+@pytest.mark.parametrize("name", ["colgen_A", "colgen_B", "colgen_C", "colgen_E"])
 def test_colgen_sequence_matches_reference(name):
+    """Greedy sequences recorded from the reference's own PricingProblem / updateOpenAperture /
+    solveRMC (colgen_E: Laptop variant with the elimination phase switched on)."""
     z, case = load_golden(name)
     st = O.OracleState(case)
-    hist = O.col_gen(st, C=float(z["C"]), kappasize=int(z["kappasize"]), max_iter=int(z["max_iter"]))
+    elim = bool(z["elimination"])
+    hist = O.col_gen(st, C=float(z["C"]), kappasize=int(z["kappasize"]), max_iter=int(z["max_iter"]), elimination=elim)
     assert [h["idx"] for h in hist] == list(z["idx"])
+    assert [len(h["removed"]) for h in hist] == list(z["removed_count"])
+    assert [k for h in hist for k in h["removed"]] == list(z["removed_flat"])
+    if elim:
+        assert int(z["removed_count"].sum()) > 0, "fixture no longer exercises the elimination phase"
+    if "kelly" in z.files:      # Kelly measure of the control points still selected at the end
+        last = {}
+        for h in hist:
+            last[h["idx"]] = h["kelly"]
+            for k in h["removed"]:
+                last.pop(k, None)
+        assert sorted(last) == list(z["kelly_idx"])
+        assert [last[k] for k in sorted(last)] == list(z["kelly"])
     for h, l, r, p, x, fun in zip(hist, z["l"], z["r"], z["pstar"], z["x"], z["fun"]):
         assert h["l"] == list(l) and h["r"] == list(r)
         assert h["pstar"] == p and h["fun"] == fun
         assert np.array_equal(h["x"], x)
     # the global-form evaluation drives the same greedy sequence
     st2 = O.OracleState(case)
-    hist2 = O.col_gen(st2, C=float(z["C"]), kappasize=int(z["kappasize"]), max_iter=int(z["max_iter"]), clean=True)
+    hist2 = O.col_gen(st2, C=float(z["C"]), kappasize=int(z["kappasize"]), max_iter=int(z["max_iter"]), clean=True,
+                      elimination=elim)
     assert [h["idx"] for h in hist2] == list(z["idx"])
     for h, l, r in zip(hist2, z["l"], z["r"]):
         assert h["l"] == list(l) and h["r"] == list(r)

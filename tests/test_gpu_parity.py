@@ -73,13 +73,22 @@ def test_pricing_against_reference_fixture(name):
     data.plan.close()
 
 
-@pytest.mark.parametrize("name", ["colgen_A", "colgen_B", "colgen_C"])
+@pytest.mark.parametrize("name", ["colgen_A", "colgen_B", "colgen_C", "colgen_E"])
 def test_greedy_sequence_against_reference_fixture(name):
     z, case = load_golden(name)
     data = vl.bind(case, store="f32", acc="f64")
-    vl.colGen(float(z["C"]), False, int(z["kappasize"]), max_iter=int(z["max_iter"]))
+    vl.eliminationPhase = bool(z["elimination"])
+    try:
+        vl.colGen(float(z["C"]), False, int(z["kappasize"]), max_iter=int(z["max_iter"]))
+    finally:
+        vl.eliminationPhase = False
     hist = data.history
     assert [h["idx"] for h in hist] == list(z["idx"])
+    assert [k for h in hist for k in h["removed"]] == list(z["removed_flat"])
+    if "kelly" in z.files:
+        got = {k: v for k, v in enumerate(vl.penalizationweights) if v is not None}
+        assert sorted(got) == list(z["kelly_idx"])
+        assert np.allclose([got[k] for k in sorted(got)], z["kelly"], rtol=1e-14, atol=0)
     for h, l, r, p, x, fun in zip(hist, z["l"], z["r"], z["pstar"], z["x"], z["fun"]):
         assert h["l"] == list(l) and h["r"] == list(r)          # bit-exact leaf positions
         assert abs(h["pstar"] - p) <= 1e-9 * abs(p)

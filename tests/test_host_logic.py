@@ -165,3 +165,26 @@ def test_kernel_algorithm_twin_matches_oracle_on_random_states():
                 bg = st.Dlist[i0] @ st.voxelgradient
                 p, l, r = emulate_price(rows, M, C, 1.0, 1.0, 0.5, bg)
                 assert (l, r) == (l0, r0) and p == p0, (seed, C, vmax, i0)
+
+
+def test_kelly_measure_vs_oracle():
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        m = int(rng.integers(1, 9))
+        l = [int(rng.integers(-1, 10)) for _ in range(m)]
+        r = [lv + int(rng.integers(1, 8)) for lv in l]
+        assert abs(vl.kelly_measure(l, r) - O.kelly_measure(l, r)) <= 1e-14 * abs(O.kelly_measure(l, r))
+
+
+def test_quad_helpers_vs_oracle():
+    rng = np.random.default_rng(13)
+    nv, ns = 500, 6
+    owner = rng.integers(0, ns, size=nv)
+    regions = [vl.region(s, np.flatnonzero(owner == s), np.flatnonzero(owner == s), s < 2) for s in range(ns)]
+    regions[3] = vl.region(3, np.array([], dtype=int), np.array([], dtype=int), False)     # an empty structure
+    fd = rng.random(3 * ns) * 10
+    prio = rng.permutation(ns).tolist()
+    a = vl.quadHelpers(fd, regions, nv, prio)
+    b = O.quad_helpers(fd, regions, nv, prio)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

@@ -42,8 +42,10 @@ N = None          # beamlets per leaf row  (len(data.yinter), :466)
 M = None          # leaf rows              (len(data.xinter), :468)
 kappa = []        # candidate ordering used by the WholeCircle branch (:30,959-966)
 eliminationThreshold = 10E-3
+eliminationPhase = False     # the reference hard-codes False inside colGen (:940); settable here
 kappasize = 16
 numcores = 8
+penalizationweights = []     # Kelly complexity measure per selected control point (Laptop variant :484,863)
 
 
 class region:
@@ -262,6 +264,27 @@ def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool 
     return d
 
 
+def quadHelpers(functionData, regions, numvoxels, priority=None):
+    """Per-voxel quadHelperThresh / quadHelperOver / quadHelperUnder from the 3 x numstructs
+    objective table (thresholds, over-weights, under-weights) and the structures' voxel lists
+    (greedyVMATsampling.py:554-576): columns reordered by `priority`, weights divided by the
+    structure's size, later structures overwrite earlier ones where voxel lists overlap."""
+    fd = np.array(functionData, dtype=float).reshape(3, -1)
+    if priority is not None:
+        fd = fd[:, priority]
+    thr = np.zeros(numvoxels)
+    over = np.zeros(numvoxels)
+    under = np.zeros(numvoxels)
+    for s, reg in enumerate(regions):
+        n = reg.sizeInVoxels
+        if n > 0:
+            idx = np.asarray(reg.indices, dtype=np.int64)
+            thr[idx] = fd[0, s]
+            over[idx] = fd[1, s] * 1 / n
+            under[idx] = fd[2, s] * 1 / n
+    return thr, over, under
+
+
 def calcObjGrad(x, user_data=None):
     """(objective, aperture gradient) at intensities x (greedyVMATsampling.py:578-582)."""
     data.currentIntensities = x
@@ -400,8 +423,24 @@ def PricingProblem(C, C2, C3, b, vmax, speedlim, N, M, bw):
     for k in range(len(cands)):
         if M != len(l[k]):
             sys.exit("Length of left vector is less than 28")
+    if len(penalizationweights) == data.numbeams:         # Laptop variant bookkeeping (:863)
+        penalizationweights[cands[indstar][0]] = kelly_measure(l[indstar], r[indstar])
     return (np.float64(p[indstar]), [np.int64(v) for v in l[indstar]], [np.int64(v) for v in r[indstar]],
             cands[indstar][0])
+
+
+def kelly_measure(l, r):
+    """Aperture complexity perimeter / area of leaf vectors (l, r): Kelly's measure as computed
+    inside the Laptop variant's PricingProblem (greedyVMATsamplingLaptop.py:850-862)."""
+    l = np.asarray(l, dtype=float)
+    r = np.asarray(r, dtype=float)
+    width = r - l
+    area = 0.25 * (width.sum() + width[1:].sum())
+    edge = np.sign(width)
+    perimeter = width[0] + edge[0] + width[-1] + edge[-1] + edge[1:].sum()
+    step = (np.abs(np.diff(l)) + np.abs(np.diff(r)) - 2 * np.maximum(0, l[:-1] - r[1:])
+            - 2 * np.maximum(0, l[1:] - r[:-1]))
+    return (perimeter + step.sum()) / area
 
 
 def updateOpenAperture(i):
@@ -463,10 +502,10 @@ def colGen(C, WholeCircle, initialApertures, max_iter=None):
     """Greedy column generation (greedyVMATsampling.py:937-1061): price, add the best
     aperture, re-optimise intensities, resample candidates; returns pstar.  Each step is
     appended to data.history.  (`max_iter` is an addition for bounded test runs.)"""
-    global kappa
+    global kappa, penalizationweights
     C2 = 1.0
     C3 = 1.0
-    eliminationPhase = False
+    penalizationweights = [None] * data.numbeams
     vmax = 2.25
     speedlim = 0.83
     beamletwidth = 0.5
@@ -506,15 +545,18 @@ def colGen(C, WholeCircle, initialApertures, max_iter=None):
                     removed.append(thisindex)
                     data.notinC.insertAngle(thisindex, data.pointtoAngle[thisindex])
                     data.caligraphicC.removeIndex(thisindex)
+                    penalizationweights[thisindex] = None
+        data.history.append(dict(idx=int(bestApertureIndex), l=[int(v) for v in lm], r=[int(v) for v in rm],
+                                 pstar=float(pstar), x=np.array(rmpres.x, dtype=float), fun=float(rmpres.fun),
+                                 nit=int(rmpres.nit), nfev=int(rmpres.nfev), removed=list(removed),
+                                 kelly=float(kelly_measure(lm, rm))))
         if len(data.listIndexofAperturesRemovedEachStep) > 1:
+            # the same aperture keeps entering and leaving: stop (:1020-1031)
             if np.any(np.isin(removed, data.listIndexofAperturesRemovedEachStep[-1])):
                 break
             if np.any(np.isin(removed, data.listIndexofAperturesRemovedEachStep[-2])):
                 break
         data.listIndexofAperturesRemovedEachStep.append(removed)
-        data.history.append(dict(idx=int(bestApertureIndex), l=[int(v) for v in lm], r=[int(v) for v in rm],
-                                 pstar=float(pstar), x=np.array(rmpres.x, dtype=float), fun=float(rmpres.fun),
-                                 nit=int(rmpres.nit), nfev=int(rmpres.nfev)))
         while not data.notinC.isEmpty():
             kappa.append(data.notinC.loc[0])
             data.notinC.removeIndex(data.notinC.loc[0])
