@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--k2-tasks", type=int, default=0)
     ap.add_argument("--k2-threads", type=int, default=0)
     ap.add_argument("--k1-threads", type=int, default=0)
+    ap.add_argument("--index-bytes", type=int, default=0, help="4 forces int32 column indices (default: uint16 when they fit)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -212,7 +213,7 @@ def main():
         rows, D, thr, over, under = slab_of(case, rank, world)
     plan = DosePlan(D, case.beam_ptr, thr, over, under, device=local, store=args.store, acc=args.acc,
                     tile_voxels=args.tile, k2_tasks=args.k2_tasks, k2_threads=args.k2_threads,
-                    k1_threads=args.k1_threads)
+                    k1_threads=args.k1_threads, index_bytes=args.index_bytes)
     if args.workload in DEVICE_WORKLOADS:      # the CSR copies are no longer needed: the plan holds its own layouts
         case.csr = None
         del D
@@ -293,9 +294,9 @@ def main():
             "config": {"workload": f"{args.workload}: {case.V} voxels x {case.B} beamlets, {case.nb} control points, "
                                    f"nnz {case.nnz} ({100.0 * case.nnz / (case.V * case.B):.2f} % dense), geometric sparsity",
                        "nnz_this_rank": nnz_local,
-                       "store_dtype": args.store, "acc_dtype": args.acc, "sharding": f"voxel slabs x{world}",
+                       "store_dtype": args.store, "acc_dtype": args.acc, "index_bytes": info["index_bytes"], "sharding": f"voxel slabs x{world}",
                        "l2": "both layouts of D (2 x ~%d MB) exceed the 126 MB L2; no flush between steps"
-                             % (nnz_local * (sv + 4) // 1_000_000),
+                             % (nnz_local * (sv + info["index_bytes"]) // 1_000_000),
                        "scale": args.scale},
             "e2e": {"value": K / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": case.nb * 8,
                     "d2h_bytes_per_step": (case.nb + 1) * 8, "ms_per_step": 1e3 * e2e_s / K},
@@ -306,14 +307,16 @@ def main():
         algo = info["algorithmic_bytes_per_eval"]
         if kt is not None and kt["n"] > 0:
             # dominant kernel: whichever of K1 (dose+penalty) / K2 (transposed) is slower
-            k1_bytes = nnz_local * (sv + 4) + 4 * (plan.V + 1) + 12 * plan.V + 8 * plan.V + 4 * plan.B
-            k2_bytes = nnz_local * (sv + 4) + 4 * plan.V + 4 * (plan.B + 1) + 4 * plan.B
+            si = info["index_bytes"]
+            k1_bytes = nnz_local * (sv + si) + 4 * (plan.V + 1) + 12 * plan.V + 8 * plan.V + 4 * plan.B
+            k2_bytes = nnz_local * (sv + si) + 4 * plan.V + 4 * (plan.B + 1) + 4 * plan.B
             name, kms, kb = ("k2_beamlet_grad", kt["k2_ms"], k2_bytes) if kt["k2_ms"] >= kt["k1_ms"] else \
                             ("k1_dose_penalty", kt["k1_ms"], k1_bytes)
             ach = kb / (kms * 1e-3) / 1e9
             traffic = None      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
             tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-            if os.path.isfile(tpath) and args.workload == "cfg2" and args.scale == 1.0 and (args.store, args.acc) == ("f32", "f32"):
+            if os.path.isfile(tpath) and args.workload == "cfg2" and args.scale == 1.0 and \
+                    (args.store, args.acc, info["index_bytes"]) == ("f32", "f32", json.load(open(tpath)).get("index_bytes", 4)):
                 traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(name)
             line["roofline"] = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,

@@ -43,7 +43,8 @@ typedef struct vmat_options {
     int32_t k2_threads;     /* threads per CTA of the transposed kernel (0 = default)          */
     int32_t k2_tasks;       /* CTAs of the transposed kernel (0 = default)                     */
     int32_t use_graph;      /* 1: replay the three-kernel evaluation as one CUDA graph         */
-    int32_t reserved[9];    /* [2]: chunk cap per slice (longer rows get several lanes); 0 = default */
+    int32_t reserved[9];    /* [5]: 4 forces int32 column indices (default: uint16 whenever they fit) */
+                            /* [2]: chunk cap per slice (longer rows get several lanes); 0 = default */
 } vmat_options_t;
 
 /* Library / build identification. */
@@ -71,10 +72,11 @@ int vmat_plan_create(vmat_plan_t** plan, int device, int64_t V, int64_t B, int32
                      const vmat_options_t* opt);
 int vmat_plan_destroy(vmat_plan_t* plan);
 
-/* Bytes of HBM one evaluation must move for this plan's layouts, and the SURVEY 8(d)
- * algorithmic figure 2*nnz*(s_v+4) + 28V + 12B for the same matrix. */
+/* Bytes of HBM one evaluation must move for this plan's layouts (padding and headers included),
+ * the SURVEY 8(d) algorithmic figure 2*nnz*(s_v+s_i) + 28V + 12B for the same matrix with this
+ * plan's index width s_i, kernel launches per evaluation, and s_i itself (2 = uint16, 4 = int32). */
 int vmat_plan_info(const vmat_plan_t* plan, int64_t* nnz, int64_t* layout_bytes_per_eval,
-                   int64_t* algorithmic_bytes_per_eval, int32_t* launches_per_eval);
+                   int64_t* algorithmic_bytes_per_eval, int32_t* launches_per_eval, int32_t* index_bytes);
 
 /*
  * Set the two beamlet weight vectors of control point `beam` (length beam_ptr[beam+1]-

@@ -28,9 +28,8 @@ def main():
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     variants = json.loads(args.variants) if args.variants else [
-        dict(), dict(k1_threads=512), dict(chunk_cap=12), dict(chunk_cap=48), dict(tile_voxels=4096),
-        dict(tile_voxels=16384), dict(k2_tasks=148 * 2), dict(k2_tasks=148 * 6),
-        dict(store="bf16"), dict(acc="f64"),
+        dict(), dict(index_bytes=4), dict(tile_voxels=4096), dict(tile_voxels=16384), dict(chunk_cap=16), dict(chunk_cap=32),
+        dict(store="bf16"), dict(acc="f64"), dict(store="bf16", index_bytes=4),
     ]
     for v in variants:
         v = dict(v)
@@ -52,7 +51,7 @@ def main():
         t = plan.get_timing()
         ms = e0.elapsed_time(e1) / args.steps
         sv = {"f32": 4, "bf16": 2, "f64": 8}[store]
-        kb = info["nnz"] * (sv + 4) / 1e9
+        kb = info["nnz"] * (sv + info["index_bytes"]) / 1e9
         print(json.dumps(dict(variant=dict(v, store=store, acc=acc), step_ms=round(ms, 5),
                               k1_ms=round(t["k1_ms"], 5), k2_ms=round(t["k2_ms"], 5), k3_ms=round(t["k3_ms"], 5),
                               k1_GBps=round(kb / t["k1_ms"] * 1e3, 1), k2_GBps=round(kb / t["k2_ms"] * 1e3, 1),

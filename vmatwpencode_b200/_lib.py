@@ -49,7 +49,7 @@ SIGNATURES = {
                                    _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(Options)]),
     "vmat_plan_destroy": (C.c_int, [_P]),
     "vmat_plan_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
-                                 C.POINTER(C.c_int32)]),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vmat_set_aperture": (C.c_int, [_P, C.c_int32, _P, _P]),
     "vmat_eval": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     "vmat_set_intensities": (C.c_int, [_P, _P]),

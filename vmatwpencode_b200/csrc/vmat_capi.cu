@@ -46,6 +46,7 @@ struct vmat_plan {
     size_t acc_size = 4;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    int iw = 4;                    // bytes per stored column index: 2 (uint16) when every index fits, else 4
     int smem_optin = 0;
 
     std::vector<int32_t> beam_ptr;
@@ -119,6 +120,8 @@ extern "C" void vmat_default_options(vmat_options_t* o) {
         case VMAT_F64:  { using VT = double; __VA_ARGS__; break; }           \
         default: return fail(VMAT_E_ARG, "bad store dtype");                 \
     }
+#define DISPATCH_IW(IW, ...)                                                 \
+    if (P->iw == 2) { constexpr int IW = 2; __VA_ARGS__; } else { constexpr int IW = 4; __VA_ARGS__; }
 #define DISPATCH_ACC(dt, AT, ...)                                            \
     switch (dt) {                                                            \
         case VMAT_F32: { using AT = float; __VA_ARGS__; break; }             \
@@ -129,7 +132,7 @@ extern "C" void vmat_default_options(vmat_options_t* o) {
 template <typename VT> struct Unroll { static constexpr int U = 4; };
 template <> struct Unroll<double> { static constexpr int U = 2; };
 
-static int store_units(int dt) { return dt == VMAT_F32 ? 64 : dt == VMAT_BF16 ? 48 : 96; }
+static int store_units(int dt, int iw) { return 8 * iw + (dt == VMAT_F32 ? 32 : dt == VMAT_BF16 ? 16 : 64); }
 static int store_bytes(int dt) { return dt == VMAT_F32 ? 4 : dt == VMAT_BF16 ? 2 : 8; }
 
 template <typename AT>
@@ -177,16 +180,16 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
     const unsigned char* t0 = thr ? thr->as<unsigned char>() : nullptr;
     const unsigned char* t1 = over ? over->as<unsigned char>() : nullptr;
     const unsigned char* t2 = under ? under->as<unsigned char>() : nullptr;
-    DISPATCH_STORE(store_dtype, VT, {
+    DISPATCH_STORE(store_dtype, VT, { DISPATCH_IW(IW, {
         if (src_dtype == VMAT_F32)
-            k_fill_stream<VT, float><<<(unsigned)blocks, threads, 0, P->stream>>>(
+            k_fill_stream<VT, float, IW><<<(unsigned)blocks, threads, 0, P->stream>>>(
                 nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
                 tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const float*>(d_val), sell.as<uint4>());
         else
-            k_fill_stream<VT, double><<<(unsigned)blocks, threads, 0, P->stream>>>(
+            k_fill_stream<VT, double, IW><<<(unsigned)blocks, threads, 0, P->stream>>>(
                 nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
                 tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const double*>(d_val), sell.as<uint4>());
-    });
+    }); });
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(P->stream));
     return 0;
@@ -245,9 +248,11 @@ constexpr int kW2 = 4;      // ... of the transposed kernel
 
 template <typename VT, typename AT>
 static int k2_occupancy_t(vmat_plan* P, int* occ) {
-    auto kern = k2_beamlet_grad<VT, AT, kW2>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, (kW2 + 1) * 32, P->k2_smem));
+    DISPATCH_IW(IW, {
+        auto kern = k2_beamlet_grad<VT, AT, kW2, IW>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, (kW2 + 1) * 32, P->k2_smem));
+    });
     if (*occ < 1) return fail(VMAT_E_ARG, "transposed kernel does not fit on an SM with these options");
     return 0;
 }
@@ -256,17 +261,17 @@ static int k2_occupancy_t(vmat_plan* P, int* occ) {
 
 template <typename VT, typename AT>
 static int k1_occupancy_t(vmat_plan* P, int* occ) {
-    DISPATCH_W1(W, {
+    DISPATCH_IW(IW, { DISPATCH_W1(W, {
         if (P->x_in_smem) {
-            auto kern = k1_dose_penalty<VT, AT, true, W>;
+            auto kern = k1_dose_penalty<VT, AT, true, W, IW>;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, P->k1_threads, P->k1_smem));
         } else {
-            auto kern = k1_dose_penalty<VT, AT, false, W>;
+            auto kern = k1_dose_penalty<VT, AT, false, W, IW>;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, P->k1_threads, P->k1_smem));
         }
-    });
+    }); });
     if (*occ < 1) return fail(VMAT_E_ARG, "dose kernel does not fit on an SM with these options");
     return 0;
 }
@@ -332,11 +337,16 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaDeviceGetAttribute(&P->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaStream_t st = P->stream;
+    {   // index width: uint16 when every stored index fits (x index < B; K2 indices are tile-local, < T)
+        const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : (P->opt.acc_dtype == VMAT_F64 ? 4096 : 8192);
+        const bool fits16 = B <= 65536 && ((T0 + 63) / 64 * 64) <= 65536;
+        P->iw = (P->opt.reserved[5] == 4 || !fits16) ? 4 : 2;      // reserved[5] = 4 forces int32 indices
+    }
     {   // dose-kernel CTA shape
         const size_t as0 = P->acc_size;
         const size_t xy = (((size_t)B * as0 + 127) & ~(size_t)127) + (((size_t)nb * 8 + 127) & ~(size_t)127);
         const int hu1 = 8 + 3 * (32 * (int)as0 / 16);
-        const size_t stage4 = (size_t)4 * std::max<int>(store_units(P->opt.store_dtype), hu1) * 16;
+        const size_t stage4 = (size_t)4 * std::max<int>(store_units(P->opt.store_dtype, P->iw), hu1) * 16;
         const bool fits2 = 2 * (xy + 8 * stage4 + 2048) <= (size_t)P->smem_optin;
         // measured on config 2: one 16-warp CTA per SM (48.8 us) beats three 4-warp CTAs (52.0 us)
         P->W1 = (P->opt.k1_threads > 0 && P->opt.k1_threads < 512 && fits2) ? 4 : 16;
@@ -364,7 +374,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     }
 
     // ---- K1 layout: voxels sorted by row length (descending, stable) ----------------
-    const int units = store_units(P->opt.store_dtype);
+    const int units = store_units(P->opt.store_dtype, P->iw);
     const int es = (int)P->acc_size;
     {
         std::vector<int32_t> order(V);
@@ -553,7 +563,7 @@ extern "C" int vmat_plan_destroy(vmat_plan_t* P) {
 }
 
 extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layout_bytes, int64_t* algo_bytes,
-                              int32_t* launches) {
+                              int32_t* launches, int32_t* index_bytes) {
     if (!P) return fail(VMAT_E_ARG, "null plan");
     const int64_t as = (int64_t)P->acc_size, sv = store_bytes(P->opt.store_dtype);
     if (nnz) *nnz = P->nnz;
@@ -567,8 +577,9 @@ extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layou
         b += P->B * (as + 4) + P->B * 8 * 2;
         *layout_bytes = b;
     }
-    if (algo_bytes) *algo_bytes = 2 * P->nnz * (sv + 4) + 28 * P->V + 12 * P->B;
+    if (algo_bytes) *algo_bytes = 2 * P->nnz * (sv + P->iw) + 28 * P->V + 12 * P->B;    // SURVEY 8(d) with this plan's index width
     if (launches) *launches = P->x_in_smem ? 3 : 4;
+    if (index_bytes) *index_bytes = P->iw;
     return VMAT_OK;
 }
 
@@ -599,17 +610,17 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.nb = P->nb;
         if (host_mode && (P->host_path & 1)) { a1.y = P->d_hy; a1.y_mirror = P->y.as<double>(); a1.seq = P->counter.as<unsigned long long>() + 4; }
         else if (host_mode) { a1.seq = P->counter.as<unsigned long long>() + 4; a1.y_mirror = P->y.as<double>(); }
-        DISPATCH_W1(W, {
+        DISPATCH_IW(IW, { DISPATCH_W1(W, {
             if (P->x_in_smem) {
-                auto kern = k1_dose_penalty<VT, AT, true, W>;
+                auto kern = k1_dose_penalty<VT, AT, true, W, IW>;
                 CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
                 CU(launch_pdl(kern, P->k1_grid, P->k1_threads, P->k1_smem, st, P->pdl, a1));
             } else {
-                auto kern = k1_dose_penalty<VT, AT, false, W>;
+                auto kern = k1_dose_penalty<VT, AT, false, W, IW>;
                 CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
                 CU(launch_pdl(kern, P->k1_grid, P->k1_threads, P->k1_smem, st, P->pdl, a1));
             }
-        });
+        }); });
         if (ev) CU(cudaEventRecord(ev[1], st));
         K2Args<AT> a2{};
         a2.sell = P->sell2.as<uint4>(); a2.ss_off = P->off2.as<int64_t>(); a2.ss_tpr = P->tpr2.as<uint8_t>();
@@ -618,11 +629,11 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.nstages = P->nstages2; a2.stage_bytes = P->stage_bytes2;
         a2.k1_counter = P->counter.as<unsigned int>();
         a2.fpart = P->fpart.as<double>(); a2.fblock = P->fblock.as<double>(); a2.nfpart = P->nslices1;
-        {   // always launched (even with an empty task list): it also folds the objective partials
-            auto kern2 = k2_beamlet_grad<VT, AT, kW2>;
+        DISPATCH_IW(IW, {   // always launched (even with an empty task list): it also folds the objective partials
+            auto kern2 = k2_beamlet_grad<VT, AT, kW2, IW>;
             CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
             CU(launch_pdl(kern2, P->k2_grid, (kW2 + 1) * 32, P->k2_smem, st, P->pdl, a2));
-        }
+        });
     }
     if (ev) CU(cudaEventRecord(ev[2], st));
     K3Args<AT> a3{};

@@ -116,6 +116,11 @@ template <> struct Store<double> {
     }
 };
 
+// chunk geometry in 16-byte units: index block (4 indices per lane, IW bytes each) then value block
+template <typename VT> __host__ __device__ constexpr int val_units() { return 8 * (int)sizeof(VT); }     // f32 32, bf16 16, f64 64
+__host__ __device__ constexpr int idx_units(int IW) { return 8 * IW; }                                   // i32 32, u16 16
+template <typename VT, int IW> __host__ __device__ constexpr int chunk_units() { return idx_units(IW) + val_units<VT>(); }
+
 // ---- arithmetic without FMA contraction where the reference order matters -----------
 __device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }

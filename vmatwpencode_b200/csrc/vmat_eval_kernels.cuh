@@ -9,8 +9,9 @@
 //     CTA processes with W consumer warps in lock step;
 //   * a super-slice is one contiguous run of the stream: a header (per warp: the 32 row ids and,
 //     for K1, the rows' penalty tables) followed by nch stages; stage c holds chunk c of every
-//     warp; a chunk is 4 nonzeros of each of the warp's 32 rows: 32 int4 index vectors, then
-//     the 32 value vectors (vmat_common.cuh: Store<>);
+//     warp; a chunk is 4 nonzeros of each of the warp's 32 lanes: the 32 index vectors (4 x int32,
+//     or 4 x uint16 when every index fits - x has fewer than 65 536 entries and K2's indices are
+//     tile-local), then the 32 value vectors;
 //   * a producer thread streams the CTA's super-slices with TMA bulk copies into a shared-memory
 //     ring (full/empty mbarriers); consumers read their chunk with conflict-free 128-bit shared
 //     loads.  The stream is never touched by the LSU global path and no slice boundary stalls it;
@@ -32,27 +33,35 @@ template <typename AT> __host__ __device__ constexpr int header_units_k1() { ret
 constexpr int kHeaderUnitsK2 = 8;
 
 // one chunk of one warp from the ring: acc += sum_k val[k] * gather(idx[k])
-template <typename VT, typename AT, typename Gather>
+template <typename VT, typename AT, int IW, typename Gather>
 __device__ __forceinline__ void chunk_fma(const unsigned char* __restrict__ cp, int lane, AT& acc, Gather g) {
-    const uint4 idx = *reinterpret_cast<const uint4*>(cp + lane * 16);
+    uint32_t i0, i1, i2, i3;
+    if constexpr (IW == 4) {
+        const uint4 idx = *reinterpret_cast<const uint4*>(cp + lane * 16);
+        i0 = idx.x; i1 = idx.y; i2 = idx.z; i3 = idx.w;
+    } else {
+        const uint2 idx = *reinterpret_cast<const uint2*>(cp + lane * 8);
+        i0 = idx.x & 0xffffu; i1 = idx.x >> 16; i2 = idx.y & 0xffffu; i3 = idx.y >> 16;
+    }
+    const unsigned char* vp = cp + idx_units(IW) * 16;
     AT v[4];
     if constexpr (sizeof(VT) == 4) {
-        const uint4 r = *reinterpret_cast<const uint4*>(cp + 512 + lane * 16);
+        const uint4 r = *reinterpret_cast<const uint4*>(vp + lane * 16);
         v[0] = (AT)__uint_as_float(r.x); v[1] = (AT)__uint_as_float(r.y);
         v[2] = (AT)__uint_as_float(r.z); v[3] = (AT)__uint_as_float(r.w);
     } else if constexpr (sizeof(VT) == 2) {
-        const uint2 r = *reinterpret_cast<const uint2*>(cp + 512 + lane * 8);
+        const uint2 r = *reinterpret_cast<const uint2*>(vp + lane * 8);
         v[0] = (AT)__uint_as_float(r.x << 16); v[1] = (AT)__uint_as_float(r.x & 0xffff0000u);
         v[2] = (AT)__uint_as_float(r.y << 16); v[3] = (AT)__uint_as_float(r.y & 0xffff0000u);
     } else {
-        const double2 a = *reinterpret_cast<const double2*>(cp + 512 + lane * 16);
-        const double2 b = *reinterpret_cast<const double2*>(cp + 1024 + lane * 16);
+        const double2 a = *reinterpret_cast<const double2*>(vp + lane * 16);
+        const double2 b = *reinterpret_cast<const double2*>(vp + 512 + lane * 16);
         v[0] = (AT)a.x; v[1] = (AT)a.y; v[2] = (AT)b.x; v[3] = (AT)b.y;
     }
-    acc = fma_acc(v[0], g(idx.x), acc);
-    acc = fma_acc(v[1], g(idx.y), acc);
-    acc = fma_acc(v[2], g(idx.z), acc);
-    acc = fma_acc(v[3], g(idx.w), acc);
+    acc = fma_acc(v[0], g(i0), acc);
+    acc = fma_acc(v[1], g(i1), acc);
+    acc = fma_acc(v[2], g(i2), acc);
+    acc = fma_acc(v[3], g(i3), acc);
 }
 
 // ring bookkeeping shared by producer and consumers
@@ -117,9 +126,9 @@ struct K1Args {
     unsigned long long* seq;      // nullptr on the resident path
 };
 
-template <typename VT, typename AT, bool XS, int W>
+template <typename VT, typename AT, bool XS, int W, int IW>
 __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT> a) {
-    constexpr int KU = Store<VT>::kUnits, HU = header_units_k1<AT>();
+    constexpr int KU = chunk_units<VT, IW>(), HU = header_units_k1<AT>();
     constexpr int kMaxStages = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages];
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT>
             un = reinterpret_cast<const AT*>(hp + 128 + 64 * sizeof(AT))[lane];
             acc = (AT)0;
         } else {
-            chunk_fma<VT, AT>(sp + warp * (KU * 16), lane, acc, gather);
+            chunk_fma<VT, AT, IW>(sp + warp * (KU * 16), lane, acc, gather);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[pos.stage]);
@@ -256,9 +265,9 @@ struct K2Args {
     int32_t nfpart;
 };
 
-template <typename VT, typename AT, int W>
+template <typename VT, typename AT, int W, int IW>
 __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT> a) {
-    constexpr int KU = Store<VT>::kUnits, HU = kHeaderUnitsK2;
+    constexpr int KU = chunk_units<VT, IW>(), HU = kHeaderUnitsK2;
     constexpr int kMaxStages = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tilebar;
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
             row = reinterpret_cast<const int32_t*>(sp + warp * (HU * 16))[lane];
             acc = (AT)0;
         } else {
-            chunk_fma<VT, AT>(sp + warp * (KU * 16), lane, acc, gather);
+            chunk_fma<VT, AT, IW>(sp + warp * (KU * 16), lane, acc, gather);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[pos.stage]);
@@ -607,7 +616,7 @@ template <> struct StoreCvt<__nv_bfloat16> {
 // one warp per slice s = ss*W + w: writes the warp's part of the super-slice header (row ids and,
 // when `tables` is set, thr/over/under of elem size `es`) and copies the lane's segment (CSR
 // positions seg_start .. +seg_len) into the chunked stages; padding = (index 0, value 0)
-template <typename VT, typename ST>
+template <typename VT, typename ST, int IW>
 __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int64_t* __restrict__ ss_off,
                               const int64_t* __restrict__ seg_start, const int32_t* __restrict__ seg_len,
                               const int32_t* __restrict__ seg_colbase, const uint8_t* __restrict__ ss_tpr,
@@ -616,14 +625,14 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
                               const unsigned char* __restrict__ under, int32_t es,
                               const int32_t* __restrict__ col, const ST* __restrict__ val,
                               uint4* __restrict__ sell) {
-    using S = Store<VT>;
+    constexpr int KU = chunk_units<VT, IW>(), IU = idx_units(IW);
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= nslices) return;
     const int64_t ss = gw / W;
     const int w = (int)(gw % W);
     const int64_t off = ss_off[ss];
-    const int nch = (int)((ss_off[ss + 1] - off - (int64_t)W * HU) / ((int64_t)W * S::kUnits));
+    const int nch = (int)((ss_off[ss + 1] - off - (int64_t)W * HU) / ((int64_t)W * KU));
     const int64_t slot = gw * 32 + lane;
     unsigned char* hp = reinterpret_cast<unsigned char*>(sell + off + (int64_t)w * HU);
     reinterpret_cast<int32_t*>(hp)[lane] = rows[slot];
@@ -639,7 +648,7 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
     const int tpr = ss_tpr[ss], part = lane % tpr;      // the row's nonzeros go round-robin (4 at a time) over its lanes
     uint4* data = sell + off + (int64_t)W * HU;
     for (int c = 0; c < nch; ++c) {
-        uint4* chunk = data + ((int64_t)c * W + w) * S::kUnits;
+        uint4* chunk = data + ((int64_t)c * W + w) * KU;
         int32_t ix[4];
         VT vv[4];
 #pragma unroll
@@ -648,17 +657,22 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
             if (e < len) { ix[k] = col[st + e] - cb; vv[k] = StoreCvt<VT>::cvt(val[st + e]); }
             else         { ix[k] = 0;                vv[k] = StoreCvt<VT>::cvt(0.0f); }
         }
-        chunk[lane] = make_uint4((uint32_t)ix[0], (uint32_t)ix[1], (uint32_t)ix[2], (uint32_t)ix[3]);
+        if constexpr (IW == 4) {
+            chunk[lane] = make_uint4((uint32_t)ix[0], (uint32_t)ix[1], (uint32_t)ix[2], (uint32_t)ix[3]);
+        } else {
+            reinterpret_cast<uint2*>(chunk)[lane] = make_uint2((uint32_t)ix[0] | ((uint32_t)ix[1] << 16),
+                                                              (uint32_t)ix[2] | ((uint32_t)ix[3] << 16));
+        }
         if constexpr (sizeof(VT) == 4) {
             float4 f = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            chunk[32 + lane] = *reinterpret_cast<uint4*>(&f);
+            chunk[IU + lane] = *reinterpret_cast<uint4*>(&f);
         } else if constexpr (sizeof(VT) == 2) {
             __nv_bfloat16 h[4] = {vv[0], vv[1], vv[2], vv[3]};
-            reinterpret_cast<uint2*>(chunk + 32)[lane] = *reinterpret_cast<uint2*>(h);
+            reinterpret_cast<uint2*>(chunk + IU)[lane] = *reinterpret_cast<uint2*>(h);
         } else {
             double2 a2 = make_double2(vv[0], vv[1]), b2 = make_double2(vv[2], vv[3]);
-            chunk[32 + lane] = *reinterpret_cast<uint4*>(&a2);
-            chunk[64 + lane] = *reinterpret_cast<uint4*>(&b2);
+            chunk[IU + lane] = *reinterpret_cast<uint4*>(&a2);
+            chunk[IU + 32 + lane] = *reinterpret_cast<uint4*>(&b2);
         }
     }
 }

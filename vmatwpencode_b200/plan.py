@@ -38,7 +38,7 @@ class DosePlan:
 
     def __init__(self, D, beam_ptr, thr, over, under, device: int = 0, store: str = "f32",
                  acc: str = "f32", tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0,
-                 k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0):
+                 k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0, index_bytes: int = 0):
         """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
         {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
         lib = _lib.load()
@@ -57,6 +57,7 @@ class DosePlan:
         opt.reserved[2] = chunk_cap
         opt.reserved[3] = 0 if pdl else 1
         opt.reserved[4] = host_path
+        opt.reserved[5] = index_bytes          # 4 forces int32 column indices; 0 = uint16 whenever they fit
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         over = np.ascontiguousarray(over, dtype=np.float64)
@@ -105,10 +106,11 @@ class DosePlan:
             pass
 
     def info(self) -> dict:
-        nnz, lay, alg, nl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
-        check(self._lib.vmat_plan_info(self._h, C.byref(nnz), C.byref(lay), C.byref(alg), C.byref(nl)), "vmat_plan_info")
+        nnz, lay, alg, nl, iw = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        check(self._lib.vmat_plan_info(self._h, C.byref(nnz), C.byref(lay), C.byref(alg), C.byref(nl), C.byref(iw)),
+              "vmat_plan_info")
         return dict(nnz=nnz.value, layout_bytes_per_eval=lay.value, algorithmic_bytes_per_eval=alg.value,
-                    launches_per_eval=nl.value, V=self.V, B=self.B, nb=self.nb, store=self.store, acc=self.acc)
+                    launches_per_eval=nl.value, index_bytes=iw.value, V=self.V, B=self.B, nb=self.nb, store=self.store, acc=self.acc)
 
     # -- aperture weights -----------------------------------------------------------
     def set_aperture(self, beam: int, w_dose, w_grad):
