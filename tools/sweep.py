@@ -28,8 +28,9 @@ def main():
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     variants = json.loads(args.variants) if args.variants else [
-        dict(), dict(index_bytes=4), dict(tile_voxels=4096), dict(tile_voxels=16384), dict(chunk_cap=16), dict(chunk_cap=32),
-        dict(store="bf16"), dict(acc="f64"), dict(store="bf16", index_bytes=4),
+        dict(), dict(k2_stages=12), dict(k2_stages=16), dict(tile_voxels=4096), dict(tile_voxels=4096, k2_stages=12),
+        dict(tile_voxels=4096, k2_stages=16), dict(tile_voxels=2048, k2_stages=16), dict(k1_stages=8), dict(k1_stages=16),
+        dict(index_bytes=4), dict(store="bf16"), dict(acc="f64"),
     ]
     for v in variants:
         v = dict(v)

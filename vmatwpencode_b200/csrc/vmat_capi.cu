@@ -338,7 +338,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaDeviceGetAttribute(&P->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaStream_t st = P->stream;
     {   // index width: uint16 when every stored index fits (x index < B; K2 indices are tile-local, < T)
-        const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : (P->opt.acc_dtype == VMAT_F64 ? 4096 : 8192);
+        const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : 4096;
         const bool fits16 = B <= 65536 && ((T0 + 63) / 64 * 64) <= 65536;
         P->iw = (P->opt.reserved[5] == 4 || !fits16) ? 4 : 2;      // reserved[5] = 4 forces int32 indices
     }
@@ -422,12 +422,12 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
     // ---- K2 layout: column tiles of T voxels; per tile, beamlet segments sorted by length
     {
-        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : (P->opt.acc_dtype == VMAT_F64 ? 4096 : 8192);
+        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : 4096;
         T = (T + 63) / 64 * 64;
         const int32_t W = kW2, HU = 8;
         P->W2 = W;
         P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
-        P->nstages2 = 8;
+        P->nstages2 = P->opt.reserved[1] > 0 ? std::max(2, std::min(16, P->opt.reserved[1])) : 8;
         const size_t tile_bytes = ((size_t)T * P->acc_size + 127) & ~(size_t)127;
         P->k2_smem = tile_bytes + (size_t)P->nstages2 * P->stage_bytes2;
         if (P->k2_smem + 2048 > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");

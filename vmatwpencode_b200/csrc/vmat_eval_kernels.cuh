@@ -32,36 +32,32 @@ struct StageInfo { int32_t ss, flags, tile, tpr; };
 template <typename AT> __host__ __device__ constexpr int header_units_k1() { return 8 + 3 * (32 * (int)sizeof(AT) / 16); }
 constexpr int kHeaderUnitsK2 = 8;
 
-// one chunk of one warp from the ring: acc += sum_k val[k] * gather(idx[k])
-template <typename VT, typename AT, int IW, typename Gather>
-__device__ __forceinline__ void chunk_fma(const unsigned char* __restrict__ cp, int lane, AT& acc, Gather g) {
-    uint32_t i0, i1, i2, i3;
+// one chunk of one warp, as it sits in a ring stage: 4 indices and 4 values per lane
+template <typename AT> struct ChunkRegs { uint32_t i[4]; AT v[4]; };
+
+template <typename VT, typename AT, int IW>
+__device__ __forceinline__ void chunk_load(const unsigned char* __restrict__ cp, int lane, ChunkRegs<AT>& c) {
     if constexpr (IW == 4) {
         const uint4 idx = *reinterpret_cast<const uint4*>(cp + lane * 16);
-        i0 = idx.x; i1 = idx.y; i2 = idx.z; i3 = idx.w;
+        c.i[0] = idx.x; c.i[1] = idx.y; c.i[2] = idx.z; c.i[3] = idx.w;
     } else {
         const uint2 idx = *reinterpret_cast<const uint2*>(cp + lane * 8);
-        i0 = idx.x & 0xffffu; i1 = idx.x >> 16; i2 = idx.y & 0xffffu; i3 = idx.y >> 16;
+        c.i[0] = idx.x & 0xffffu; c.i[1] = idx.x >> 16; c.i[2] = idx.y & 0xffffu; c.i[3] = idx.y >> 16;
     }
     const unsigned char* vp = cp + idx_units(IW) * 16;
-    AT v[4];
     if constexpr (sizeof(VT) == 4) {
         const uint4 r = *reinterpret_cast<const uint4*>(vp + lane * 16);
-        v[0] = (AT)__uint_as_float(r.x); v[1] = (AT)__uint_as_float(r.y);
-        v[2] = (AT)__uint_as_float(r.z); v[3] = (AT)__uint_as_float(r.w);
+        c.v[0] = (AT)__uint_as_float(r.x); c.v[1] = (AT)__uint_as_float(r.y);
+        c.v[2] = (AT)__uint_as_float(r.z); c.v[3] = (AT)__uint_as_float(r.w);
     } else if constexpr (sizeof(VT) == 2) {
         const uint2 r = *reinterpret_cast<const uint2*>(vp + lane * 8);
-        v[0] = (AT)__uint_as_float(r.x << 16); v[1] = (AT)__uint_as_float(r.x & 0xffff0000u);
-        v[2] = (AT)__uint_as_float(r.y << 16); v[3] = (AT)__uint_as_float(r.y & 0xffff0000u);
+        c.v[0] = (AT)__uint_as_float(r.x << 16); c.v[1] = (AT)__uint_as_float(r.x & 0xffff0000u);
+        c.v[2] = (AT)__uint_as_float(r.y << 16); c.v[3] = (AT)__uint_as_float(r.y & 0xffff0000u);
     } else {
         const double2 a = *reinterpret_cast<const double2*>(vp + lane * 16);
         const double2 b = *reinterpret_cast<const double2*>(vp + 512 + lane * 16);
-        v[0] = (AT)a.x; v[1] = (AT)a.y; v[2] = (AT)b.x; v[3] = (AT)b.y;
+        c.v[0] = (AT)a.x; c.v[1] = (AT)a.y; c.v[2] = (AT)b.x; c.v[3] = (AT)b.y;
     }
-    acc = fma_acc(v[0], g(i0), acc);
-    acc = fma_acc(v[1], g(i1), acc);
-    acc = fma_acc(v[2], g(i2), acc);
-    acc = fma_acc(v[3], g(i3), acc);
 }
 
 // ring bookkeeping shared by producer and consumers
@@ -84,6 +80,43 @@ __device__ __forceinline__ void ring_push(unsigned char* ring, int stage_bytes, 
         mbar_arrive(&full[pos.stage]);
     }
     pos.advance(nstages);
+}
+
+// consumer side, data stage at `pos`: acc += this warp's chunk . gathered vector.  When the stage is
+// not the last of its super-slice the next stage is data of the same super-slice too: both are
+// taken in one pass (two sets of shared-memory loads and gathers in flight, one round of barrier
+// traffic per two chunks).  The row sum order is unchanged.  On return `pos`/`info` describe the
+// last stage consumed (the caller advances past it).
+template <typename VT, typename AT, int IW, typename Gather>
+__device__ __forceinline__ void consume_data(const unsigned char* ring, int SB, int warp_off, uint64_t* full,
+                                             uint64_t* empty, const StageInfo* sinfo, RingPos& pos, int nst,
+                                             StageInfo& info, int lane, AT& acc, Gather g) {
+    ChunkRegs<AT> A;
+    chunk_load<VT, AT, IW>(ring + (size_t)pos.stage * SB + warp_off, lane, A);
+    if (info.flags & kStageLast) {
+        AT x0 = g(A.i[0]), x1 = g(A.i[1]), x2 = g(A.i[2]), x3 = g(A.i[3]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[pos.stage]);
+        acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
+        acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
+        return;
+    }
+    RingPos nx = pos;
+    nx.advance(nst);
+    mbar_wait(&full[nx.stage], nx.phase);
+    const StageInfo info2 = sinfo[nx.stage];
+    ChunkRegs<AT> Bc;
+    chunk_load<VT, AT, IW>(ring + (size_t)nx.stage * SB + warp_off, lane, Bc);
+    AT x0 = g(A.i[0]), x1 = g(A.i[1]), x2 = g(A.i[2]), x3 = g(A.i[3]);
+    AT y0 = g(Bc.i[0]), y1 = g(Bc.i[1]), y2 = g(Bc.i[2]), y3 = g(Bc.i[3]);
+    __syncwarp();
+    if (lane == 0) { mbar_arrive(&empty[pos.stage]); mbar_arrive(&empty[nx.stage]); }
+    acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
+    acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
+    acc = fma_acc(Bc.v[0], y0, acc); acc = fma_acc(Bc.v[1], y1, acc);
+    acc = fma_acc(Bc.v[2], y2, acc); acc = fma_acc(Bc.v[3], y3, acc);
+    pos = nx;
+    info = info2;
 }
 
 // ---------------------------------------------------------------------------------
@@ -200,21 +233,20 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT>
     int32_t row = -1;
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
-        const StageInfo info = sinfo[pos.stage];
+        StageInfo info = sinfo[pos.stage];
         if (info.ss < 0) break;
-        const unsigned char* sp = ring + (size_t)pos.stage * SB;
         if (info.flags & kStageHeader) {
-            const unsigned char* hp = sp + warp * (HU * 16);
+            const unsigned char* hp = ring + (size_t)pos.stage * SB + warp * (HU * 16);
             row = reinterpret_cast<const int32_t*>(hp)[lane];
             t  = reinterpret_cast<const AT*>(hp + 128)[lane];
             ov = reinterpret_cast<const AT*>(hp + 128 + 32 * sizeof(AT))[lane];
             un = reinterpret_cast<const AT*>(hp + 128 + 64 * sizeof(AT))[lane];
             acc = (AT)0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[pos.stage]);
         } else {
-            chunk_fma<VT, AT, IW>(sp + warp * (KU * 16), lane, acc, gather);
+            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, gather);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[pos.stage]);
         if (info.flags & kStageLast) {
             for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // tpr lanes of a row
             double fterm = 0.0;
@@ -331,10 +363,10 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     uint32_t tparity = 0;
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
-        const StageInfo info = sinfo[pos.stage];
+        StageInfo info = sinfo[pos.stage];
         if (info.ss < 0) break;
-        const unsigned char* sp = ring + (size_t)pos.stage * SB;
         if (info.flags & kStageHeader) {
+            const unsigned char* sp = ring + (size_t)pos.stage * SB;
             if (info.tile != cur_tile) {
                 named_bar_sync(1, W * 32);            // all consumers are done with the previous tile
                 if (tid == 0) {
@@ -350,11 +382,11 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
             }
             row = reinterpret_cast<const int32_t*>(sp + warp * (HU * 16))[lane];
             acc = (AT)0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[pos.stage]);
         } else {
-            chunk_fma<VT, AT, IW>(sp + warp * (KU * 16), lane, acc, gather);
+            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, gather);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[pos.stage]);
         if (info.flags & kStageLast) {
             for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (row >= 0) a.partial[(int64_t)cur_tile * a.B + row] = acc;

@@ -38,7 +38,8 @@ class DosePlan:
 
     def __init__(self, D, beam_ptr, thr, over, under, device: int = 0, store: str = "f32",
                  acc: str = "f32", tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0,
-                 k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0, index_bytes: int = 0):
+                 k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0, index_bytes: int = 0,
+                 k1_stages: int = 0, k2_stages: int = 0):
         """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
         {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
         lib = _lib.load()
@@ -54,6 +55,7 @@ class DosePlan:
         opt.acc_dtype = _lib.DTYPE_CODES[acc]
         opt.tile_voxels, opt.k1_threads, opt.k2_threads, opt.k2_tasks = tile_voxels, k1_threads, k2_threads, k2_tasks
         opt.use_graph = 1 if use_graph else 0
+        opt.reserved[0], opt.reserved[1] = k1_stages, k2_stages      # ring depths (0 = default)
         opt.reserved[2] = chunk_cap
         opt.reserved[3] = 0 if pdl else 1
         opt.reserved[4] = host_path
