@@ -128,6 +128,38 @@ def kmedoids_fixture():
     print("kmedoids fixtures written")
 
 
+def ingest_fixture(name, seed):
+    """What the reference's own loader statements (greedyVMATsampling.py:286-576) produce for a
+    synthetic CORT-format data set (oracle/cort_fixture.py, regenerated from `seed` by the tests)."""
+    import tempfile
+    from oracle.cort_fixture import write_cort_like
+    root = tempfile.mkdtemp()
+    cfg = write_cort_like(root, seed=seed)
+    ns = R.run_reference_loader(cfg)
+    data = ns["data"]
+    out = dict(seed=np.int64(seed), numvoxels=np.int64(data.numvoxels), numbeams=np.int64(data.numbeams),
+               N=np.int64(ns["N"]), M=np.int64(ns["M"]), numX=np.int64(data.numX), totaldijs=np.int64(data.totaldijs),
+               ga=np.asarray(ns["ga"], dtype=np.int64), xinter=np.asarray(data.xinter), yinter=np.asarray(data.yinter),
+               beamletsPerBeam=np.asarray(data.beamletsPerBeam, dtype=np.int64),
+               xdir=np.concatenate(data.xdirection), ydir=np.concatenate(data.ydirection),
+               voxelAssignment=np.asarray(data.voxelAssignment), originalVoxels=np.asarray(ns["originalVoxels"]),
+               maskValue=np.asarray(data.maskValue), fullMaskValue=np.asarray(data.fullMaskValue),
+               thr=ns["quadHelperThresh"], over=ns["quadHelperOver"], under=ns["quadHelperUnder"],
+               functionData=np.asarray(data.functionData), pointtoAngle=np.asarray(list(data.pointtoAngle), dtype=np.int64),
+               region_index=np.asarray([r.index for r in data.regions], dtype=np.int64),
+               region_target=np.asarray([r.target for r in data.regions]),
+               region_size=np.asarray([r.sizeInVoxels for r in data.regions], dtype=np.int64),
+               region_indices=np.concatenate([np.asarray(r.indices, dtype=np.int64).ravel() for r in data.regions]),
+               region_full_size=np.asarray([np.asarray(r.fullIndices).size for r in data.regions], dtype=np.int64),
+               region_full=np.concatenate([np.asarray(r.fullIndices, dtype=np.int64).ravel() for r in data.regions]))
+    import scipy.sparse as sp
+    D = sp.hstack([d.transpose() for d in data.Dlist], format="csr")       # V x B like the kernels take it
+    D.sort_indices()
+    out.update(D_indptr=D.indptr.astype(np.int64), D_indices=D.indices.astype(np.int32), D_data=D.data)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "voxels", data.numvoxels, "beams", data.numbeams, "grid", ns["M"], "x", ns["N"], "nnz", D.nnz)
+
+
 def main():
     if not R.reference_available():
         raise SystemExit("reference not mounted at " + R.REFERENCE_ROOT)
@@ -167,6 +199,8 @@ def main():
     colgen_fixture("colgen_C", make_case(V=2000, nb=36, M=3, N=5, density=0.05, seed=33, gastep=1), 0.5, 8, 14)
     colgen_fixture("colgen_E", make_case(V=2500, nb=14, M=4, N=6, density=0.04, seed=35, gastep=10), 0.01, 5, 14,
                    elimination=True, module="greedyVMATsamplingLaptop")
+    ingest_fixture("ingest_A", seed=1)
+    ingest_fixture("ingest_B", seed=2)
     kmedoids_fixture()
 
 

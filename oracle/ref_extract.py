@@ -202,3 +202,42 @@ def ref_colgen(ns, case, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vma
         if max_iter is not None and len(history) >= max_iter:
             break
     return history
+
+
+def run_reference_loader(cfg: dict, module: str = "greedyVMATsampling"):
+    """Execute the reference's own loader - the TOP-LEVEL statements of the script between
+    ``start = time.time()`` and the quadHelper loops (greedyVMATsampling.py:286-576), plus the
+    class definitions they need - on a data set written by oracle/cort_fixture.py.  The hard-coded
+    path / priority / gantry-range assignments are dropped and replaced by `cfg`.
+    Returns the namespace (``data``, ``DlistT``, ``quadHelper*``, ``N``, ``M``, ...)."""
+    import glob
+    import scipy.io as sio
+    path = os.path.join(REFERENCE_ROOT, module + ".py")
+    tree = ast.parse(open(path).read())
+    seeded = {"readfolder", "readfolderD", "outputfolder", "objfile", "structurefile", "algfile", "priority",
+              "gastart", "gaend", "gastep", "WholeCircle", "IntheOffice", "AtHome", "kappa"}
+    first = next(n.lineno for n in tree.body
+                 if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "start")
+    last = max(n.end_lineno for n in tree.body
+               if isinstance(n, ast.For) and "quadHelperThresh" in ast.dump(n))
+    keep = []
+    for n in tree.body:
+        if isinstance(n, ast.ClassDef) and n.name in ("region", "apertureList", "vmat_class"):
+            keep.append(n)
+        elif first <= n.lineno <= last:
+            if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") in seeded:
+                continue
+            keep.append(n)
+    ns = extract(module, names=[])          # shimmed numpy, SerialPool, __name__ == '__main__'
+    ns.update(glob=glob, os=os, sio=sio, ga=[], ca=[], outputfolder=cfg["readfolder"],
+              pointtoAngle=range(cfg["gastart"], cfg["gaend"], cfg["gastep"]))
+    ns.update({k: (list(v) if k == "priority" else v) for k, v in cfg.items()})
+    cwd = os.getcwd()
+    try:
+        import warnings
+        with quiet(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    return ns
