@@ -170,6 +170,16 @@ int vmat_price(vmat_plan_t* plan, int32_t ncand, const int32_t* cand_beam,
 int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
                        const double* curmin, double* cost /* n */);
 
+/*
+ * Dose-volume histograms of the last evaluation's dose (printresults, greedyVMATsampling.py:
+ * 888-912): vmat_dose_max returns max(dose); vmat_dvh_histogram counts, for every structure s
+ * (bit s of full_mask[v], data.fullMaskValue), the voxels whose dose falls in
+ * [edges[k], edges[k+1]) - np.histogram with explicit edges, last bin closed.  Host arrays.
+ */
+int vmat_dose_max(vmat_plan_t* plan, double* max_dose);
+int vmat_dvh_histogram(vmat_plan_t* plan, const uint64_t* full_mask /* V */, int32_t nstructs,
+                       const double* edges, int32_t nedges, int64_t* hist /* nstructs*(nedges-1) */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,6 +160,22 @@ def ingest_fixture(name, seed):
     print(name, "voxels", data.numvoxels, "beams", data.numbeams, "grid", ns["M"], "x", ns["N"], "nnz", D.nnz)
 
 
+def dvh_fixture():
+    """Dose-volume histograms from the reference's own printresults (Laptop variant) for a seeded
+    dose vector and structure bit masks."""
+    rng = np.random.default_rng(17)
+    V, nstructs = 3000, 7
+    mask = rng.integers(1, 2 ** nstructs, size=V)
+    mask[rng.random(V) < 0.3] &= 0b0111011            # structure 2 and 6 thinner; structure 5 never alone
+    mask[mask == 0] = 1
+    mask &= ~(1 << 5)                                  # structure 5 is empty
+    dose = np.round(rng.random(V) * 4.0, 3)            # many values on 0.1 bin edges x.y00
+    bin_center, dvh = R.ref_printresults(dose, mask.astype(float), nstructs)
+    np.savez_compressed(os.path.join(GOLDEN, "dvh.npz"), dose=dose, full_mask=mask.astype(np.int64),
+                        numstructs=np.int64(nstructs), bin_center=bin_center, dvh_matrix=dvh)
+    print("dvh fixture", dvh.shape)
+
+
 def main():
     if not R.reference_available():
         raise SystemExit("reference not mounted at " + R.REFERENCE_ROOT)
@@ -199,6 +215,7 @@ def main():
     colgen_fixture("colgen_C", make_case(V=2000, nb=36, M=3, N=5, density=0.05, seed=33, gastep=1), 0.5, 8, 14)
     colgen_fixture("colgen_E", make_case(V=2500, nb=14, M=4, N=6, density=0.04, seed=35, gastep=10), 0.01, 5, 14,
                    elimination=True, module="greedyVMATsamplingLaptop")
+    dvh_fixture()
     ingest_fixture("ingest_A", seed=1)
     ingest_fixture("ingest_B", seed=2)
     kmedoids_fixture()

@@ -241,3 +241,24 @@ def run_reference_loader(cfg: dict, module: str = "greedyVMATsampling"):
     finally:
         os.chdir(cwd)
     return ns
+
+
+def ref_printresults(dose, full_mask, numstructs):
+    """The reference's own printresults (Laptop variant, greedyVMATsamplingLaptop.py:902-949) with
+    plotting modules that only record: returns the (bin_center, dvh_matrix) of its first plot call."""
+    import types
+    ns = extract("greedyVMATsamplingLaptop", names=["printresults"])
+    calls = []
+    fake = types.SimpleNamespace(plot=lambda *a, **k: calls.append(a), xlim=lambda *a, **k: None)
+    noop = lambda *a, **k: None
+    ns["pylab"] = fake
+    ns["plt"] = types.SimpleNamespace(grid=noop, xlabel=noop, ylabel=noop, title=noop, legend=noop, savefig=noop, close=noop)
+    ns["data"] = types.SimpleNamespace(fullMaskValue=full_mask, currentDose=np.asarray(dose), numstructs=numstructs)
+    ns["allNames"] = ["S%02d_VOILIST.mat" % s for s in range(numstructs)]
+    try:
+        with quiet():
+            ns["printresults"](1, "/tmp/", 0)
+    except IndexError:          # the second plot picks structures 7..20 of the head-and-neck case
+        pass
+    bin_center, dvh_t = calls[0][0], calls[0][1]
+    return np.asarray(bin_center), np.asarray(dvh_t).T

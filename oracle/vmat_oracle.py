@@ -433,6 +433,23 @@ def solve_rmc(st: OracleState, YU, evaluator=None):
                         options={"ftol": 1e-1, "maxiter": 200})
 
 
+def dvh_matrix(dose, full_mask, numstructs):
+    """The numbers printresults plots (greedyVMATsampling.py:888-912): per structure s (bit s of
+    the full mask) the cumulative dose-volume histogram on 0.1-wide bins up to max dose + 10."""
+    mask = np.array([int(i) for i in full_mask])
+    max_dose = max([float(i) for i in dose])
+    bin_center = np.arange(0, max_dose + 10, 0.1)
+    out = np.zeros((numstructs, len(bin_center)))
+    for s in range(numstructs):
+        holder = sorted(np.asarray(dose)[[i for i, v in enumerate(mask & 2 ** s) if v > 0]])
+        if 0 == len(holder):
+            continue
+        hist, _ = np.histogram(holder, bin_center)
+        hist = np.cumsum(np.append(hist, 0))
+        out[s, ] = 1 - (hist / max(hist))
+    return bin_center, out
+
+
 def kelly_measure(l, r):
     """Aperture complexity (perimeter / area) of leaf vectors l, r
     (greedyVMATsamplingLaptop.py:850-862, inside its PricingProblem)."""

@@ -141,3 +141,10 @@ def test_global_form_equals_literal_when_open_map_has_duplicates():
     d1 = st.currentDose.copy()
     f2, g2, d2, vg2, gb2 = O.calc_obj_grad_clean(st, y.copy())
     assert relerr(d2, d1) <= 1e-13 and abs(f2 - f1) <= 1e-13 * abs(f1) and relerr(g2, g1) <= 1e-13
+
+
+def test_dvh_matches_reference_printresults():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "dvh.npz"))
+    b, m = O.dvh_matrix(z["dose"], z["full_mask"].astype(float), int(z["numstructs"]))
+    assert np.array_equal(b, z["bin_center"]) and np.array_equal(m, z["dvh_matrix"])
+    assert np.all(m[5] == 0)          # the empty structure keeps a zero row

@@ -442,3 +442,28 @@ def test_kmedoid_costs_tree_path_and_voxel_points():
     for c in (1, 3000):
         want = np.minimum(cur, np.sqrt(((P - P[c]) ** 2).sum(axis=1))).sum()
         assert abs(cost[c] - want) <= 1e-12 * want
+
+
+@pytest.mark.parametrize("acc", ["f64", "f32"])
+def test_dvh_on_device_matches_oracle(acc):
+    """printresults' dose-volume histograms from the GPU-resident dose: integer bin counts, so
+    exact against the oracle fed with the same dose values."""
+    case = make_case(V=20_000, nb=10, M=4, N=6, density=0.02, seed=83)
+    data = vl.bind(case, store="f32", acc=acc)
+    all_candidates(data, case)
+    for bm, (l, r) in {2: (0, 5), 7: (1, 6)}.items():
+        select(data, case, bm, [l] * case.M, [r] * case.M, vl.updateOpenAperture)
+    y = np.zeros(case.nb); y[2] = 3.0; y[7] = 2.0
+    vl.calcObjGrad(y)
+    rng = np.random.default_rng(2)
+    nstructs = 6
+    mask = rng.integers(1, 2 ** nstructs, size=case.V)
+    mask &= ~(1 << 4)                                       # an empty structure
+    mask[mask == 0] = 1
+    data.fullMaskValue = mask.astype(float)
+    data.numstructs = nstructs
+    bins, dvh = vl.printresults(1)
+    b0, m0 = O.dvh_matrix(data.currentDose, mask.astype(float), nstructs)
+    assert np.array_equal(bins, b0) and np.array_equal(dvh, m0)
+    assert abs(data.plan.dose_max() - data.currentDose.max()) == 0
+    data.plan.close()

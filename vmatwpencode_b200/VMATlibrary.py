@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import random
 import sys
 import time
@@ -255,6 +256,10 @@ def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool 
     d.llist = [[-1] * len(d.xinter) for _ in range(case.nb)]           # fully open (:952-954)
     d.rlist = [[len(d.yinter) + 1] * len(d.xinter) for _ in range(case.nb)]
     d.totaldijs = int(case.D.nnz)
+    for name in ("numstructs", "numtargets", "numoars", "regions", "maskValue", "fullMaskValue", "regionIndices",
+                 "targets", "oars", "functionData", "voxelAssignment"):       # present on ingested cases
+        if hasattr(case, name):
+            setattr(d, name, getattr(case, name))
     if gpu:     # gpu=False: host-side bookkeeping only (geometry, updateOpenAperture); no evaluation
         d.plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, device=device,
                           store=store, acc=acc, **plan_opts)
@@ -496,6 +501,32 @@ def solveRMC(YU):
                        bounds=boundschoice, options={"ftol": 1e-1, "maxiter": 200})
     data.rmp_seconds = time.time() - start
     return res
+
+
+def printresults(iterationNumber, myfolder=None, Cvalue=None):
+    """Dose-volume histograms of the current dose: (bin_center, dvh_matrix[numstructs, bins]) - the
+    numbers the reference's printresults plots (greedyVMATsampling.py:888-912; Laptop :902-926).
+    Dose maximum and histograms are computed on the GPU from the resident dose; nothing is
+    plotted.  With `myfolder` the two arrays are saved there as an .npz."""
+    if data.plan is None or data._fg is None:
+        raise VmatError("printresults needs an evaluated plan: call data.calcDose() first")
+    maxDose = data.plan.dose_max()
+    dose_resln = 0.1
+    dose_ub = maxDose + 10
+    bin_center = np.arange(0, dose_ub, dose_resln)
+    full = np.array([int(v) for v in data.fullMaskValue], dtype=np.uint64)
+    hist = data.plan.dvh_histogram(full, data.numstructs, bin_center)
+    dvh_matrix = np.zeros((data.numstructs, len(bin_center)))
+    for s in range(data.numstructs):
+        if hist[s].sum() == 0 and not np.any(full & np.uint64(2 ** s)):
+            continue                                              # empty structure: row stays 0 (:904-905)
+        cum = np.cumsum(np.append(hist[s], 0))
+        dvh_matrix[s, :] = 1 - cum / max(cum)
+    if myfolder:
+        tag = "" if Cvalue is None else "-C" + str(Cvalue)
+        np.savez(os.path.join(myfolder, "DVH-iteration-" + str(iterationNumber) + tag + ".npz"),
+                 bin_center=bin_center, dvh_matrix=dvh_matrix)
+    return bin_center, dvh_matrix
 
 
 def colGen(C, WholeCircle, initialApertures, max_iter=None):

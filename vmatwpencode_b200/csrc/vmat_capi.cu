@@ -951,6 +951,46 @@ extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_bea
 }
 
 // ---------------------------------------------------------------------------------
+// dose-volume histograms
+// ---------------------------------------------------------------------------------
+extern "C" int vmat_dose_max(vmat_plan_t* P, double* out) {
+    if (!P || !out) return fail(VMAT_E_ARG, "null");
+    CU(cudaSetDevice(P->device)); CU(cudaDeviceSynchronize());
+    DevBuf m;
+    CU(m.alloc(8)); CU(cudaMemset(m.p, 0, 8));
+    DISPATCH_ACC(P->opt.acc_dtype, AT, {
+        k7_dose_max<AT><<<P->sm_count * 4, 256, 0, P->stream>>>(P->V, P->d.as<AT>(), m.as<unsigned long long>());
+    });
+    CU(cudaGetLastError());
+    unsigned long long bits = 0;
+    CU(cudaMemcpyAsync(&bits, m.p, 8, cudaMemcpyDeviceToHost, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    std::memcpy(out, &bits, 8);
+    return VMAT_OK;
+}
+
+extern "C" int vmat_dvh_histogram(vmat_plan_t* P, const uint64_t* full_mask, int32_t nstructs,
+                                  const double* edges, int32_t nedges, int64_t* hist) {
+    if (!P || !full_mask || !edges || !hist || nstructs < 1 || nstructs > 64 || nedges < 2)
+        return fail(VMAT_E_ARG, "vmat_dvh_histogram: bad argument");
+    CU(cudaSetDevice(P->device)); CU(cudaDeviceSynchronize());
+    DevBuf dm, de, dh;
+    const size_t nh = (size_t)nstructs * (nedges - 1);
+    CU(dm.alloc(P->V * 8)); CU(de.alloc((size_t)nedges * 8)); CU(dh.alloc(nh * 8));
+    CU(cudaMemcpy(dm.p, full_mask, P->V * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(de.p, edges, (size_t)nedges * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dh.p, 0, nh * 8));
+    DISPATCH_ACC(P->opt.acc_dtype, AT, {
+        k7_dvh_hist<AT><<<P->sm_count * 4, 256, 0, P->stream>>>(P->V, P->d.as<AT>(), dm.as<unsigned long long>(), nstructs,
+                                                                 de.as<double>(), nedges, dh.as<unsigned long long>());
+    });
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hist, dh.p, nh * 8, cudaMemcpyDeviceToHost, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    return VMAT_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // k-medoid insertion costs
 // ---------------------------------------------------------------------------------
 extern "C" int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,

@@ -57,4 +57,41 @@ __global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost(int64_t n, int dim
     if (tid == 0) cost[c] = sh[0];
 }
 
+// ---------------------------------------------------------------------------------
+// K7: dose-volume histograms (printresults, greedyVMATsampling.py:888-912).  Integer counts with
+// integer atomics: exact whatever the order.  Bin k holds edges[k] <= d < edges[k+1]; the last bin
+// also takes d == edges[last] (np.histogram with explicit edges).
+// ---------------------------------------------------------------------------------
+template <typename AT>
+__global__ void k7_dose_max(int64_t V, const AT* __restrict__ dose, unsigned long long* __restrict__ out) {
+    double m = 0.0;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, (double)dose[v]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+template <typename AT>
+__global__ void k7_dvh_hist(int64_t V, const AT* __restrict__ dose, const unsigned long long* __restrict__ full_mask,
+                            int nstructs, const double* __restrict__ edges, int nedges,
+                            unsigned long long* __restrict__ hist) {
+    const int nbins = nedges - 1;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        const double d = (double)dose[v];
+        if (!(d >= edges[0]) || d > edges[nedges - 1]) continue;
+        int lo = 0, hi = nedges;                 // first edge > d
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (edges[mid] <= d) lo = mid + 1; else hi = mid; }
+        int k = lo - 1;
+        if (k >= nbins) k = nbins - 1;
+        unsigned long long m = full_mask[v];
+        while (m) {
+            const int s = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (s < nstructs) atomicAdd(&hist[(size_t)s * nbins + k], 1ull);
+        }
+    }
+}
+
 }  // namespace vmat

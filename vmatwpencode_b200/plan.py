@@ -217,6 +217,22 @@ class DosePlan:
         check(self._lib.vmat_get_beamlet_grad(self._h, _ptr(out)), "vmat_get_beamlet_grad")
         return out
 
+    # -- dose-volume histograms ------------------------------------------------------
+    def dose_max(self) -> float:
+        m = C.c_double()
+        check(self._lib.vmat_dose_max(self._h, C.byref(m)), "vmat_dose_max")
+        return m.value
+
+    def dvh_histogram(self, full_mask, nstructs: int, edges) -> np.ndarray:
+        """int64[nstructs, len(edges)-1]: voxels of structure s (bit s of full_mask) per dose bin."""
+        fm = np.ascontiguousarray(full_mask, dtype=np.uint64)
+        ed = np.ascontiguousarray(edges, dtype=np.float64)
+        if len(fm) != self.V:
+            raise VmatError("full_mask must have one entry per voxel")
+        hist = np.zeros((nstructs, len(ed) - 1), dtype=np.int64)
+        check(self._lib.vmat_dvh_histogram(self._h, _ptr(fm), nstructs, _ptr(ed), len(ed), _ptr(hist)), "vmat_dvh_histogram")
+        return hist
+
     # -- pricing --------------------------------------------------------------------
     def price(self, cands: Sequence[int], params: PriceParams, rows):
         """Batched PPsubroutine: `rows` is a ctypes array of PriceRow, len(cands)*M."""
