@@ -467,3 +467,22 @@ def test_dvh_on_device_matches_oracle(acc):
     assert np.array_equal(bins, b0) and np.array_equal(dvh, m0)
     assert abs(data.plan.dose_max() - data.currentDose.max()) == 0
     data.plan.close()
+
+
+def test_result_bundle_round_trip(tmp_path):
+    """The pickle colGen leaves behind (25 fields, :1053-1060) is readable the way picklereader.py
+    reads it (positional unpacking of a list)."""
+    import pickle
+    case = make_case(V=4000, nb=8, M=4, N=6, density=0.03, seed=84)
+    data = vl.bind(case, store="f32", acc="f64")
+    vl.colGen(0.01, False, 4, max_iter=3)
+    pik = str(tmp_path / "pickle-C-0.01-save.dat")
+    vl.saveResults(pik, 0.01, allNames=["a", "b"])
+    with open(pik, "rb") as f:
+        items = pickle.load(f)
+    assert len(items) == 25 and items[0] == case.nb and items[9] == case.M and items[10] == case.N
+    assert np.array_equal(items[1], data.rmpres.x) and np.array_equal(items[14], data.currentDose)
+    assert np.array_equal(items[19], case.thr) and items[11] == data.llist
+    back = vl.loadResults(pik)
+    assert back["YU"] == 10.0 / 0.83 and back["objectiveValue"] == data.objectiveValue
+    data.plan.close()

@@ -256,6 +256,7 @@ def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool 
     d.llist = [[-1] * len(d.xinter) for _ in range(case.nb)]           # fully open (:952-954)
     d.rlist = [[len(d.yinter) + 1] * len(d.xinter) for _ in range(case.nb)]
     d.totaldijs = int(case.D.nnz)
+    d.case_thr, d.case_over, d.case_under = np.asarray(case.thr), np.asarray(case.over), np.asarray(case.under)
     for name in ("numstructs", "numtargets", "numoars", "regions", "maskValue", "fullMaskValue", "regionIndices",
                  "targets", "oars", "functionData", "voxelAssignment"):       # present on ingested cases
         if hasattr(case, name):
@@ -527,6 +528,36 @@ def printresults(iterationNumber, myfolder=None, Cvalue=None):
         np.savez(os.path.join(myfolder, "DVH-iteration-" + str(iterationNumber) + tag + ".npz"),
                  bin_center=bin_center, dvh_matrix=dvh_matrix)
     return bin_center, dvh_matrix
+
+
+RESULT_FIELDS = ("numbeams", "x", "C", "C2", "C3", "vmax", "speedlim", "RU", "YU", "M", "N", "llist", "rlist",
+                 "fullMaskValue", "currentDose", "currentIntensities", "numstructs", "allNames", "objectiveValue",
+                 "quadHelperThresh", "quadHelperOver", "quadHelperUnder", "regionIndices", "targets", "oars")
+
+
+def saveResults(PIK, C, C2=1.0, C3=1.0, vmax=2.25, speedlim=0.83, RU=10.0, allNames=None):
+    """Write the 25-field result list colGen pickles at the end of a run
+    (greedyVMATsampling.py:1053-1060) in the order picklereader.py:108-134 unpacks it."""
+    import pickle
+    plan = data.plan
+    thr = over = under = None
+    if plan is not None:
+        thr, over, under = data.case_thr, data.case_over, data.case_under
+    datasave = [data.numbeams, data.rmpres.x, C, C2, C3, vmax, speedlim, RU, RU / speedlim, M, N, data.llist, data.rlist,
+                data.fullMaskValue, data.currentDose, data.currentIntensities, data.numstructs,
+                list(allNames) if allNames is not None else [], data.objectiveValue, thr, over, under,
+                data.regionIndices, data.targets, data.oars]
+    with open(PIK, "wb") as f:
+        pickle.dump(datasave, f, pickle.HIGHEST_PROTOCOL)
+    return datasave
+
+
+def loadResults(PIK):
+    """Read a result bundle back as a dict keyed by the names picklereader.py uses."""
+    import pickle
+    with open(PIK, "rb") as f:
+        items = pickle.load(f)
+    return dict(zip(RESULT_FIELDS, items))
 
 
 def colGen(C, WholeCircle, initialApertures, max_iter=None):
