@@ -171,6 +171,18 @@ int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
                        const double* curmin, double* cost /* n */);
 
 /*
+ * Restricted-master-problem fast path (solveRMC, greedyVMATsampling.py:858-885): while the
+ * apertures of the listed control points stay fixed, vmat_rmp_begin caches their dose columns
+ * D_i^T w_dose_i and gradient columns D_i^T w_grad_i (dense, V each); vmat_rmp_eval then evaluates
+ * (f, g) for intensities y[nb] from the cache (control points outside the list contribute nothing
+ * and get g = 0, as they have zero weights in calcDose anyway).  vmat_rmp_end drops the cache.
+ * The beamlet gradient used by pricing is NOT refreshed by vmat_rmp_eval.
+ */
+int vmat_rmp_begin(vmat_plan_t* plan, int32_t ncols, const int32_t* beams);
+int vmat_rmp_eval(vmat_plan_t* plan, const double* y, double* f, double* g);
+int vmat_rmp_end(vmat_plan_t* plan);
+
+/*
  * Dose-volume histograms of the last evaluation's dose (printresults, greedyVMATsampling.py:
  * 888-912): vmat_dose_max returns max(dose); vmat_dvh_histogram counts, for every structure s
  * (bit s of full_mask[v], data.fullMaskValue), the voxels whose dose falls in

@@ -486,3 +486,50 @@ def test_result_bundle_round_trip(tmp_path):
     back = vl.loadResults(pik)
     assert back["YU"] == 10.0 / 0.83 and back["objectiveValue"] == data.objectiveValue
     data.plan.close()
+
+
+@pytest.mark.parametrize("acc,tol", [("f64", 1e-11), ("f32", 1e-5)])
+def test_rmp_column_cache_equals_sparse_evaluation(acc, tol):
+    """solveRMC's fast path: evaluations from cached dense aperture columns equal the sparse ones."""
+    case = make_case(V=30_000, nb=14, M=5, N=8, density=0.015, seed=85, ragged=True)
+    st = O.OracleState(case)
+    data = vl.bind(case, store="f32", acc=acc)
+    for state in (st, data):
+        all_candidates(state, case)
+    rng = np.random.default_rng(6)
+    sel = [1, 4, 5, 9, 12]
+    for bm in sel:
+        l = [int(rng.integers(-1, case.N - 2)) for _ in range(case.M)]
+        r = [int(min(case.N, lv + rng.integers(1, 6))) for lv in l]
+        select(st, case, bm, l, r, lambda k: O.update_open_aperture(st, k))
+        select(data, case, bm, l, r, vl.updateOpenAperture)
+    data._sync_apertures()
+    data.plan.rmp_begin(sel)
+    for trial in range(4):
+        y = np.zeros(case.nb)
+        y[sel] = rng.random(len(sel)) * 3
+        f0, g0 = O.calc_obj_grad_literal(st, y.copy())
+        f, g = data.plan.rmp_eval(y)
+        assert abs(f - f0) <= tol * abs(f0) and relerr(g, np.asarray(g0).ravel()) <= tol
+        assert relerr(data.plan.dose(), st.currentDose) <= tol
+        f2, g2 = data.plan.rmp_eval(y)
+        assert f2 == f and np.array_equal(g, g2)                 # reproducible
+    data.plan.rmp_end()
+    f3, g3 = data.plan.eval(y)                                    # the sparse path still works afterwards
+    assert abs(f3 - f0) <= tol * abs(f0)
+    data.plan.close()
+
+
+def test_greedy_loop_same_with_and_without_column_cache():
+    z, case = load_golden("colgen_B")
+    seqs = []
+    for flag in (True, False):
+        vl.use_column_cache = flag
+        try:
+            data = vl.bind(case, store="f32", acc="f64")
+            vl.colGen(float(z["C"]), False, int(z["kappasize"]), max_iter=int(z["max_iter"]))
+            seqs.append([(h["idx"], tuple(h["l"]), tuple(h["r"])) for h in data.history])
+            data.plan.close()
+        finally:
+            vl.use_column_cache = True
+    assert seqs[0] == seqs[1] == [(int(i), tuple(l), tuple(r)) for i, l, r in zip(z["idx"], z["l"], z["r"])]

@@ -46,6 +46,7 @@ eliminationThreshold = 10E-3
 eliminationPhase = False     # the reference hard-codes False inside colGen (:940); settable here
 kappasize = 16
 numcores = 8
+use_column_cache = True      # solveRMC evaluates from cached dense aperture columns (see solveRMC)
 penalizationweights = []     # Kelly complexity measure per selected control point (Laptop variant :484,863)
 
 
@@ -158,6 +159,8 @@ class vmat_class:
         self._gb = None
         self._fg = None
         self._vb_cache = {}
+        self._rmp_active = False     # solveRMC is running on the dense column cache
+        self._gb_valid = False       # the plan's beamlet gradient belongs to the current dose
 
     # currentDose / voxelgradient are read back from the GPU only when somebody looks
     @property
@@ -216,9 +219,14 @@ class vmat_class:
         published by calcGradientandObjValue()."""
         if self.plan is None:
             raise VmatError("no GPU plan bound: call VMATlibrary.bind(case) first")
-        self._sync_apertures()
         y = np.asarray(self.currentIntensities, dtype=float).ravel()
-        self._fg = self.plan.eval(y)
+        if self._rmp_active:
+            self._fg = self.plan.rmp_eval(y)         # apertures are fixed during an RMP: dense columns
+            self._gb_valid = False
+        else:
+            self._sync_apertures()
+            self._fg = self.plan.eval(y)
+            self._gb_valid = True
         self._dose = self._vg = self._gb = None
         self.dZdK = _LazyDZdK(self)
 
@@ -376,6 +384,8 @@ def _price(cands, C_, C2, C3, b, vmax, speedlim, Nn, Mm, bw):
     """Price a list of (index, predec, succ, angdistancem, angdistancep) in one launch."""
     if data._fg is None:
         raise VmatError("pricing needs the beamlet gradient of an evaluation: call data.calcDose() first")
+    if not data._gb_valid:       # the last evaluations came from the RMP column cache: refresh D^T vg
+        data.calcDose()
     rows = (PriceRow * (len(cands) * Mm))()
     for k, (idx, predec, succ, am, ap) in enumerate(cands):
         _fill_price_rows(rows, k * Mm, am, ap, vmax, speedlim, predec, succ, Nn, Mm, idx, bw)
@@ -494,12 +504,25 @@ def solveRMC(YU):
     only where an aperture is selected (greedyVMATsampling.py:858-885).  scipy stays on the
     host so that the iterates are the reference's; every callback is one GPU evaluation."""
     start = time.time()
-    calcObjGrad(data.currentIntensities)
-    boundschoice = [(0, YU) if k in data.caligraphicC.loc else (0, 0) for k in range(data.numbeams)]
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        res = minimize(calcObjGrad, data.currentIntensities, method="L-BFGS-B", jac=True,
-                       bounds=boundschoice, options={"ftol": 1e-1, "maxiter": 200})
+    cached = bool(use_column_cache and data.plan is not None and data.caligraphicC.len() > 0
+                  and getattr(data.plan, "fused_exchange", False) is False)
+    if cached:
+        # The apertures do not change inside an RMP, so D_i^T strengths_i and D_i^T diagmaker_i are
+        # computed once (sparse kernel) and every L-BFGS-B callback works on those dense columns.
+        data._sync_apertures()
+        data.plan.rmp_begin(list(data.caligraphicC.loc))
+        data._rmp_active = True
+    try:
+        calcObjGrad(data.currentIntensities)
+        boundschoice = [(0, YU) if k in data.caligraphicC.loc else (0, 0) for k in range(data.numbeams)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = minimize(calcObjGrad, data.currentIntensities, method="L-BFGS-B", jac=True,
+                           bounds=boundschoice, options={"ftol": 1e-1, "maxiter": 200})
+    finally:
+        if cached:
+            data._rmp_active = False
+            data.plan.rmp_end()
     data.rmp_seconds = time.time() - start
     return res
 

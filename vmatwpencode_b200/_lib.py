@@ -66,6 +66,9 @@ SIGNATURES = {
     "vmat_get_dose": (C.c_int, [_P, _P]),
     "vmat_get_voxelgrad": (C.c_int, [_P, _P]),
     "vmat_get_beamlet_grad": (C.c_int, [_P, _P]),
+    "vmat_rmp_begin": (C.c_int, [_P, C.c_int32, _P]),
+    "vmat_rmp_eval": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
+    "vmat_rmp_end": (C.c_int, [_P]),
     "vmat_dose_max": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "vmat_dvh_histogram": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P]),
     "vmat_price": (C.c_int, [_P, C.c_int32, _P, C.POINTER(PriceParams), C.POINTER(PriceRow), _P, _P, _P]),

@@ -5,6 +5,7 @@
 #include "vmat_eval_kernels.cuh"
 #include "vmat_price_kernels.cuh"
 #include "vmat_kmedoid_kernels.cuh"
+#include "vmat_rmp_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -82,6 +83,12 @@ struct vmat_plan {
     // pricing scratch
     DevBuf price_rows, price_cand, price_p, price_l, price_r, price_dad;
     size_t price_cap_cand = 0, price_cap_dad = 0;
+    // natural-order penalty tables and the RMP column cache (vmat_rmp_begin)
+    DevBuf thr_n, over_n, under_n, colA, colG, col_y, col_w, rmp_yk, rmp_beams, rmp_fpart, rmp_gpart;
+    std::vector<int32_t> rmp_cols;
+    int64_t rmp_ld = 0;
+    bool col_mode = false;
+    const void* col_w_ptr = nullptr;
     // per-kernel timing (vmat_set_timing)
     bool timing = false;
     std::vector<cudaEvent_t> tev;      // 4 events per evaluation slot
@@ -521,6 +528,14 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(P->counter.alloc(64));          CU(cudaMemset(P->counter.p, 0, 64));
     CU(P->fblock.alloc((size_t)std::max(1, P->k2_grid) * 8)); CU(cudaMemset(P->fblock.p, 0, (size_t)std::max(1, P->k2_grid) * 8));
     CU(P->scratch64.alloc(std::max<int64_t>(V, B) * 8));
+    {
+        std::vector<double> tt(thr, thr + V), oo(over, over + V), uu(under, under + V);
+        int rc = 0;
+        DISPATCH_ACC(P->opt.acc_dtype, AT, {
+            rc |= upload_cast<AT>(P->thr_n, tt, st); rc |= upload_cast<AT>(P->over_n, oo, st); rc |= upload_cast<AT>(P->under_n, uu, st);
+        });
+        if (rc) return VMAT_E_CUDA;
+    }
     CU(P->comm_buf.alloc((2 * (size_t)(B + 1) + 64) * 8));  CU(cudaMemset(P->comm_buf.p, 0, (2 * (size_t)(B + 1) + 64) * 8));
     CU(P->comm_state.alloc(64));         CU(cudaMemset(P->comm_state.p, 0, 64));
     CU(cudaHostAlloc(&P->h_y, nb * 8, cudaHostAllocMapped));
@@ -598,7 +613,8 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         if (!P->x_in_smem) {
             if (host_mode) CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, st));
             k4_expand_x<AT><<<(unsigned)((P->B + 255) / 256), 256, 0, st>>>(
-                (int32_t)P->B, P->y.as<double>(), P->beam_of.as<int32_t>(), P->w_dose.as<AT>(), P->xg.as<AT>());
+                (int32_t)P->B, P->col_mode ? P->col_y.as<double>() : P->y.as<double>(), P->beam_of.as<int32_t>(),
+                P->col_mode ? static_cast<const AT*>(P->col_w_ptr) : P->w_dose.as<AT>(), P->xg.as<AT>());
         }
         K1Args<AT> a1{};
         a1.sell = P->sell1.as<uint4>(); a1.ss_off = P->off1.as<int64_t>(); a1.ss_tpr = P->tpr1.as<uint8_t>(); a1.nss = P->nss1;
@@ -608,6 +624,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.d = P->d.as<AT>(); a1.vg = P->vg.as<AT>(); a1.fpart = P->fpart.as<double>();
         a1.counter = P->counter.as<unsigned int>();
         a1.nb = P->nb;
+        if (P->col_mode) { a1.y = P->col_y.as<double>(); a1.w_dose = static_cast<const AT*>(P->col_w_ptr); }
         if (host_mode && (P->host_path & 1)) { a1.y = P->d_hy; a1.y_mirror = P->y.as<double>(); a1.seq = P->counter.as<unsigned long long>() + 4; }
         else if (host_mode) { a1.seq = P->counter.as<unsigned long long>() + 4; a1.y_mirror = P->y.as<double>(); }
         DISPATCH_IW(IW, { DISPATCH_W1(W, {
@@ -621,6 +638,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
                 CU(launch_pdl(kern, P->k1_grid, P->k1_threads, P->k1_smem, st, P->pdl, a1));
             }
         }); });
+        if (P->col_mode) { CU(cudaGetLastError()); return 0; }      // column build: the dose kernel only
         if (ev) CU(cudaEventRecord(ev[1], st));
         K2Args<AT> a2{};
         a2.sell = P->sell2.as<uint4>(); a2.ss_off = P->off2.as<int64_t>(); a2.ss_tpr = P->tpr2.as<uint8_t>();
@@ -947,6 +965,110 @@ extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_bea
     CU(cudaMemcpyAsync(l, P->price_l.p, nrow * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(r, P->price_r.p, nrow * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return VMAT_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// restricted-master-problem column cache
+// ---------------------------------------------------------------------------------
+template <typename AT>
+static int rmp_begin_t(vmat_plan* P, int32_t ncols, const int32_t* beams) {
+    cudaStream_t st = P->stream;
+    const int64_t ld = (P->V + 63) / 64 * 64;
+    P->rmp_ld = ld;
+    CU(P->colA.alloc((size_t)ncols * ld * sizeof(AT)));
+    CU(P->colG.alloc((size_t)ncols * ld * sizeof(AT)));
+    CU(P->col_y.alloc(P->nb * 8));
+    CU(P->col_w.alloc(P->B * sizeof(AT)));
+    k_cast_from_f64<AT><<<(unsigned)((P->B + 255) / 256), 256, 0, st>>>(P->B, P->w_grad.as<double>(), P->col_w.as<AT>());
+    CU(cudaGetLastError());
+    const double one = 1.0;
+    for (int32_t k = 0; k < ncols; ++k) {
+        CU(cudaMemsetAsync(P->col_y.p, 0, P->nb * 8, st));
+        CU(cudaMemcpyAsync(P->col_y.as<double>() + beams[k], &one, 8, cudaMemcpyHostToDevice, st));
+        for (int which = 0; which < 2; ++which) {
+            P->col_mode = true;
+            P->col_w_ptr = which == 0 ? P->w_dose.p : P->col_w.p;
+            CU(cudaMemsetAsync(P->counter.p, 0, 4, st));
+            const int rc = launch_eval(P, st, 0, false);
+            P->col_mode = false;
+            if (rc) return rc;
+            AT* dst = (which == 0 ? P->colA.as<AT>() : P->colG.as<AT>()) + (size_t)k * ld;
+            CU(cudaMemcpyAsync(dst, P->d.p, P->V * sizeof(AT), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    CU(cudaMemsetAsync(P->counter.p, 0, 4, st));
+    const int32_t chunk = 16384;
+    const int32_t nchunks = (int32_t)((P->V + chunk - 1) / chunk);
+    const int64_t nblk = (P->V + 255) / 256;
+    CU(P->rmp_yk.alloc(ncols * 8));
+    CU(P->rmp_fpart.alloc(nblk * 8 * 8));    CU(cudaMemsetAsync(P->rmp_fpart.p, 0, nblk * 8 * 8, st));
+    CU(P->rmp_gpart.alloc((size_t)ncols * nchunks * 8));
+    std::vector<int32_t> hb(beams, beams + ncols);
+    if (upload_vec(P->rmp_beams, hb, st)) return VMAT_E_CUDA;
+    CU(cudaMemsetAsync(P->result.p, 0, (P->nb + 1) * 8, st));
+    CU(cudaMemsetAsync(P->counter.as<unsigned int>() + 12, 0, 4, st));
+    CU(cudaStreamSynchronize(st));
+    P->rmp_cols = hb;
+    return 0;
+}
+
+extern "C" int vmat_rmp_begin(vmat_plan_t* P, int32_t ncols, const int32_t* beams) {
+    if (!P || ncols < 1 || ncols > 512 || !beams) return fail(VMAT_E_ARG, "vmat_rmp_begin: need 1..512 control points");
+    for (int32_t k = 0; k < ncols; ++k)
+        if (beams[k] < 0 || beams[k] >= P->nb) return fail(VMAT_E_ARG, "vmat_rmp_begin: bad control point");
+    if (P->comm_nranks > 1) return fail(VMAT_E_UNSUPPORTED, "vmat_rmp_begin: not available on the sharded path");
+    CU(cudaSetDevice(P->device));
+    CU(cudaDeviceSynchronize());
+    DISPATCH_ACC(P->opt.acc_dtype, AT, { return rmp_begin_t<AT>(P, ncols, beams); });
+    return 0;
+}
+
+template <typename AT>
+static int rmp_eval_t(vmat_plan* P) {
+    cudaStream_t st = P->stream;
+    const int32_t ncols = (int32_t)P->rmp_cols.size();
+    RmpArgs<AT> a{};
+    a.V = P->V; a.ld = P->rmp_ld; a.ncols = ncols; a.chunk = 16384; a.nchunks = (int32_t)((P->V + a.chunk - 1) / a.chunk);
+    a.A = P->colA.as<AT>(); a.G = P->colG.as<AT>(); a.yk = P->rmp_yk.as<double>(); a.beams = P->rmp_beams.as<int32_t>();
+    a.thr = P->thr_n.as<AT>(); a.over = P->over_n.as<AT>(); a.under = P->under_n.as<AT>();
+    a.d = P->d.as<AT>(); a.vg = P->vg.as<AT>();
+    const int64_t nblk = (P->V + 255) / 256;
+    a.fpart = P->rmp_fpart.as<double>(); a.nfpart = (int32_t)(nblk * 8);
+    a.gpart = P->rmp_gpart.as<double>(); a.result = P->result.as<double>();
+    a.done = P->counter.as<unsigned int>() + 12;
+    k8_rmp_dose<AT><<<(unsigned)nblk, 256, 0, st>>>(a);
+    k8_rmp_grad<AT><<<dim3((unsigned)a.nchunks, (unsigned)ncols), 256, 0, st>>>(a);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vmat_rmp_eval(vmat_plan_t* P, const double* y, double* f, double* g) {
+    if (!P || !y) return fail(VMAT_E_ARG, "vmat_rmp_eval: null");
+    if (P->rmp_cols.empty()) return fail(VMAT_E_STATE, "vmat_rmp_eval: no column cache (call vmat_rmp_begin)");
+    CU(cudaSetDevice(P->device));
+    const int32_t ncols = (int32_t)P->rmp_cols.size();
+    std::memcpy(P->h_y, y, P->nb * 8);
+    std::vector<double> yk(ncols);
+    for (int32_t k = 0; k < ncols; ++k) yk[k] = y[P->rmp_cols[k]];
+    std::memcpy(P->h_res, yk.data(), std::min<size_t>(ncols, P->nb + 1) * 8);       // pinned staging
+    if ((size_t)ncols <= (size_t)P->nb + 1) CU(cudaMemcpyAsync(P->rmp_yk.p, P->h_res, ncols * 8, cudaMemcpyHostToDevice, P->stream));
+    else CU(cudaMemcpy(P->rmp_yk.p, yk.data(), ncols * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
+    DISPATCH_ACC(P->opt.acc_dtype, AT, { if (int rc = rmp_eval_t<AT>(P)) return rc; });
+    CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    if (f) *f = P->h_res[0];
+    if (g) std::memcpy(g, P->h_res + 1, P->nb * 8);
+    return VMAT_OK;
+}
+
+extern "C" int vmat_rmp_end(vmat_plan_t* P) {
+    if (!P) return fail(VMAT_E_ARG, "null plan");
+    CU(cudaSetDevice(P->device));
+    CU(cudaDeviceSynchronize());
+    P->colA.alloc(0); P->colG.alloc(0); P->rmp_gpart.alloc(0); P->rmp_fpart.alloc(0);
+    P->rmp_cols.clear();
     return VMAT_OK;
 }
 

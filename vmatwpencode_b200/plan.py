@@ -217,6 +217,20 @@ class DosePlan:
         check(self._lib.vmat_get_beamlet_grad(self._h, _ptr(out)), "vmat_get_beamlet_grad")
         return out
 
+    # -- restricted master problem: dense column cache ---------------------------------
+    def rmp_begin(self, beams):
+        b = np.ascontiguousarray(beams, dtype=np.int32)
+        check(self._lib.vmat_rmp_begin(self._h, len(b), _ptr(b)), "vmat_rmp_begin")
+
+    def rmp_eval(self, y):
+        self._y[:] = y
+        f = C.c_double()
+        check(self._lib.vmat_rmp_eval(self._h, _ptr(self._y), C.byref(f), _ptr(self._g)), "vmat_rmp_eval")
+        return f.value, self._g.copy()
+
+    def rmp_end(self):
+        check(self._lib.vmat_rmp_end(self._h), "vmat_rmp_end")
+
     # -- dose-volume histograms ------------------------------------------------------
     def dose_max(self) -> float:
         m = C.c_double()
