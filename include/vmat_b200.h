@@ -175,7 +175,9 @@ int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
  * apertures of the listed control points stay fixed, vmat_rmp_begin caches their dose columns
  * D_i^T w_dose_i and gradient columns D_i^T w_grad_i (dense, V each); vmat_rmp_eval then evaluates
  * (f, g) for intensities y[nb] from the cache (control points outside the list contribute nothing
- * and get g = 0, as they have zero weights in calcDose anyway).  vmat_rmp_end drops the cache.
+ * and get g = 0, as they have zero weights in calcDose anyway).  vmat_rmp_end ends the RMP; the
+ * columns stay cached, and the next vmat_rmp_begin only rebuilds control points whose aperture was
+ * set again (vmat_set_aperture) in between - one new aperture per greedy iteration.
  * The beamlet gradient used by pricing is NOT refreshed by vmat_rmp_eval.
  */
 int vmat_rmp_begin(vmat_plan_t* plan, int32_t ncols, const int32_t* beams);

@@ -531,5 +531,5 @@ def test_greedy_loop_same_with_and_without_column_cache():
             seqs.append([(h["idx"], tuple(h["l"]), tuple(h["r"])) for h in data.history])
             data.plan.close()
         finally:
-            vl.use_column_cache = True
+            vl.use_column_cache = False
     assert seqs[0] == seqs[1] == [(int(i), tuple(l), tuple(r)) for i, l, r in zip(z["idx"], z["l"], z["r"])]

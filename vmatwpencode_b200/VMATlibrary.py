@@ -46,7 +46,8 @@ eliminationThreshold = 10E-3
 eliminationPhase = False     # the reference hard-codes False inside colGen (:940); settable here
 kappasize = 16
 numcores = 8
-use_column_cache = True      # solveRMC evaluates from cached dense aperture columns (see solveRMC)
+use_column_cache = False     # True: solveRMC evaluates from cached dense aperture columns (pays off when an
+                             # RMP needs many evaluations; with the reference's ftol=1e-1 it needs ~5)
 penalizationweights = []     # Kelly complexity measure per selected control point (Laptop variant :484,863)
 
 

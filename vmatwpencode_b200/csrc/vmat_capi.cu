@@ -85,7 +85,11 @@ struct vmat_plan {
     size_t price_cap_cand = 0, price_cap_dad = 0;
     // natural-order penalty tables and the RMP column cache (vmat_rmp_begin)
     DevBuf thr_n, over_n, under_n, colA, colG, col_y, col_w, rmp_yk, rmp_beams, rmp_fpart, rmp_gpart;
-    std::vector<int32_t> rmp_cols;
+    std::vector<int32_t> rmp_cols;                 // control points of the active RMP
+    std::vector<int32_t> col_slot, col_built;      // per control point: slot in colA/colG (-1 none), aperture epoch it was built from
+    std::vector<int32_t> ap_epoch;                 // per control point: bumped by vmat_set_aperture
+    DevBuf rmp_slots;
+    int32_t col_cap = 0, col_used = 0;
     int64_t rmp_ld = 0;
     bool col_mode = false;
     const void* col_w_ptr = nullptr;
@@ -704,6 +708,8 @@ extern "C" int vmat_set_aperture(vmat_plan_t* P, int32_t beam, const double* w_d
     CU(cudaSetDevice(P->device));
     const int32_t lo = P->beam_ptr[beam], n = P->beam_ptr[beam + 1] - lo;
     if (n == 0) return VMAT_OK;
+    if (P->ap_epoch.empty()) P->ap_epoch.assign(P->nb, 0);
+    P->ap_epoch[beam]++;                 // cached RMP columns of this control point are stale now
     const size_t as = P->acc_size;
     CU(cudaStreamSynchronize(P->stream));
     if (w_dose) {
@@ -975,17 +981,40 @@ template <typename AT>
 static int rmp_begin_t(vmat_plan* P, int32_t ncols, const int32_t* beams) {
     cudaStream_t st = P->stream;
     const int64_t ld = (P->V + 63) / 64 * 64;
-    P->rmp_ld = ld;
-    CU(P->colA.alloc((size_t)ncols * ld * sizeof(AT)));
-    CU(P->colG.alloc((size_t)ncols * ld * sizeof(AT)));
-    CU(P->col_y.alloc(P->nb * 8));
-    CU(P->col_w.alloc(P->B * sizeof(AT)));
-    k_cast_from_f64<AT><<<(unsigned)((P->B + 255) / 256), 256, 0, st>>>(P->B, P->w_grad.as<double>(), P->col_w.as<AT>());
-    CU(cudaGetLastError());
+    if (P->ap_epoch.empty()) P->ap_epoch.assign(P->nb, 0);
+    if (P->col_cap == 0) {
+        // column store: room for every control point if that fits in a quarter of the free memory
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per = 2 * (size_t)ld * sizeof(AT);
+        const int32_t cap = (int32_t)std::min<size_t>((size_t)P->nb, free_b / 4 / per);
+        if (cap < 1) return fail(VMAT_E_NOMEM, "vmat_rmp_begin: no memory for the column cache");
+        CU(P->colA.alloc((size_t)cap * ld * sizeof(AT)));
+        CU(P->colG.alloc((size_t)cap * ld * sizeof(AT)));
+        CU(P->col_y.alloc(P->nb * 8));
+        CU(P->col_w.alloc(P->B * sizeof(AT)));
+        P->col_cap = cap; P->col_used = 0; P->rmp_ld = ld;
+        P->col_slot.assign(P->nb, -1); P->col_built.assign(P->nb, -1);
+        const int64_t nblk = (P->V + 255) / 256;
+        CU(P->rmp_fpart.alloc(nblk * 8 * 8));    CU(cudaMemsetAsync(P->rmp_fpart.p, 0, nblk * 8 * 8, st));
+    }
+    // (re)build only the columns whose aperture changed since they were cached
+    bool cast_done = false;
     const double one = 1.0;
     for (int32_t k = 0; k < ncols; ++k) {
+        const int32_t bm = beams[k];
+        if (P->col_slot[bm] >= 0 && P->col_built[bm] == P->ap_epoch[bm]) continue;
+        if (P->col_slot[bm] < 0) {
+            if (P->col_used >= P->col_cap) return fail(VMAT_E_NOMEM, "vmat_rmp_begin: column cache is full");
+            P->col_slot[bm] = P->col_used++;
+        }
+        if (!cast_done) {
+            k_cast_from_f64<AT><<<(unsigned)((P->B + 255) / 256), 256, 0, st>>>(P->B, P->w_grad.as<double>(), P->col_w.as<AT>());
+            CU(cudaGetLastError());
+            cast_done = true;
+        }
         CU(cudaMemsetAsync(P->col_y.p, 0, P->nb * 8, st));
-        CU(cudaMemcpyAsync(P->col_y.as<double>() + beams[k], &one, 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(P->col_y.as<double>() + bm, &one, 8, cudaMemcpyHostToDevice, st));
         for (int which = 0; which < 2; ++which) {
             P->col_mode = true;
             P->col_w_ptr = which == 0 ? P->w_dose.p : P->col_w.p;
@@ -993,19 +1022,20 @@ static int rmp_begin_t(vmat_plan* P, int32_t ncols, const int32_t* beams) {
             const int rc = launch_eval(P, st, 0, false);
             P->col_mode = false;
             if (rc) return rc;
-            AT* dst = (which == 0 ? P->colA.as<AT>() : P->colG.as<AT>()) + (size_t)k * ld;
+            AT* dst = (which == 0 ? P->colA.as<AT>() : P->colG.as<AT>()) + (size_t)P->col_slot[bm] * ld;
             CU(cudaMemcpyAsync(dst, P->d.p, P->V * sizeof(AT), cudaMemcpyDeviceToDevice, st));
         }
+        P->col_built[bm] = P->ap_epoch[bm];
     }
     CU(cudaMemsetAsync(P->counter.p, 0, 4, st));
     const int32_t chunk = 16384;
     const int32_t nchunks = (int32_t)((P->V + chunk - 1) / chunk);
-    const int64_t nblk = (P->V + 255) / 256;
     CU(P->rmp_yk.alloc(ncols * 8));
-    CU(P->rmp_fpart.alloc(nblk * 8 * 8));    CU(cudaMemsetAsync(P->rmp_fpart.p, 0, nblk * 8 * 8, st));
     CU(P->rmp_gpart.alloc((size_t)ncols * nchunks * 8));
-    std::vector<int32_t> hb(beams, beams + ncols);
+    std::vector<int32_t> hb(beams, beams + ncols), hs(ncols);
+    for (int32_t k = 0; k < ncols; ++k) hs[k] = P->col_slot[beams[k]];
     if (upload_vec(P->rmp_beams, hb, st)) return VMAT_E_CUDA;
+    if (upload_vec(P->rmp_slots, hs, st)) return VMAT_E_CUDA;
     CU(cudaMemsetAsync(P->result.p, 0, (P->nb + 1) * 8, st));
     CU(cudaMemsetAsync(P->counter.as<unsigned int>() + 12, 0, 4, st));
     CU(cudaStreamSynchronize(st));
@@ -1030,7 +1060,7 @@ static int rmp_eval_t(vmat_plan* P) {
     const int32_t ncols = (int32_t)P->rmp_cols.size();
     RmpArgs<AT> a{};
     a.V = P->V; a.ld = P->rmp_ld; a.ncols = ncols; a.chunk = 16384; a.nchunks = (int32_t)((P->V + a.chunk - 1) / a.chunk);
-    a.A = P->colA.as<AT>(); a.G = P->colG.as<AT>(); a.yk = P->rmp_yk.as<double>(); a.beams = P->rmp_beams.as<int32_t>();
+    a.A = P->colA.as<AT>(); a.G = P->colG.as<AT>(); a.yk = P->rmp_yk.as<double>(); a.beams = P->rmp_beams.as<int32_t>(); a.slots = P->rmp_slots.as<int32_t>();
     a.thr = P->thr_n.as<AT>(); a.over = P->over_n.as<AT>(); a.under = P->under_n.as<AT>();
     a.d = P->d.as<AT>(); a.vg = P->vg.as<AT>();
     const int64_t nblk = (P->V + 255) / 256;
@@ -1067,8 +1097,7 @@ extern "C" int vmat_rmp_end(vmat_plan_t* P) {
     if (!P) return fail(VMAT_E_ARG, "null plan");
     CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());
-    P->colA.alloc(0); P->colG.alloc(0); P->rmp_gpart.alloc(0); P->rmp_fpart.alloc(0);
-    P->rmp_cols.clear();
+    P->rmp_cols.clear();            // the columns stay cached: the next RMP only builds what changed
     return VMAT_OK;
 }
 

@@ -18,6 +18,7 @@ struct RmpArgs {
     const AT* G;                  // [ncols][ld] gradient columns
     const double* yk;             // [ncols] intensities of the cached control points
     const int32_t* beams;         // [ncols] control point of every column
+    const int32_t* slots;         // [ncols] where that control point's columns live in A / G
     const AT* thr; const AT* over; const AT* under;   // natural voxel order
     AT* d; AT* vg;                // [V]
     double* fpart;                // [gridDim.x of the dose kernel * warps] objective partials
@@ -30,15 +31,16 @@ struct RmpArgs {
 template <typename AT>
 __global__ void __launch_bounds__(256) k8_rmp_dose(const RmpArgs<AT> a) {
     __shared__ double ys[512];
+    __shared__ int32_t sl[512];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < a.ncols; k += 256) ys[k] = a.yk[k];
+    for (int k = tid; k < a.ncols; k += 256) { ys[k] = a.yk[k]; sl[k] = a.slots[k]; }
     __syncthreads();
     const int64_t v = (int64_t)blockIdx.x * 256 + tid;
     double fterm = 0.0;
     if (v < a.V) {
         AT acc = (AT)0;
         const AT* col = a.A + v;
-        for (int k = 0; k < a.ncols; ++k) acc = fma_acc(col[(int64_t)k * a.ld], (AT)ys[k], acc);
+        for (int k = 0; k < a.ncols; ++k) acc = fma_acc(col[(int64_t)sl[k] * a.ld], (AT)ys[k], acc);
         const AT t = a.thr[v], ov = a.over[v], un = a.under[v];
         AT o = sub_rn(acc, t);  o = o > (AT)0 ? o : (AT)0;
         AT u = sub_rn(t, acc);  u = u > (AT)0 ? u : (AT)0;
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(256) k8_rmp_grad(const RmpArgs<AT> a) {
     const int tid = threadIdx.x;
     const int c = blockIdx.x, k = blockIdx.y;
     const int64_t v0 = (int64_t)c * a.chunk, v1 = min(a.V, v0 + a.chunk);
-    const AT* col = a.G + (int64_t)k * a.ld;
+    const AT* col = a.G + (int64_t)a.slots[k] * a.ld;
     double s = 0.0;
     for (int64_t v = v0 + tid; v < v1; v += 256) s += (double)col[v] * (double)a.vg[v];
     sh[tid] = s;
