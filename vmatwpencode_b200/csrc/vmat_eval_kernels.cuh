@@ -190,7 +190,10 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT>
             named_bar_sync(1, W * 32);
         }
     }
-    pdl_wait();     // d, vg, fpart and the slice counter belong to the previous evaluation until here
+    // d, vg, fpart and the slice counter belong to the previous evaluation until its kernels are
+    // done: consumers wait here; the producer first streams its statically assigned super-slice
+    // (read-only data into its own ring) and waits only before it touches the counter
+    if (warp < W) pdl_wait();
     if (a.seq != nullptr && blockIdx.x == 0 && warp < W) {
         if (XS) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
         if (tid == 0) atomicAdd(a.seq, 1ull);
@@ -202,15 +205,20 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT>
             const uint64_t pol = l2_evict_first_policy();
             RingPos pos;
             const unsigned int ns = (unsigned)a.nss;
-            unsigned int cur = atomicAdd(a.counter, 1u), nxt = atomicAdd(a.counter, 1u);
-            int64_t o0 = 0, o1 = 0;
-            if (cur < ns) { o0 = a.ss_off[cur]; o1 = a.ss_off[cur + 1]; }
+            // super-slices 0 .. gridDim-1 (the longest) are assigned statically, the rest are
+            // claimed from the counter, one claim ahead of use
+            const unsigned int G = gridDim.x;
+            unsigned int cur = blockIdx.x, nxt = 0, nn = 0;
+            bool claimed = false;
+            int64_t o0 = 0, o1 = 0, n0 = 0, n1 = 0;
+            int tpr = 1, ntpr = 1;
+            if (cur < ns) { o0 = a.ss_off[cur]; o1 = a.ss_off[cur + 1]; tpr = a.ss_tpr[cur]; }
             while (cur < ns) {
-                const unsigned int nn = atomicAdd(a.counter, 1u);
-                int64_t n0 = 0, n1 = 0;
-                if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; }
+                if (claimed) {
+                    nn = G + atomicAdd(a.counter, 1u);
+                    if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; ntpr = a.ss_tpr[nxt]; }
+                }
                 const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
-                const int tpr = a.ss_tpr[cur];
                 ring_push(ring, SB, full, empty, sinfo, pos, nst,
                           StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0), 0, tpr},
                           a.sell + o0, W * HU * 16, pol);
@@ -219,7 +227,14 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT>
                     ring_push(ring, SB, full, empty, sinfo, pos, nst,
                               StageInfo{(int32_t)cur, c == nch - 1 ? kStageLast : 0, 0, tpr},
                               data + (int64_t)c * W * KU, W * KU * 16, pol);
-                cur = nxt; nxt = nn; o0 = n0; o1 = n1;
+                if (!claimed) {
+                    pdl_wait();                       // the counter was reset by the previous evaluation's K2
+                    nxt = G + atomicAdd(a.counter, 1u);
+                    nn = G + atomicAdd(a.counter, 1u);
+                    if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; ntpr = a.ss_tpr[nxt]; }
+                    claimed = true;
+                }
+                cur = nxt; nxt = nn; o0 = n0; o1 = n1; tpr = ntpr;
             }
             ring_push(ring, SB, full, empty, sinfo, pos, nst, StageInfo{-1, 0, 0, 0}, nullptr, 0, pol);
         }
@@ -347,6 +362,19 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
 
     pdl_wait();          // vg is complete, the previous K3 has consumed `partial`
     if (blockIdx.x == 0 && tid == 0) *a.k1_counter = 0u;
+    int cur_tile = -1;
+    bool tile_pending = false;
+    if (t_begin < t_end) {   // the first tile is requested right away, not when the first header arrives
+        cur_tile = a.tasks[t_begin].tile;
+        if (tid == 0) {
+            const int64_t base = (int64_t)cur_tile * a.T;
+            const int n = (int)min((int64_t)a.T, a.V - base);
+            const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(AT) + 15) & ~(size_t)15);
+            mbar_expect_tx(&tilebar, bytes);
+            tma_bulk_g2s(vt, a.vg + base, bytes, &tilebar);
+        }
+        tile_pending = true;
+    }
     if (warp == 0) {     // objective: this CTA's fixed share of the per-slice partials (order fixed -> reproducible)
         const int per = (a.nfpart + gridDim.x - 1) / gridDim.x;
         const int f0 = blockIdx.x * per, f1 = min(a.nfpart, f0 + per);
@@ -359,7 +387,6 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     RingPos pos;
     AT acc = (AT)0;
     int32_t row = -1;
-    int cur_tile = -1;
     uint32_t tparity = 0;
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
@@ -379,6 +406,11 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
                 mbar_wait(&tilebar, tparity);
                 tparity ^= 1u;
                 cur_tile = info.tile;
+                tile_pending = false;
+            } else if (tile_pending) {
+                mbar_wait(&tilebar, tparity);
+                tparity ^= 1u;
+                tile_pending = false;
             }
             row = reinterpret_cast<const int32_t*>(sp + warp * (HU * 16))[lane];
             acc = (AT)0;
