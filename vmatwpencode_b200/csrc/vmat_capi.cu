@@ -1,6 +1,7 @@
 // libvmat_b200.so - C ABI (include/vmat_b200.h) over the sm_100a kernels.
-// Plan construction (CSR -> row-sorted sliced-ELL layouts), evaluation launch sequence
-// (K1 -> K2 -> K3, optionally replayed as one CUDA graph), result transfer.
+// Plan construction (CSR -> row-sorted sliced-ELL streams), evaluation launch sequence
+// (K1 -> K2 -> K3 chained by programmatic dependent launch, replayed as one CUDA graph on the
+// host-buffer path), result transfer, cross-GPU exchange set-up, pricing, RMP column cache, DVH.
 #include "../../include/vmat_b200.h"
 #include "vmat_eval_kernels.cuh"
 #include "vmat_price_kernels.cuh"
@@ -139,9 +140,6 @@ extern "C" void vmat_default_options(vmat_options_t* o) {
         case VMAT_F64: { using AT = double; __VA_ARGS__; break; }            \
         default: return fail(VMAT_E_ARG, "bad accumulate dtype");            \
     }
-
-template <typename VT> struct Unroll { static constexpr int U = 4; };
-template <> struct Unroll<double> { static constexpr int U = 2; };
 
 static int store_units(int dt, int iw) { return 8 * iw + (dt == VMAT_F32 ? 32 : dt == VMAT_BF16 ? 16 : 64); }
 static int store_bytes(int dt) { return dt == VMAT_F32 ? 4 : dt == VMAT_BF16 ? 2 : 8; }

@@ -7,21 +7,7 @@
 namespace vmat {
 
 constexpr int kWarp = 32;
-constexpr int kChunk = 4;          // nonzeros per lane per chunk (one 128-bit index load)
-
-// ---- streaming 128/64-bit loads that do not pollute L1 -------------------------------
-__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint2 ldg_stream8(const void* p) {
-    uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
-                 : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
+constexpr int kChunk = 4;          // nonzeros per lane per chunk
 
 // ---- TMA bulk copy (global -> shared) completed on an mbarrier ---------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,48 +59,6 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
-
-// ---- layout traits: one SELL chunk = 32 lanes x 4 nonzeros -------------------------
-// A chunk is a run of 16-byte units: 32 units of int4 indices (unit `lane` belongs to
-// lane), then the values.  f32: 32 units of float4.  bf16: 16 units (lane owns 8 bytes).
-// f64: 64 units, (v0,v1) of every lane first, then (v2,v3) of every lane.
-template <typename VT> struct Store;
-template <> struct Store<float> {
-    static constexpr int kUnits = 64;
-    static constexpr int kBytesPerNnz = 8;
-    struct Raw { uint4 v; };
-    __device__ static __forceinline__ Raw load(const uint4* chunk, int lane) {
-        return Raw{ldg_stream16(chunk + 32 + lane)};
-    }
-    template <typename AT> __device__ static __forceinline__ void unpack(const Raw& r, AT (&o)[4]) {
-        o[0] = (AT)__uint_as_float(r.v.x); o[1] = (AT)__uint_as_float(r.v.y);
-        o[2] = (AT)__uint_as_float(r.v.z); o[3] = (AT)__uint_as_float(r.v.w);
-    }
-};
-template <> struct Store<__nv_bfloat16> {
-    static constexpr int kUnits = 48;
-    static constexpr int kBytesPerNnz = 6;
-    struct Raw { uint2 v; };
-    __device__ static __forceinline__ Raw load(const uint4* chunk, int lane) {
-        return Raw{ldg_stream8(reinterpret_cast<const unsigned char*>(chunk + 32) + lane * 8)};
-    }
-    template <typename AT> __device__ static __forceinline__ void unpack(const Raw& r, AT (&o)[4]) {
-        o[0] = (AT)__uint_as_float(r.v.x << 16); o[1] = (AT)__uint_as_float(r.v.x & 0xffff0000u);
-        o[2] = (AT)__uint_as_float(r.v.y << 16); o[3] = (AT)__uint_as_float(r.v.y & 0xffff0000u);
-    }
-};
-template <> struct Store<double> {
-    static constexpr int kUnits = 96;
-    static constexpr int kBytesPerNnz = 12;
-    struct Raw { uint4 a, b; };
-    __device__ static __forceinline__ Raw load(const uint4* chunk, int lane) {
-        return Raw{ldg_stream16(chunk + 32 + lane), ldg_stream16(chunk + 64 + lane)};
-    }
-    template <typename AT> __device__ static __forceinline__ void unpack(const Raw& r, AT (&o)[4]) {
-        o[0] = (AT)__hiloint2double(r.a.y, r.a.x); o[1] = (AT)__hiloint2double(r.a.w, r.a.z);
-        o[2] = (AT)__hiloint2double(r.b.y, r.b.x); o[3] = (AT)__hiloint2double(r.b.w, r.b.z);
-    }
-};
 
 // chunk geometry in 16-byte units: index block (4 indices per lane, IW bytes each) then value block
 template <typename VT> __host__ __device__ constexpr int val_units() { return 8 * (int)sizeof(VT); }     // f32 32, bf16 16, f64 64
