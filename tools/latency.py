@@ -8,7 +8,7 @@ from vmatwpencode_b200.plan import DosePlan
 
 case, y, w_dose, w_grad = workload("cfg2", 1.0)
 Dt = case.D.tocsc()
-for name, kw in [("zero-copy both", dict(host_path=3)), ("zero-copy y only", dict(host_path=1)),
+for name, kw in [("tags + y in launch params", dict(host_path=6)), ("tags + H2D node (default)", dict(host_path=2)), ("zero-copy both", dict(host_path=3)), ("zero-copy y only", dict(host_path=1)),
                  ("zero-copy result only", dict(host_path=2)), ("memcpy nodes", dict(host_path=4)),
                  ("memcpy nodes, no graph", dict(host_path=4, use_graph=False)), ("zero-copy both, no graph", dict(host_path=3, use_graph=False)),
                  ("memcpy nodes, no pdl", dict(host_path=4, pdl=False))]:

@@ -340,7 +340,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     if (P->opt.store_dtype < 0 || P->opt.store_dtype > 2) return fail(VMAT_E_ARG, "bad store_dtype");
     P->acc_size = P->opt.acc_dtype == VMAT_F64 ? 8 : 4;
     P->pdl = P->opt.reserved[3] == 0;
-    P->host_path = P->opt.reserved[4] > 0 ? (P->opt.reserved[4] & 3) : 2;   // reserved[4]: 4 = memcpy nodes both ways, 1/2/3 = zero-copy bits      // reserved[3] = 1 disables programmatic dependent launch
+    P->host_path = P->opt.reserved[4] > 0 ? (P->opt.reserved[4] & 7) : 2;     // bit 2 (4): y inside the launch parameters (no graph)   // reserved[4]: 4 = memcpy nodes both ways, 1/2/3 = zero-copy bits      // reserved[3] = 1 disables programmatic dependent launch
     P->beam_ptr.assign(beam_ptr, beam_ptr + nb + 1);
     CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -626,6 +626,10 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.d = P->d.as<AT>(); a1.vg = P->vg.as<AT>(); a1.fpart = P->fpart.as<double>();
         a1.counter = P->counter.as<unsigned int>();
         a1.nb = P->nb;
+        if (host_mode && (P->host_path & 4) && P->nb <= kInlineY && P->x_in_smem) {
+            a1.y_inline_n = P->nb;
+            std::memcpy(a1.y_inline, P->h_y, (size_t)P->nb * 8);
+        }
         if (P->col_mode) { a1.y = P->col_y.as<double>(); a1.w_dose = static_cast<const AT*>(P->col_w_ptr); }
         if (host_mode && (P->host_path & 1)) { a1.y = P->d_hy; a1.y_mirror = P->y.as<double>(); a1.seq = P->counter.as<unsigned long long>() + 4; }
         else if (host_mode) { a1.seq = P->counter.as<unsigned long long>() + 4; a1.y_mirror = P->y.as<double>(); }
@@ -748,9 +752,10 @@ extern "C" int vmat_eval(vmat_plan_t* P, const double* y, double* f, double* g) 
     CU(cudaSetDevice(P->device));
     std::memcpy(P->h_y, y, P->nb * 8);
     const bool multi = P->comm_nranks > 1;            // fused exchange: plain copies, no host tags
-    const bool zc_y = (P->host_path & 1) && !multi, zc_res = (P->host_path & 2) && !multi;
+    const bool inline_y = (P->host_path & 4) && !multi && P->nb <= kInlineY && P->x_in_smem;
+    const bool zc_y = ((P->host_path & 1) && !multi) || inline_y, zc_res = (P->host_path & 2) && !multi;
     const unsigned long long expect = ++P->host_seq;
-    if (P->graph_exec && !multi) {
+    if (P->graph_exec && !multi && !inline_y) {
         CU(cudaGraphLaunch(P->graph_exec, P->stream));
     } else {
         if (!zc_y) CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));

@@ -135,6 +135,8 @@ __global__ void k4_expand_x(int32_t B, const double* __restrict__ y, const int32
 // CTA = W consumer warps + 1 producer warp; persistent, one CTA per SM; super-slices are
 // claimed from an atomic counter, longest first.
 // ---------------------------------------------------------------------------------
+constexpr int kInlineY = 384;
+
 template <typename AT>
 struct K1Args {
     const uint4* sell;            // stream (voxel-major)
@@ -157,10 +159,14 @@ struct K1Args {
     double* y_mirror;             // [nb] or nullptr
     int32_t nb;
     unsigned long long* seq;      // nullptr on the resident path
+    // host-buffer path, nb <= kInlineY: the intensities travel inside the launch parameters, so no
+    // host-to-device copy sits in front of the kernel
+    int32_t y_inline_n;
+    double y_inline[kInlineY];
 };
 
 template <typename VT, typename AT, bool XS, int W, int IW>
-__global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT> a) {
+__global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_constant__ K1Args<AT> a) {
     constexpr int KU = chunk_units<VT, IW>(), HU = header_units_k1<AT>();
     constexpr int kMaxStages = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -184,7 +190,8 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const K1Args<AT>
         if (XS) {   // x_j = y[beam(j)] * w_dose[j]   (K4 folded into the prologue; consumers only -
                     // the producer is already streaming D meanwhile)
             // y (possibly in mapped host memory) is read once per CTA into shared memory
-            for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y[j];
+            if (a.y_inline_n > 0) { for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y_inline[j]; }
+            else { for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y[j]; }
             named_bar_sync(1, W * 32);
             for (int j = tid; j < a.B; j += W * 32) xs[j] = mul_rn((AT)ys[a.beam_of[j]], a.w_dose[j]);
             named_bar_sync(1, W * 32);
