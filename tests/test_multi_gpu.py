@@ -71,3 +71,47 @@ def test_two_gpu_sharded_evaluation(tmp_path):
     assert np.abs(z["gb_fused"] - gb0).max() <= 1e-11 * np.abs(gb0).max()
     # the fused exchange adds the ranks in rank order on every rank: evaluations repeat bit for bit
     assert np.array_equal(z["fused"][0], z["fused"][3]) and np.array_equal(z["fused"][1], z["fused"][4])
+
+
+def _greedy_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from vmatwpencode_b200 import VMATlibrary as vl
+    from vmatwpencode_b200.synth import make_case
+    case = make_case(V=20_000, nb=16, M=5, N=8, density=0.01, seed=94, gastep=10)
+    data = vl.bind(case, device=rank, store="f32", acc="f64", shard=True)
+    vl.colGen(0.01, False, 6, max_iter=8)
+    hist = [(h["idx"], h["l"], h["r"], h["fun"]) for h in data.history]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, hist)
+    if rank == 0:
+        np.save(out, np.array([g == gathered[0] for g in gathered]))
+        import pickle
+        with open(out + ".pkl", "wb") as f:
+            pickle.dump(hist, f)
+    dist.barrier()
+    data.plan.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_greedy_loop_matches_oracle(tmp_path):
+    """The whole greedy loop on a voxel-sharded plan: both ranks take the same decisions (the
+    fused exchange gives them identical bits) and the aperture sequence is the oracle's."""
+    import pickle
+    import torch.multiprocessing as mp
+    from oracle import vmat_oracle as O
+    from vmatwpencode_b200.synth import make_case
+    out = str(tmp_path / "same.npy")
+    mp.spawn(_greedy_worker, args=(2, 29900 + os.getpid() % 90, out), nprocs=2, join=True)
+    assert np.load(out).all()
+    hist = pickle.load(open(out + ".pkl", "rb"))
+    case = make_case(V=20_000, nb=16, M=5, N=8, density=0.01, seed=94, gastep=10)
+    want = O.col_gen(O.OracleState(case), C=0.01, kappasize=6, max_iter=8, clean=True)
+    assert [h[0] for h in hist] == [w["idx"] for w in want] and len(want) > 0
+    for h, w in zip(hist, want):
+        assert h[1] == w["l"] and h[2] == w["r"]

@@ -240,12 +240,19 @@ class vmat_class:
         self.aperturegradient = np.asmatrix(g).transpose()
 
 
-def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool = True, **plan_opts):
+def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool = True, group=None,
+         shard: bool = False, **plan_opts):
     """Create the module-level ``data`` for a case (anything with the attributes of
     vmatwpencode_b200.synth.Case) and upload its D to GPU `device`.
 
     `acc="f64"` (default here) accumulates in double so that the greedy loop reproduces the
-    reference's aperture sequence; `acc="f32"` is the throughput mode."""
+    reference's aperture sequence; `acc="f32"` is the throughput mode.
+
+    `shard=True` (under torchrun, one process per GPU, torch.distributed initialised): this rank
+    keeps only its voxel slab of D; every evaluation all-reduces the beamlet gradient and the
+    objective inside the reduction kernel over peer memory, summing the ranks in rank order, so
+    all ranks see bit-identical (f, g, beamlet gradient) and run the same greedy loop in lock
+    step.  ``data.currentDose`` / ``voxelgradient`` are then the slab's."""
     global data, N, M
     d = vmat_class()
     d.numvoxels = case.V
@@ -270,7 +277,21 @@ def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool 
                  "targets", "oars", "functionData", "voxelAssignment"):       # present on ingested cases
         if hasattr(case, name):
             setattr(d, name, getattr(case, name))
-    if gpu:     # gpu=False: host-side bookkeeping only (geometry, updateOpenAperture); no evaluation
+    if gpu and shard:
+        import torch
+        import torch.distributed as dist
+        from .dist import slab_of
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        rows, Dslab, thr, over, under = slab_of(case, rank, world)
+        d.plan = DosePlan(Dslab, case.beam_ptr, thr, over, under, device=device, store=store, acc=acc, **plan_opts)
+        d.slab = rows
+        if world > 1:
+            mine = torch.tensor(list(d.plan.comm_handle()), dtype=torch.uint8, device=f"cuda:{device}")
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine, group=group)
+            d.plan.comm_attach(rank, world, b"".join(bytes(h.cpu().tolist()) for h in allh))
+            dist.barrier(group)
+    elif gpu:     # gpu=False: host-side bookkeeping only (geometry, updateOpenAperture); no evaluation
         d.plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, device=device,
                           store=store, acc=acc, **plan_opts)
     data = d
