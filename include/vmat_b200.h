@@ -169,6 +169,10 @@ int vmat_price(vmat_plan_t* plan, int32_t ncand, const int32_t* cand_beam,
  */
 int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
                        const double* curmin, double* cost /* n */);
+/* Same with the candidates given separately (n_cand x dim) from the points summed over (n x dim):
+ * a rank's shard of the point set in the multi-GPU use; the caller adds the per-rank costs. */
+int vmat_kmedoid_costs_shard(int device, int64_t n_cand, const double* cand, int64_t n, int32_t dim,
+                             const double* points, const double* curmin, double* cost /* n_cand */);
 
 /*
  * Restricted-master-problem fast path (solveRMC, greedyVMATsampling.py:858-885): while the

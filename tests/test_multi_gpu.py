@@ -115,3 +115,32 @@ def test_two_gpu_greedy_loop_matches_oracle(tmp_path):
     assert [h[0] for h in hist] == [w["idx"] for w in want] and len(want) > 0
     for h, w in zip(hist, want):
         assert h[1] == w["l"] and h[2] == w["r"]
+
+
+def _km_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from vmatwpencode_b200 import kmedoids as km
+    rng = np.random.default_rng(11)
+    P = np.round(rng.random((3000, 3)) * 64)            # voxel-like integer coordinates
+    got = km.givemewholelist([0, 7], P, device=rank, group=dist.group.WORLD, limit=12)
+    if rank == 0:
+        np.save(out, np.array(got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_kmedoid_voxel_sampling(tmp_path):
+    import torch.multiprocessing as mp
+    from vmatwpencode_b200 import kmedoids as km
+    out = str(tmp_path / "km.npy")
+    mp.spawn(_km_worker, args=(2, 29990 + os.getpid() % 9, out), nprocs=2, join=True)
+    rng = np.random.default_rng(11)
+    P = np.round(rng.random((3000, 3)) * 64)
+    single = km.givemewholelist([0, 7], P, limit=12)
+    assert list(np.load(out)) == single

@@ -73,6 +73,7 @@ SIGNATURES = {
     "vmat_dvh_histogram": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P]),
     "vmat_price": (C.c_int, [_P, C.c_int32, _P, C.POINTER(PriceParams), C.POINTER(PriceRow), _P, _P, _P]),
     "vmat_kmedoid_costs": (C.c_int, [C.c_int, C.c_int64, C.c_int32, _P, _P, _P]),
+    "vmat_kmedoid_costs_shard": (C.c_int, [C.c_int, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
 }
 
 _lib = None

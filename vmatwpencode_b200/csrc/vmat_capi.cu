@@ -1147,16 +1147,25 @@ extern "C" int vmat_dvh_histogram(vmat_plan_t* P, const uint64_t* full_mask, int
 // ---------------------------------------------------------------------------------
 // k-medoid insertion costs
 // ---------------------------------------------------------------------------------
+extern "C" int vmat_kmedoid_costs_shard(int device, int64_t nc, const double* cand, int64_t n, int32_t dim,
+                                        const double* points, const double* curmin, double* cost) {
+    if (nc <= 0 || n < 0 || dim <= 0 || dim > 8 || !cand || !cost || (n > 0 && (!points || !curmin)))
+        return fail(VMAT_E_ARG, "vmat_kmedoid_costs: bad argument");
+    CU(cudaSetDevice(device));
+    DevBuf dc, dp, dm, dout;
+    CU(dc.alloc(nc * dim * 8)); CU(dp.alloc(n * dim * 8)); CU(dm.alloc(n * 8)); CU(dout.alloc(nc * 8));
+    CU(cudaMemcpy(dc.p, cand, nc * dim * 8, cudaMemcpyHostToDevice));
+    if (n > 0) {
+        CU(cudaMemcpy(dp.p, points, n * dim * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dm.p, curmin, n * 8, cudaMemcpyHostToDevice));
+    }
+    k6_kmedoid_cost<<<(unsigned)nc, kKmThreads>>>(n, dim, dc.as<double>(), dp.as<double>(), dm.as<double>(), dout.as<double>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(cost, dout.p, nc * 8, cudaMemcpyDeviceToHost));
+    return VMAT_OK;
+}
+
 extern "C" int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
                                   const double* curmin, double* cost) {
-    if (n <= 0 || dim <= 0 || dim > 8 || !points || !curmin || !cost) return fail(VMAT_E_ARG, "vmat_kmedoid_costs: bad argument");
-    CU(cudaSetDevice(device));
-    DevBuf dp, dm, dc;
-    CU(dp.alloc(n * dim * 8)); CU(dm.alloc(n * 8)); CU(dc.alloc(n * 8));
-    CU(cudaMemcpy(dp.p, points, n * dim * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dm.p, curmin, n * 8, cudaMemcpyHostToDevice));
-    k6_kmedoid_cost<<<(unsigned)n, kKmThreads>>>(n, dim, dp.as<double>(), dm.as<double>(), dc.as<double>());
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(cost, dc.p, n * 8, cudaMemcpyDeviceToHost));
-    return VMAT_OK;
+    return vmat_kmedoid_costs_shard(device, n, points, n, dim, points, curmin, cost);
 }

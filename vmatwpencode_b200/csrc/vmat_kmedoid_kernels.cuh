@@ -15,16 +15,20 @@ namespace vmat {
 constexpr int kKmThreads = 256;
 constexpr int64_t kKmSequentialMax = 4096;
 
-__device__ __forceinline__ double km_dist(const double* __restrict__ P, int dim, int64_t c, int64_t j) {
+__device__ __forceinline__ double km_dist(const double* __restrict__ Pc, const double* __restrict__ P, int dim,
+                                          int64_t c, int64_t j) {
     double s = 0.0;
     for (int d = 0; d < dim; ++d) {
-        const double df = __dsub_rn(P[c * dim + d], P[j * dim + d]);
+        const double df = __dsub_rn(Pc[c * dim + d], P[j * dim + d]);
         s = __dadd_rn(s, __dmul_rn(df, df));
     }
     return __dsqrt_rn(s);
 }
 
-__global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost(int64_t n, int dim, const double* __restrict__ P,
+// candidates Pc[gridDim.x] against the points P[n] (a rank's shard of the point set in the
+// multi-GPU use; the caller adds the per-rank costs)
+__global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost(int64_t n, int dim, const double* __restrict__ Pc,
+                                                             const double* __restrict__ P,
                                                              const double* __restrict__ curmin,
                                                              double* __restrict__ cost) {
     __shared__ double sh[kKmThreads];
@@ -35,7 +39,7 @@ __global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost(int64_t n, int dim
         double total = 0.0;
         for (int64_t j0 = 0; j0 < n; j0 += kKmThreads) {
             const int64_t j = j0 + tid;
-            sh[tid] = (j < n) ? fmin(curmin[j], km_dist(P, dim, c, j)) : 0.0;
+            sh[tid] = (j < n) ? fmin(curmin[j], km_dist(Pc, P, dim, c, j)) : 0.0;
             __syncthreads();
             if (tid == 0) {
                 const int lim = (int)min((int64_t)kKmThreads, n - j0);
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost(int64_t n, int dim
         return;
     }
     double v = 0.0;
-    for (int64_t j = tid; j < n; j += kKmThreads) v += fmin(curmin[j], km_dist(P, dim, c, j));
+    for (int64_t j = tid; j < n; j += kKmThreads) v += fmin(curmin[j], km_dist(Pc, P, dim, c, j));
     sh[tid] = v;
     __syncthreads();
     for (int o = kKmThreads / 2; o > 0; o >>= 1) {

@@ -43,11 +43,28 @@ def listdiff(a, b):
     return [aa for aa in a if aa not in b]
 
 
-def insertnewelement(kappa, ba, device: int = 0, _state=None):
-    """Append the candidate that minimises distancemin; the first best wins (kmedoids.py:48-60)."""
+def _sharded_costs(P, cur, device, group):
+    """Every rank sums over its shard of the points j; the per-rank costs are all-reduced (the voxel
+    use of BASELINE.json's north star: the point set is too large for one distance pass)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = P.shape[0]
+    j0, j1 = n * rank // world, n * (rank + 1) // world
+    part = kmedoid_costs(P[j0:j1], cur[j0:j1], device, candidates=P)
+    t = torch.from_numpy(part)
+    if dist.get_backend(group) == "nccl":
+        t = t.to(f"cuda:{device}")
+    dist.all_reduce(t, group=group)
+    return t.cpu().numpy()
+
+
+def insertnewelement(kappa, ba, device: int = 0, _state=None, group=None):
+    """Append the candidate that minimises distancemin; the first best wins (kmedoids.py:48-60).
+    With a torch.distributed `group` the distance pass is sharded over the points."""
     P = _points(ba) if _state is None else _state["P"]
     cur = _nearest(P, kappa) if _state is None else _state["cur"]
-    cost = kmedoid_costs(P, cur, device)
+    cost = kmedoid_costs(P, cur, device) if group is None else _sharded_costs(P, cur, device, group)
     taken = np.zeros(P.shape[0], dtype=bool)
     taken[list(kappa)] = True
     cost = np.where(taken, np.inf, cost)
@@ -59,11 +76,13 @@ def insertnewelement(kappa, ba, device: int = 0, _state=None):
     return kappa
 
 
-def givemewholelist(kappa, ba, device: int = 0):
-    """Order all points by greedy k-medoid insertion (kmedoids.py:62-68)."""
+def givemewholelist(kappa, ba, device: int = 0, group=None, limit=None):
+    """Order all points by greedy k-medoid insertion (kmedoids.py:62-68); `limit` stops after that
+    many medoids (voxel subsampling wants the first k, not the whole ordering)."""
     kappa = list(kappa)
     P = _points(ba)
     state = {"P": P, "cur": _nearest(P, kappa)}
-    while len(kappa) < P.shape[0]:
-        kappa = insertnewelement(kappa, ba, device, state)
+    stop = P.shape[0] if limit is None else min(limit, P.shape[0])
+    while len(kappa) < stop:
+        kappa = insertnewelement(kappa, ba, device, state, group)
     return kappa

@@ -260,13 +260,20 @@ class DosePlan:
         return p, l, r
 
 
-def kmedoid_costs(points, curmin, device: int = 0) -> np.ndarray:
-    """cost[c] = sum_j min(curmin[j], dist(c, j))  (kmedoids.py:32-60) on the GPU."""
+def kmedoid_costs(points, curmin, device: int = 0, candidates=None) -> np.ndarray:
+    """cost[c] = sum_j min(curmin[j], dist(c, j))  (kmedoids.py:32-60) on the GPU.  With
+    `candidates` (n_cand x dim) the sum runs over `points` (e.g. one rank's shard) only."""
     P = np.ascontiguousarray(points, dtype=np.float64)
     if P.ndim == 1:
         P = P.reshape(-1, 1)
     cm = np.ascontiguousarray(curmin, dtype=np.float64)
-    out = np.empty(P.shape[0])
     lib = _lib.load()
-    check(lib.vmat_kmedoid_costs(device, P.shape[0], P.shape[1], _ptr(P), _ptr(cm), _ptr(out)), "vmat_kmedoid_costs")
+    if candidates is None:
+        out = np.empty(P.shape[0])
+        check(lib.vmat_kmedoid_costs(device, P.shape[0], P.shape[1], _ptr(P), _ptr(cm), _ptr(out)), "vmat_kmedoid_costs")
+        return out
+    Cc = np.ascontiguousarray(candidates, dtype=np.float64).reshape(-1, P.shape[1])
+    out = np.empty(Cc.shape[0])
+    check(lib.vmat_kmedoid_costs_shard(device, Cc.shape[0], _ptr(Cc), P.shape[0], P.shape[1], _ptr(P), _ptr(cm),
+                                       _ptr(out)), "vmat_kmedoid_costs_shard")
     return out
