@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--C", type=float, default=0.01)
     ap.add_argument("--kappa", type=int, default=16)
+    ap.add_argument("--profile", action="store_true", help="cProfile the GPU loop (sparse only) and print the top of it to stderr")
     ap.add_argument("--literal", action="store_true", help="also time the reference's literal operation order (slow)")
     args = ap.parse_args()
     case = make_config(args.workload)
@@ -40,6 +41,16 @@ def main():
         seqs[name] = [(h["idx"], tuple(h["l"]), tuple(h["r"])) for h in data.history]
         data.plan.close()
     vl.use_column_cache = False
+    if args.profile:
+        import cProfile
+        import pstats
+        data = vl.bind(case, store="f32", acc="f64")
+        pr = cProfile.Profile()
+        pr.enable()
+        vl.colGen(args.C, False, args.kappa, max_iter=args.iters)
+        pr.disable()
+        data.plan.close()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     t0 = time.perf_counter()
     hist = O.col_gen(O.OracleState(case), C=args.C, kappasize=args.kappa, max_iter=args.iters, clean=True)
     out["cpu_oracle_clean_s"] = round(time.perf_counter() - t0, 4)

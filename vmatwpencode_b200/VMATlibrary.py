@@ -160,6 +160,7 @@ class vmat_class:
         self._gb = None
         self._fg = None
         self._vb_cache = {}
+        self._price_static = {}
         self._rmp_active = False     # solveRMC is running on the dense column cache
         self._gb_valid = False       # the plan's beamlet gradient belongs to the current dose
 
@@ -329,19 +330,24 @@ def calcObjGrad(x, user_data=None):
     return data.objectiveValue, data.aperturegradient
 
 
+def _beamlet_grid(index):
+    """M x N occupancy of control point `index`: entry (i, y) says a beamlet sits at
+    (xinter[i], yinter[y]) - the membership tests of :589-596 for all leaf rows at once."""
+    hit = data._vb_cache.get(index)
+    if hit is None:
+        inrow = np.asarray(data.xdirection[index])[:, None] == np.asarray(data.xinter)[None, :]
+        incol = np.asarray(data.ydirection[index])[:, None] == np.asarray(data.yinter)[None, :]
+        hit = data._vb_cache[index] = (inrow.T.astype(np.int32) @ incol.astype(np.int32)) > 0
+    return hit
+
+
 def fvalidbeamlets(i, index):
     """Beamlet y-indices that exist in leaf row i of control point `index`, and the same
     range with both neighbours appended (greedyVMATsampling.py:589-602)."""
-    key = (i, index)
-    hit = data._vb_cache.get(key)
-    if hit is None:
-        inrow = data.xdirection[index] == data.xinter[i]
-        vb = np.flatnonzero(np.isin(data.yinter, data.ydirection[index][inrow]))
-        if vb.size == 0:
-            raise ValueError("min() arg is an empty sequence")       # what the reference raises
-        hit = (vb, np.concatenate(([vb.min() - 1], vb, [vb.max() + 1])))
-        data._vb_cache[key] = hit
-    return hit
+    vb = np.flatnonzero(_beamlet_grid(index)[i])
+    if vb.size == 0:
+        raise ValueError("min() arg is an empty sequence")       # what the reference raises
+    return vb, np.concatenate(([vb[0] - 1], vb, [vb[-1] + 1]))
 
 
 def _neighbour_leaves(predec, succ, Nn, Mm, vmax):
@@ -358,48 +364,61 @@ def _neighbour_leaves(predec, succ, Nn, Mm, vmax):
     return lcm, rcm, lcp, rcp, vmaxm, vmaxp
 
 
+_PRICE_ROW_DTYPE = np.dtype([("l_first", "<f8"), ("n_l", "<i4"), ("vb_min", "<i4"), ("r_lo", "<f8"), ("r_hi", "<f8"),
+                             ("r_mid", "<f8"), ("vb_mask", "<u8"), ("grad_offset", "<i4"), ("n_r_mid", "<i4")])
+
+
+def _price_static(index, Mm):
+    """Per control point, fixed by the beamlet grid: fvalidbeamlets of every leaf row as a bit mask,
+    its minimum, and the running ``leftmostleaf`` offsets of :705,756 (quirk Q1: the first row
+    counts one beamlet less)."""
+    hit = data._price_static.get(index)
+    if hit is None:
+        grid = _beamlet_grid(index)[:Mm]
+        count = grid.sum(axis=1)
+        if (count == 0).any():
+            raise ValueError("min() arg is an empty sequence")   # what the reference's fvalidbeamlets raises
+        bits = np.uint64(1) << np.arange(grid.shape[1], dtype=np.uint64)
+        mask = (grid * bits[None, :]).sum(axis=1, dtype=np.uint64)
+        offs = np.zeros(Mm, dtype=np.int32)
+        offs[1:] = np.cumsum(count)[:-1] - 1
+        hit = data._price_static[index] = (mask, grid.argmax(axis=1).astype(np.int32), offs)
+    return hit
+
+
 def _fill_price_rows(rows, base, angdistancem, angdistancep, vmax, speedlim, predec, succ, Nn, Mm,
                      thisApertureIndex, bw):
     """Host part of PPsubroutine: the leaf windows of every row (:664,672-680,713-724) and the
-    beamlet bookkeeping (fvalidbeamlets, the running ``leftmostleaf`` of :705,756)."""
+    beamlet bookkeeping (fvalidbeamlets, the running ``leftmostleaf`` of :705,756).  Same float64
+    expressions as the reference, evaluated for all M rows at once."""
     if Nn > 62:
         raise VmatError("pricing kernel supports at most 62 beamlets per leaf row")
     lcm, rcm, lcp, rcp, vmaxm, vmaxp = _neighbour_leaves(predec, succ, Nn, Mm, vmax)
+    lcm, rcm, lcp, rcp = (np.asarray(v, dtype=np.float64) for v in (lcm, rcm, lcp, rcp))
     travelm = vmaxm * (angdistancem / speedlim) / bw
     travelp = vmaxp * (angdistancep / speedlim) / bw
-    leftmost = 0
-    for m in range(Mm):
-        vb, _ = fvalidbeamlets(m, thisApertureIndex)
-        row = rows[base + m]
-        lo = math.ceil(max(-1, lcm[m] - travelm, lcp[m] - travelp))
-        hi = 1 + math.floor(min(Nn - 1, lcm[m] + travelm, lcp[m] + travelp))
-        if hi - lo <= 0:
-            # np.arange(mid, mid + 1) of the reference: one value, or two when mid + 1 rounds up
-            mid = (angdistancep * lcm[m] + angdistancem * lcp[m]) / (angdistancep + angdistancem)
-            row.l_first = mid
-            row.n_l = len(np.arange(mid, mid + 1))
-        else:
-            row.l_first = float(lo)
-            row.n_l = hi - lo
-        row.r_lo = max(rcm[m] - travelm, rcp[m] - travelp)
-        row.r_hi = min(Nn, rcm[m] + travelm, rcp[m] + travelp)
-        if math.isinf(angdistancem) or math.isinf(angdistancep):
-            row.r_mid = float("nan")          # unreachable: an infinite travel never empties a range
-            row.n_r_mid = 1
-        else:
-            row.r_mid = (angdistancep * rcm[m] + angdistancem * rcp[m]) / (angdistancep + angdistancem)
-            row.n_r_mid = len(np.arange(row.r_mid, row.r_mid + 1))
-        mask = 0
-        for yv in vb:
-            mask |= 1 << int(yv)
-        row.vb_mask = mask
-        row.vb_min = int(vb.min())
-        if m == 0:
-            row.grad_offset = 0
-            leftmost = len(vb) - 1                     # quirk Q1
-        else:
-            row.grad_offset = leftmost
-            leftmost = len(vb) + leftmost
+    out = np.frombuffer(rows, dtype=_PRICE_ROW_DTYPE)[base:base + Mm]
+    lo = np.ceil(np.maximum(-1.0, np.maximum(lcm - travelm, lcp - travelp)))
+    hi = 1.0 + np.floor(np.minimum(Nn - 1.0, np.minimum(lcm + travelm, lcp + travelp)))
+    empty = hi - lo <= 0
+    out["l_first"] = lo
+    out["n_l"] = (hi - lo).astype(np.int32)
+    finite = not (math.isinf(angdistancem) or math.isinf(angdistancep))
+    if finite and empty.any():
+        # np.arange(mid, mid + 1) of the reference: one value, or two when mid + 1 rounds up
+        mid = (angdistancep * lcm + angdistancem * lcp) / (angdistancep + angdistancem)
+        out["l_first"][empty] = mid[empty]
+        out["n_l"][empty] = np.ceil((mid[empty] + 1) - mid[empty]).astype(np.int32)
+    out["r_lo"] = np.maximum(rcm - travelm, rcp - travelp)
+    out["r_hi"] = np.minimum(float(Nn), np.minimum(rcm + travelm, rcp + travelp))
+    if finite:
+        rmid = (angdistancep * rcm + angdistancem * rcp) / (angdistancep + angdistancem)
+        out["r_mid"] = rmid
+        out["n_r_mid"] = np.ceil((rmid + 1) - rmid).astype(np.int32)
+    else:
+        out["r_mid"] = np.nan                 # unreachable: an infinite travel never empties a range
+        out["n_r_mid"] = 1
+    out["vb_mask"], out["vb_min"], out["grad_offset"] = _price_static(thisApertureIndex, Mm)
 
 
 def _price(cands, C_, C2, C3, b, vmax, speedlim, Nn, Mm, bw):
