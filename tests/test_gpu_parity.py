@@ -191,6 +191,34 @@ def test_argument_errors_are_reported_not_ignored():
     plan.close()
 
 
+def test_malformed_csr_is_rejected_at_plan_build():
+    """Out-of-range or unsorted indices would become wild shared-memory reads; the plan refuses them."""
+    import torch
+    case = make_case(V=600, nb=3, M=2, N=4, density=0.1, seed=74)
+    Dr = case.D.tocsr(); Dr.sort_indices()
+    Dc = Dr.tocsc(); Dc.sort_indices()
+    dev = lambda a, t: torch.as_tensor(np.ascontiguousarray(a), dtype=t, device="cuda")
+    def parts():
+        return dict(vrowptr=dev(Dr.indptr, torch.int64), vcol=dev(Dr.indices, torch.int32), vval=dev(Dr.data, torch.float32),
+                    browptr=dev(Dc.indptr, torch.int64), bcol=dev(Dc.indices, torch.int32), bval=dev(Dc.data, torch.float32))
+    args = (case.beam_ptr, case.thr, case.over, case.under)
+    DosePlan(parts(), *args).close()                       # the untouched payload is fine
+    bad = parts(); bad["vcol"][5] = case.B                 # beamlet index out of range
+    with pytest.raises(_lib.VmatError, match="out of range"):
+        DosePlan(bad, *args)
+    bad = parts(); bad["bcol"][3] = -1
+    with pytest.raises(_lib.VmatError, match="out of range"):
+        DosePlan(bad, *args)
+    bad = parts()
+    row = int(np.argmax(np.diff(Dc.indptr) >= 2)); k = int(Dc.indptr[row])
+    bad["bcol"][k], bad["bcol"][k + 1] = bad["bcol"][k + 1].clone(), bad["bcol"][k].clone()
+    with pytest.raises(_lib.VmatError, match="sorted"):
+        DosePlan(bad, *args)
+    bad = parts(); bad["vrowptr"][4] = bad["vrowptr"][5] + 1
+    with pytest.raises(_lib.VmatError, match="decrease"):
+        DosePlan(bad, *args)
+
+
 def test_pricing_random_states_vs_oracle():
     """Bigger leaf grids, ragged rows, tight leaf speeds (fractional fallbacks), C in {0, >0}."""
     for seed, (nb, M, N, ragged, gastep) in enumerate([(10, 6, 12, True, 2), (8, 9, 9, False, 10), (14, 4, 20, True, 1)]):
@@ -442,6 +470,27 @@ def test_kmedoid_costs_tree_path_and_voxel_points():
     for c in (1, 3000):
         want = np.minimum(cur, np.sqrt(((P - P[c]) ** 2).sum(axis=1))).sum()
         assert abs(cost[c] - want) <= 1e-12 * want
+    # the tiled kernel's order of additions, restated: thread t adds points t, t+256, ... left to
+    # right, then a binary tree over the 256 threads; candidate count not a multiple of the tile
+    n = 6003
+    P = np.round(rng.random((n, 3)) * 200) / 4
+    cur = np.sqrt(((P - P[11]) ** 2).sum(axis=1))
+    cost = kmedoid_costs(P, cur)
+    for c in (0, 7, 8, 4097, n - 1):
+        s = np.zeros(n)
+        for d in range(3):
+            df = P[c, d] - P[:, d]
+            s = s + df * df
+        term = np.minimum(cur, np.sqrt(s))
+        part = np.zeros(256)
+        for j0 in range(0, n, 256):
+            blk = term[j0:j0 + 256]
+            part[:len(blk)] += blk
+        o = 128
+        while o:
+            part[:o] += part[o:2 * o]
+            o //= 2
+        assert cost[c] == part[0]
 
 
 @pytest.mark.parametrize("acc", ["f64", "f32"])

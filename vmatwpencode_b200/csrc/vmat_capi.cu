@@ -83,7 +83,7 @@ struct vmat_plan {
     cudaGraphExec_t graph_exec = nullptr;
     // pricing scratch
     DevBuf price_rows, price_cand, price_p, price_l, price_r, price_dad;
-    size_t price_cap_cand = 0, price_cap_dad = 0;
+    size_t price_cap_cand = 0, price_cap_rows = 0, price_cap_dad = 0;
     // natural-order penalty tables and the RMP column cache (vmat_rmp_begin)
     DevBuf thr_n, over_n, under_n, colA, colG, col_y, col_w, rmp_yk, rmp_beams, rmp_fpart, rmp_gpart;
     std::vector<int32_t> rmp_cols;                 // control points of the active RMP
@@ -339,8 +339,10 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     if (P->opt.acc_dtype != VMAT_F32 && P->opt.acc_dtype != VMAT_F64) return fail(VMAT_E_ARG, "bad acc_dtype");
     if (P->opt.store_dtype < 0 || P->opt.store_dtype > 2) return fail(VMAT_E_ARG, "bad store_dtype");
     P->acc_size = P->opt.acc_dtype == VMAT_F64 ? 8 : 4;
-    P->pdl = P->opt.reserved[3] == 0;
-    P->host_path = P->opt.reserved[4] > 0 ? (P->opt.reserved[4] & 7) : 2;     // bit 2 (4): y inside the launch parameters (no graph)   // reserved[4]: 4 = memcpy nodes both ways, 1/2/3 = zero-copy bits      // reserved[3] = 1 disables programmatic dependent launch
+    P->pdl = P->opt.reserved[3] == 0;     // reserved[3] = 1 disables programmatic dependent launch
+    // reserved[4]: host-buffer path bits - 1 = K1 reads y from mapped host memory, 2 = K3 publishes
+    // results + completion tags to mapped host memory (default), 4 = y travels in the launch parameters
+    P->host_path = P->opt.reserved[4] > 0 ? (P->opt.reserved[4] & 7) : 2;
     P->beam_ptr.assign(beam_ptr, beam_ptr + nb + 1);
     CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -367,6 +369,11 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaMemcpy(h_vrow.data(), vrowptr, (V + 1) * sizeof(int64_t), to_host));
     CU(cudaMemcpy(h_brow.data(), browptr, (B + 1) * sizeof(int64_t), to_host));
     const int64_t nnz = h_vrow[V];
+    if (h_vrow[0] != 0 || h_brow[0] != 0) return fail(VMAT_E_ARG, "CSR row pointers must start at 0");
+    for (int64_t v = 0; v < V; ++v)
+        if (h_vrow[v + 1] < h_vrow[v]) return fail(VMAT_E_ARG, "voxel-major row pointers must not decrease");
+    for (int64_t j = 0; j < B; ++j)
+        if (h_brow[j + 1] < h_brow[j]) return fail(VMAT_E_ARG, "beamlet-major row pointers must not decrease");
     if (nnz != h_brow[B]) return fail(VMAT_E_ARG, "voxel-major and beamlet-major CSR disagree on nnz");
     if (nnz > 0 && (!vcol || !vval || !bcol || !bval)) return fail(VMAT_E_ARG, "null CSR payload");
     P->nnz = nnz;
@@ -380,6 +387,31 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         CU(cudaMemcpy(up_vcol.p, vcol, nnz * 4, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(up_vval.p, vval, nnz * sv, cudaMemcpyHostToDevice));
         d_vcol = up_vcol.as<int32_t>(); d_vval = up_vval.p;
+    }
+
+    DevBuf csr_flag, up_vrow;
+    CU(csr_flag.alloc(4)); CU(cudaMemsetAsync(csr_flag.p, 0, 4, st));
+    auto check_csr = [&](int64_t nrows, int64_t ncols, int sorted, const int64_t* d_rowptr, const int32_t* d_col,
+                         const char* what) -> int {
+        if (nnz == 0) return 0;
+        k_check_csr<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, ncols, sorted, d_rowptr, d_col, csr_flag.as<int>());
+        CU(cudaGetLastError());
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, csr_flag.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (bad & 1) return fail(VMAT_E_ARG, std::string(what) + " CSR: index out of range");
+        if (bad & 2) return fail(VMAT_E_ARG, std::string(what) + " CSR: indices must be sorted within a row");
+        return 0;
+    };
+    {
+        const int64_t* d_vrow = vrowptr;
+        if (location == VMAT_HOST) {
+            CU(up_vrow.alloc((V + 1) * 8));
+            CU(cudaMemcpy(up_vrow.p, vrowptr, (V + 1) * 8, cudaMemcpyHostToDevice));
+            d_vrow = up_vrow.as<int64_t>();
+        }
+        if (int rc = check_csr(V, B, 0, d_vrow, d_vcol, "voxel-major")) return rc;
+        up_vrow.alloc(0);
     }
 
     // ---- K1 layout: voxels sorted by row length (descending, stable) ----------------
@@ -428,6 +460,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         CU(cudaMemcpy(up_brow.p, browptr, (B + 1) * 8, cudaMemcpyHostToDevice));
         d_bcol = up_bcol.as<int32_t>(); d_bval = up_bval.p; d_brow = up_brow.as<int64_t>();
     }
+    if (int rc = check_csr(B, V, 1, d_brow, d_bcol, "beamlet-major")) return rc;
 
     // ---- K2 layout: column tiles of T voxels; per tile, beamlet segments sorted by length
     {
@@ -950,12 +983,12 @@ extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_bea
     CU(cudaSetDevice(P->device));
     const int32_t kmax = price_max_nodes(N);
     const size_t nrow = (size_t)ncand * M;
-    if ((size_t)ncand > P->price_cap_cand || nrow * kmax > P->price_cap_dad) {
+    if ((size_t)ncand > P->price_cap_cand || nrow > P->price_cap_rows || nrow * kmax > P->price_cap_dad) {
         CU(P->price_cand.alloc(ncand * 4)); CU(P->price_p.alloc(ncand * 8));
         CU(P->price_rows.alloc(nrow * sizeof(vmat_price_row_t)));
         CU(P->price_l.alloc(nrow * 4)); CU(P->price_r.alloc(nrow * 4));
         CU(P->price_dad.alloc(nrow * kmax * sizeof(int32_t) * 3));
-        P->price_cap_cand = ncand; P->price_cap_dad = nrow * kmax;
+        P->price_cap_cand = ncand; P->price_cap_rows = nrow; P->price_cap_dad = nrow * kmax;
     }
     cudaStream_t st = P->stream;
     CU(cudaMemcpyAsync(P->price_cand.p, cand_beam, ncand * 4, cudaMemcpyHostToDevice, st));
@@ -1159,7 +1192,14 @@ extern "C" int vmat_kmedoid_costs_shard(int device, int64_t nc, const double* ca
         CU(cudaMemcpy(dp.p, points, n * dim * 8, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(dm.p, curmin, n * 8, cudaMemcpyHostToDevice));
     }
-    k6_kmedoid_cost<<<(unsigned)nc, kKmThreads>>>(n, dim, dc.as<double>(), dp.as<double>(), dm.as<double>(), dout.as<double>());
+    if (n <= kKmSequentialMax) {
+        k6_kmedoid_cost<<<(unsigned)nc, kKmThreads>>>(n, dim, dc.as<double>(), dp.as<double>(), dm.as<double>(), dout.as<double>());
+    } else {
+        const unsigned grid = (unsigned)((nc + kKmTile - 1) / kKmTile);
+#define VMAT_KM_CASE(D) case D: k6_kmedoid_cost_tiled<D><<<grid, kKmThreads>>>(n, nc, dc.as<double>(), dp.as<double>(), dm.as<double>(), dout.as<double>()); break;
+        switch (dim) { VMAT_KM_CASE(1) VMAT_KM_CASE(2) VMAT_KM_CASE(3) VMAT_KM_CASE(4) VMAT_KM_CASE(5) VMAT_KM_CASE(6) VMAT_KM_CASE(7) VMAT_KM_CASE(8) }
+#undef VMAT_KM_CASE
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpy(cost, dout.p, nc * 8, cudaMemcpyDeviceToHost));
     return VMAT_OK;

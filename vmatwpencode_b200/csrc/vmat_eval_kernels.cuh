@@ -661,6 +661,23 @@ __global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, co
 // ---------------------------------------------------------------------------------
 // layout construction (plan build time)
 // ---------------------------------------------------------------------------------
+// CSR payload check: every index in [0, ncols); with `sorted`, non-decreasing inside a row (the
+// tile segmentation below bisects beamlet rows).  One thread per row; flag bit 0 = range, bit 1 = order.
+__global__ void k_check_csr(int64_t nrows, int64_t ncols, int sorted, const int64_t* __restrict__ rowptr,
+                            const int32_t* __restrict__ col, int* __restrict__ flag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    int bad = 0;
+    int32_t prev = 0;
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        const int32_t c = col[k];
+        if (c < 0 || c >= ncols) bad |= 1;
+        if (sorted && c < prev) bad |= 2;
+        prev = c;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
 // first position in each beamlet row whose voxel id is >= t*T, for t = 0..ntiles
 __global__ void k_segment_bounds(int32_t B, int32_t ntiles, int32_t T, const int64_t* __restrict__ browptr,
                                  const int32_t* __restrict__ bcol, int64_t* __restrict__ segstart) {

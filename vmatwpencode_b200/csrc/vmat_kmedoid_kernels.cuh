@@ -61,6 +61,60 @@ __global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost(int64_t n, int dim
     if (tid == 0) cost[c] = sh[0];
 }
 
+// Large point sets (n > kKmSequentialMax): kKmTile candidates per CTA, so a point and its curmin
+// are fetched once for kKmTile distances (the one-candidate form is bound by L2 traffic, n^2 x 32 B),
+// and the square root is skipped wherever the squared distance already reaches curmin^2 (rounded
+// up, so the test can only err towards taking the root): min(curmin, sqrt(s)) is curmin there,
+// bit for bit.  Same thread <-> point mapping and tree as the one-candidate form: same sums.
+constexpr int kKmTile = 8;
+
+template <int DIM>
+__global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost_tiled(int64_t n, int64_t nc, const double* __restrict__ Pc,
+                                                                   const double* __restrict__ P,
+                                                                   const double* __restrict__ curmin,
+                                                                   double* __restrict__ cost) {
+    __shared__ double sc[kKmTile][DIM];
+    __shared__ double sh[kKmTile][kKmThreads];
+    const int64_t c0 = (int64_t)blockIdx.x * kKmTile;
+    const int tid = threadIdx.x;
+    if (tid < kKmTile * DIM) {
+        const int64_t c = min(c0 + tid / DIM, nc - 1);
+        sc[tid / DIM][tid % DIM] = Pc[c * DIM + tid % DIM];
+    }
+    __syncthreads();
+    double v[kKmTile];
+#pragma unroll
+    for (int t = 0; t < kKmTile; ++t) v[t] = 0.0;
+    for (int64_t j = tid; j < n; j += kKmThreads) {
+        double pj[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) pj[d] = P[j * DIM + d];
+        const double cm = curmin[j];
+        const double cm2 = __dmul_ru(cm, cm);
+#pragma unroll
+        for (int t = 0; t < kKmTile; ++t) {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const double df = __dsub_rn(sc[t][d], pj[d]);
+                s = __dadd_rn(s, __dmul_rn(df, df));
+            }
+            v[t] += (s >= cm2) ? cm : fmin(cm, __dsqrt_rn(s));
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kKmTile; ++t) sh[t][tid] = v[t];
+    __syncthreads();
+    for (int o = kKmThreads / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+#pragma unroll
+            for (int t = 0; t < kKmTile; ++t) sh[t][tid] += sh[t][tid + o];
+        }
+        __syncthreads();
+    }
+    if (tid < kKmTile && c0 + tid < nc) cost[c0 + tid] = sh[tid][0];
+}
+
 // ---------------------------------------------------------------------------------
 // K7: dose-volume histograms (printresults, greedyVMATsampling.py:888-912).  Integer counts with
 // integer atomics: exact whatever the order.  Bin k holds edges[k] <= d < edges[k+1]; the last bin
