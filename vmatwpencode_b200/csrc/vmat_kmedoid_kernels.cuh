@@ -82,9 +82,13 @@ __global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost_tiled(int64_t n, i
         sc[tid / DIM][tid % DIM] = Pc[c * DIM + tid % DIM];
     }
     __syncthreads();
-    double v[kKmTile];
+    double v[kKmTile], cc[kKmTile][DIM];       // the tile's candidates live in registers
 #pragma unroll
-    for (int t = 0; t < kKmTile; ++t) v[t] = 0.0;
+    for (int t = 0; t < kKmTile; ++t) {
+        v[t] = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) cc[t][d] = sc[t][d];
+    }
     for (int64_t j = tid; j < n; j += kKmThreads) {
         double pj[DIM];
 #pragma unroll
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost_tiled(int64_t n, i
             double s = 0.0;
 #pragma unroll
             for (int d = 0; d < DIM; ++d) {
-                const double df = __dsub_rn(sc[t][d], pj[d]);
+                const double df = __dsub_rn(cc[t][d], pj[d]);
                 s = __dadd_rn(s, __dmul_rn(df, df));
             }
             v[t] += (s >= cm2) ? cm : fmin(cm, __dsqrt_rn(s));
