@@ -271,6 +271,21 @@ def test_greedy_loop_vs_oracle_medium_case():
     data.plan.close()
 
 
+def test_greedy_sequence_config2_vs_oracle():
+    """BASELINE.json configs[1] at full size (300k voxels x 10 080 beamlets, 180 control points): the
+    first greedy iterations pick the same control points with the same leaves as the CPU oracle."""
+    case = make_config("cfg2")
+    data = vl.bind(case, store="f32", acc="f64")
+    vl.colGen(0.01, False, 16, max_iter=3)
+    got = [(h["idx"], tuple(h["l"]), tuple(h["r"])) for h in data.history]
+    hist = O.col_gen(O.OracleState(case), C=0.01, kappasize=16, max_iter=3, clean=True)
+    assert got == [(h["idx"], tuple(h["l"]), tuple(h["r"])) for h in hist]
+    f, _ = data.plan.eval(np.asarray(data.currentIntensities, dtype=float))
+    data.plan.close()
+    with pytest.raises(_lib.VmatError):
+        data.plan.eval(np.zeros(case.nb))            # a closed plan reports, it does not crash
+
+
 def test_kmedoids_known_answer():
     from vmatwpencode_b200 import kmedoids as km
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmedoids.npz"))

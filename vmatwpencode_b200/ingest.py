@@ -87,6 +87,13 @@ def read_ct_voxel_info(readfolder: str) -> dict:
     return dict(x=counts[0], y=counts[1], z=counts[2])
 
 
+def _loadmat_sparse(path: str) -> dict:
+    try:
+        return sio.loadmat(path, spmatrix=True)       # newer scipy: keep the sparse-matrix return type explicit
+    except TypeError:
+        return sio.loadmat(path)
+
+
 def _flat_tokens(path: str) -> List[str]:
     with open(path) as f:
         return [tok for line in f for tok in line.rstrip("\n").split("\t")]
@@ -157,7 +164,7 @@ def load_cort(readfolder: str, readfolderD: str, structurefile: str, objfile: st
     # dose matrices: big -> small voxel rows, beamlets outside the common grid cut (:487-527)
     blocks = []
     for i, g in enumerate(gantry):
-        Dbig = sp.csc_matrix(sio.loadmat(os.path.join(readfolderD, f"Gantry{g}_Couch0_D.mat"))["D"], dtype=np.float64)
+        Dbig = sp.csc_matrix(_loadmat_sparse(os.path.join(readfolderD, f"Gantry{g}_Couch0_D.mat"))["D"], dtype=np.float64)
         keep = np.flatnonzero(np.isin(xdir[i], xinter) & np.isin(ydir[i], yinter))
         blocks.append(Dbig[small_to_big, :][:, keep])
         xdir[i] = xdir[i][keep]

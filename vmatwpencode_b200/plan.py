@@ -94,12 +94,15 @@ class DosePlan:
         del keep
         self._y = np.zeros(self.nb)
         self._g = np.zeros(self.nb)
+        self._f = C.c_double()
+        # argument objects of the per-evaluation call, built once (vmat_eval is called ~10^4 times/s)
+        self._eval_args = (self._h, _ptr(self._y), C.byref(self._f), _ptr(self._g))
 
     # -- lifecycle ------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.vmat_plan_destroy(self._h)
-            self._h = C.c_void_p(0)
+            self._h.value = None            # in place: the prebuilt argument tuples see the null handle too
 
     def __del__(self):
         try:
@@ -137,9 +140,10 @@ class DosePlan:
     def eval(self, y):
         """(f, g[nb]) for intensities y[nb]: host buffers in, host buffers out."""
         self._y[:] = y
-        f = C.c_double()
-        check(self._lib.vmat_eval(self._h, _ptr(self._y), C.byref(f), _ptr(self._g)), "vmat_eval")
-        return f.value, self._g.copy()
+        rc = self._lib.vmat_eval(*self._eval_args)
+        if rc:
+            check(rc, "vmat_eval")
+        return self._f.value, self._g.copy()
 
     def set_intensities(self, y):
         self._y[:] = y
