@@ -112,6 +112,12 @@ int vmat_sync(vmat_plan_t* plan);
 int vmat_set_timing(vmat_plan_t* plan, int enable);
 int vmat_get_timing(vmat_plan_t* plan, double* ms /* 4 */, int32_t* n);
 
+/* Diagnostics: run one evaluation (current intensities) with per-CTA time stamps. out receives
+ * 8 uint64 per CTA, the dose kernel's CTAs first, then the transposed kernel's: globaltimer ns at
+ * [0] kernel entry, [1] inputs staged and predecessor finished, [2] first stage landed,
+ * [3] consumers done, [4] producer done. cap = capacity of out in elements. */
+int vmat_trace_eval(vmat_plan_t* plan, uint64_t* out, int64_t cap, int32_t* k1_ctas, int32_t* k2_ctas);
+
 /* Device pointer and element count (B+1 doubles: gb then f) of the buffer a multi-GPU
  * caller must sum across ranks between phase 1 and phase 2. */
 int vmat_reduce_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "vmat_sync": (C.c_int, [_P]),
     "vmat_set_timing": (C.c_int, [_P, C.c_int]),
     "vmat_get_timing": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
+    "vmat_trace_eval": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vmat_reduce_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "vmat_comm_handle": (C.c_int, [_P, _P]),
     "vmat_comm_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),

@@ -54,6 +54,11 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* sr
 }
 // programmatic dependent launch: the next kernel of the stream may start its prologue while this
 // one drains; it must wait here before touching anything the previous kernel wrote
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -137,6 +137,8 @@ __global__ void k4_expand_x(int32_t B, const double* __restrict__ y, const int32
 // ---------------------------------------------------------------------------------
 constexpr int kInlineY = 384;
 
+constexpr int kTraceSlots = 8;
+
 template <typename AT>
 struct K1Args {
     const uint4* sell;            // stream (voxel-major)
@@ -163,7 +165,29 @@ struct K1Args {
     // host-to-device copy sits in front of the kernel
     int32_t y_inline_n;
     double y_inline[kInlineY];
+    // diagnostics (vmat_trace_eval): per CTA, globaltimer at [entry, x staged + predecessor done,
+    // first stage landed, consumers done, producer done]; nullptr = off
+    unsigned long long* trace;
+    int32_t claim_ahead;          // 0, 1 or 2 super-slices claimed before they are needed
 };
+
+// four consecutive elements with one (float) or two (double) 16-byte loads
+__device__ __forceinline__ void load4(const float* p, float (&o)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void load4(const double* p, double (&o)[4]) {
+    const double2 v0 = reinterpret_cast<const double2*>(p)[0], v1 = reinterpret_cast<const double2*>(p)[1];
+    o[0] = v0.x; o[1] = v0.y; o[2] = v1.x; o[3] = v1.y;
+}
+
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(double* p, double a, double b, double c, double d) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+}
 
 template <typename VT, typename AT, bool XS, int W, int IW>
 __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_constant__ K1Args<AT> a) {
@@ -179,8 +203,10 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     unsigned char* ring = smem_raw + xbytes + ybytes;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nst = a.nstages, SB = a.stage_bytes;
+    unsigned long long* const trace = a.trace ? a.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
 
     if (tid == 0) {
+        if (trace) trace[0] = global_timer_ns();
         for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
         fence_barrier_init();
     }
@@ -189,11 +215,40 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     if (warp < W) {
         if (XS) {   // x_j = y[beam(j)] * w_dose[j]   (K4 folded into the prologue; consumers only -
                     // the producer is already streaming D meanwhile)
+            // The beamlet tables of this thread's first groups of four are requested before y is
+            // waited for, so the two round trips to L2 overlap.
+            constexpr int kPre = 4;
+            const int ngroups = a.B >> 2;                  // whole groups of four beamlets
+            int4 bo[kPre];
+            AT wd[kPre][4];
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int gidx = tid + k * W * 32;
+                if (gidx < ngroups) {
+                    bo[k] = reinterpret_cast<const int4*>(a.beam_of)[gidx];
+                    load4(a.w_dose + 4 * gidx, wd[k]);
+                }
+            }
             // y (possibly in mapped host memory) is read once per CTA into shared memory
             if (a.y_inline_n > 0) { for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y_inline[j]; }
             else { for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y[j]; }
             named_bar_sync(1, W * 32);
-            for (int j = tid; j < a.B; j += W * 32) xs[j] = mul_rn((AT)ys[a.beam_of[j]], a.w_dose[j]);
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int gidx = tid + k * W * 32;
+                if (gidx < ngroups) {
+                    store4(xs + 4 * gidx, mul_rn((AT)ys[bo[k].x], wd[k][0]), mul_rn((AT)ys[bo[k].y], wd[k][1]),
+                           mul_rn((AT)ys[bo[k].z], wd[k][2]), mul_rn((AT)ys[bo[k].w], wd[k][3]));
+                }
+            }
+            for (int gidx = tid + kPre * W * 32; gidx < ngroups; gidx += W * 32) {
+                const int4 b4 = reinterpret_cast<const int4*>(a.beam_of)[gidx];
+                AT w4[4];
+                load4(a.w_dose + 4 * gidx, w4);
+                store4(xs + 4 * gidx, mul_rn((AT)ys[b4.x], w4[0]), mul_rn((AT)ys[b4.y], w4[1]),
+                       mul_rn((AT)ys[b4.z], w4[2]), mul_rn((AT)ys[b4.w], w4[3]));
+            }
+            for (int j = 4 * ngroups + tid; j < a.B; j += W * 32) xs[j] = mul_rn((AT)ys[a.beam_of[j]], a.w_dose[j]);
             named_bar_sync(1, W * 32);
         }
     }
@@ -201,6 +256,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     // done: consumers wait here; the producer first streams its statically assigned super-slice
     // (read-only data into its own ring) and waits only before it touches the counter
     if (warp < W) pdl_wait();
+    if (trace && tid == 0) trace[1] = global_timer_ns();
     if (a.seq != nullptr && blockIdx.x == 0 && warp < W) {
         if (XS) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
         if (tid == 0) atomicAdd(a.seq, 1ull);
@@ -213,18 +269,18 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
             RingPos pos;
             const unsigned int ns = (unsigned)a.nss;
             // super-slices 0 .. gridDim-1 (the longest) are assigned statically, the rest are
-            // claimed from the counter, one claim ahead of use
+            // claimed from the counter `claim_ahead` super-slices before use (0 = when needed: the
+            // ring hides the claim's latency, and a CTA never sits on work others could take -
+            // the traced spread of CTA finish times shrinks with it)
             const unsigned int G = gridDim.x;
-            unsigned int cur = blockIdx.x, nxt = 0, nn = 0;
-            bool claimed = false;
-            int64_t o0 = 0, o1 = 0, n0 = 0, n1 = 0;
-            int tpr = 1, ntpr = 1;
-            if (cur < ns) { o0 = a.ss_off[cur]; o1 = a.ss_off[cur + 1]; tpr = a.ss_tpr[cur]; }
+            const int depth = a.claim_ahead;
+            unsigned int cur = blockIdx.x, q[2] = {0u, 0u};
+            int qn = 0;
+            bool first = true;
             while (cur < ns) {
-                if (claimed) {
-                    nn = G + atomicAdd(a.counter, 1u);
-                    if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; ntpr = a.ss_tpr[nxt]; }
-                }
+                const int64_t o0 = a.ss_off[cur], o1 = a.ss_off[cur + 1];
+                const int tpr = a.ss_tpr[cur];
+                if (!first) while (qn < depth) q[qn++] = G + atomicAdd(a.counter, 1u);
                 const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
                 ring_push(ring, SB, full, empty, sinfo, pos, nst,
                           StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0), 0, tpr},
@@ -234,16 +290,16 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
                     ring_push(ring, SB, full, empty, sinfo, pos, nst,
                               StageInfo{(int32_t)cur, c == nch - 1 ? kStageLast : 0, 0, tpr},
                               data + (int64_t)c * W * KU, W * KU * 16, pol);
-                if (!claimed) {
+                if (first) {
                     pdl_wait();                       // the counter was reset by the previous evaluation's K2
-                    nxt = G + atomicAdd(a.counter, 1u);
-                    nn = G + atomicAdd(a.counter, 1u);
-                    if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; ntpr = a.ss_tpr[nxt]; }
-                    claimed = true;
+                    first = false;
+                    while (qn < depth) q[qn++] = G + atomicAdd(a.counter, 1u);
                 }
-                cur = nxt; nxt = nn; o0 = n0; o1 = n1; tpr = ntpr;
+                if (depth == 0) cur = G + atomicAdd(a.counter, 1u);
+                else { cur = q[0]; q[0] = q[1]; --qn; }
             }
             ring_push(ring, SB, full, empty, sinfo, pos, nst, StageInfo{-1, 0, 0, 0}, nullptr, 0, pol);
+            if (trace) trace[4] = global_timer_ns();
         }
         return;
     }
@@ -253,10 +309,12 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     RingPos pos;
     AT acc = (AT)0, t = (AT)0, ov = (AT)0, un = (AT)0;
     int32_t row = -1;
+    bool first = true;
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
+        if (first) { first = false; if (trace && tid == 0) trace[2] = global_timer_ns(); }
         StageInfo info = sinfo[pos.stage];
-        if (info.ss < 0) break;
+        if (info.ss < 0) { if (trace && tid == 0) trace[3] = global_timer_ns(); break; }
         if (info.flags & kStageHeader) {
             const unsigned char* hp = ring + (size_t)pos.stage * SB + warp * (HU * 16);
             row = reinterpret_cast<const int32_t*>(hp)[lane];
@@ -317,6 +375,7 @@ struct K2Args {
     const double* fpart;          // [nfpart] K1's per-slice objective partials ...
     double* fblock;               // [gridDim.x] ... folded here into one fixed-order sum per CTA
     int32_t nfpart;
+    unsigned long long* trace;    // diagnostics, as in K1Args: [entry, K1 done, first stage, consumers done, producer done]
 };
 
 template <typename VT, typename AT, int W, int IW>
@@ -331,8 +390,10 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     unsigned char* ring = smem_raw + tbytes;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nst = a.nstages, SB = a.stage_bytes;
+    unsigned long long* const trace = a.trace ? a.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
     pdl_launch_dependents();
     if (tid == 0) {
+        if (trace) trace[0] = global_timer_ns();
         for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
         mbar_init(&tilebar, 1);
         fence_barrier_init();
@@ -363,11 +424,13 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
                 }
             }
             ring_push(ring, SB, full, empty, sinfo, pos, nst, StageInfo{-1, 0, 0, 0}, nullptr, 0, pol);
+            if (trace) trace[4] = global_timer_ns();
         }
         return;
     }
 
     pdl_wait();          // vg is complete, the previous K3 has consumed `partial`
+    if (trace && tid == 0) trace[1] = global_timer_ns();
     if (blockIdx.x == 0 && tid == 0) *a.k1_counter = 0u;
     int cur_tile = -1;
     bool tile_pending = false;
@@ -395,10 +458,12 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     AT acc = (AT)0;
     int32_t row = -1;
     uint32_t tparity = 0;
+    bool first = true;
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
+        if (first) { first = false; if (trace && tid == 0) trace[2] = global_timer_ns(); }
         StageInfo info = sinfo[pos.stage];
-        if (info.ss < 0) break;
+        if (info.ss < 0) { if (trace && tid == 0) trace[3] = global_timer_ns(); break; }
         if (info.flags & kStageHeader) {
             const unsigned char* sp = ring + (size_t)pos.stage * SB;
             if (info.tile != cur_tile) {

@@ -39,7 +39,7 @@ class DosePlan:
     def __init__(self, D, beam_ptr, thr, over, under, device: int = 0, store: str = "f32",
                  acc: str = "f32", tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0,
                  k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0, index_bytes: int = 0,
-                 k1_stages: int = 0, k2_stages: int = 0):
+                 k1_stages: int = 0, k2_stages: int = 0, claim_ahead: int = -1, tail_cap: int = 0, tail_pct: int = 0):
         """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
         {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
         lib = _lib.load()
@@ -59,6 +59,8 @@ class DosePlan:
         opt.reserved[2] = chunk_cap
         opt.reserved[3] = 0 if pdl else 1
         opt.reserved[4] = host_path
+        opt.reserved[6] = claim_ahead + 1      # dose kernel: super-slices claimed ahead of use (0..2; -1 = default)
+        opt.reserved[7], opt.reserved[8] = tail_cap, tail_pct     # finer super-slices for the last tail_pct % (-1 = off)
         opt.reserved[5] = index_bytes          # 4 forces int32 column indices; 0 = uint16 whenever they fit
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
@@ -169,6 +171,17 @@ class DosePlan:
         n = C.c_int32()
         check(self._lib.vmat_get_timing(self._h, _ptr(ms), C.byref(n)), "vmat_get_timing")
         return dict(k1_ms=ms[0], k2_ms=ms[1], k3_ms=ms[2], eval_ms=ms[3], n=n.value)
+
+    def trace_eval(self):
+        """One evaluation with per-CTA time stamps: (k1[ctas, 5], k2[ctas, 5]) in ns relative to the
+        earliest stamp; columns = entry, inputs ready, first stage landed, consumers done, producer done."""
+        buf = np.zeros(8 * 4096, dtype=np.uint64)
+        n1, n2 = C.c_int32(), C.c_int32()
+        check(self._lib.vmat_trace_eval(self._h, _ptr(buf), buf.size, C.byref(n1), C.byref(n2)), "vmat_trace_eval")
+        t = buf[:8 * (n1.value + n2.value)].reshape(-1, 8)[:, :5].astype(np.int64)
+        t0 = t[t > 0].min()
+        t = np.where(t > 0, t - t0, -1)
+        return t[:n1.value], t[n1.value:]
 
     def reduce_buffer(self):
         """torch view (float64, B+1: gb then f) of the buffer to all-reduce between phases 1 and 2."""
