@@ -8,15 +8,17 @@ from vmatwpencode_b200.plan import DosePlan
 
 case, y, w_dose, w_grad = workload("cfg2", 1.0)
 Dt = case.D.tocsc()
-for name, kw in [("tags + y in launch params", dict(host_path=6)), ("tags + H2D node (default)", dict(host_path=2)), ("zero-copy both", dict(host_path=3)), ("zero-copy y only", dict(host_path=1)),
-                 ("zero-copy result only", dict(host_path=2)), ("memcpy nodes", dict(host_path=4)),
-                 ("memcpy nodes, no graph", dict(host_path=4, use_graph=False)), ("zero-copy both, no graph", dict(host_path=3, use_graph=False)),
-                 ("memcpy nodes, no pdl", dict(host_path=4, pdl=False))]:
+VARIANTS = [("graph: H2D node, K3 writes results + tags to host memory", dict(host_path=2)),
+            ("graph: H2D node, D2H node, stream sync", dict(host_path=8)),
+            ("no graph: y in launch params, D2H copy, stream sync", dict(host_path=4)),
+            ("no graph: y in launch params, tags", dict(host_path=6)),
+            ("no graph: H2D copy, D2H copy, stream sync", dict(host_path=8, use_graph=False))]
+for name, kw in [v for _ in range(3) for v in VARIANTS]:
     plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, Dt=Dt, **kw)
     plan.set_weights(w_dose, w_grad)
     for _ in range(50):
         plan.eval(y)
-    n = 2000
+    n = 3000
     t0 = time.perf_counter()
     for k in range(n):
         plan.eval(y if k & 1 else y * 1.0000001)

@@ -73,7 +73,7 @@ struct vmat_plan {
     DevBuf comm_buf, comm_ptrs, comm_state;
     std::vector<void*> comm_peers;        // opened IPC mappings (own slot = nullptr)
     int comm_rank = 0, comm_nranks = 1;
-    int host_path = 2;             // bit0: K1 reads y from mapped host memory; bit1: K3 publishes results + tags to host memory
+    int host_path = 4;             // bit0: K1 reads y from mapped host memory; bit1: K3 publishes results + tags to host memory
     bool x_in_smem = true;
     bool pdl = true;               // programmatic dependent launch between the evaluation kernels
     int k1_threads = 1024, k1_grid = 148, k2_threads = 256;
@@ -266,11 +266,22 @@ constexpr int kW2 = 4;      // ... of the transposed kernel
 constexpr int kTailCapDefault = 0, kTailPctDefault = 25;   // dose-kernel tail: finer super-slices (0 = off)
 constexpr int kClaimAheadDefault = 0;     // measured on config 2: 65.5 us per evaluation against 68.5 us with two claims ahead
 
+// dynamic shared memory limit of a kernel = what the device allows next to the kernel's static part
+template <typename Kern>
+static cudaError_t allow_max_smem(Kern kern, int smem_optin) {
+    cudaFuncAttributes fa{};
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa.sharedSizeBytes);
+}
+
 template <typename VT, typename AT>
 static int k2_occupancy_t(vmat_plan* P, int* occ) {
     DISPATCH_IW(IW, {
         auto kern = k2_beamlet_grad<VT, AT, kW2, IW>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
+        // the device maximum, set once per plan: every plan asks for the same value, so plans of
+        // different shapes never shrink each other's limit and launches need no further set-up
+        CU(allow_max_smem(kern, P->smem_optin));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, (kW2 + 1) * 32, P->k2_smem));
     });
     if (*occ < 1) return fail(VMAT_E_ARG, "transposed kernel does not fit on an SM with these options");
@@ -284,11 +295,11 @@ static int k1_occupancy_t(vmat_plan* P, int* occ) {
     DISPATCH_IW(IW, { DISPATCH_W1(W, {
         if (P->x_in_smem) {
             auto kern = k1_dose_penalty<VT, AT, true, W, IW>;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
+            CU(allow_max_smem(kern, P->smem_optin));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, P->k1_threads, P->k1_smem));
         } else {
             auto kern = k1_dose_penalty<VT, AT, false, W, IW>;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
+            CU(allow_max_smem(kern, P->smem_optin));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, P->k1_threads, P->k1_smem));
         }
     }); });
@@ -352,8 +363,10 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     P->acc_size = P->opt.acc_dtype == VMAT_F64 ? 8 : 4;
     P->pdl = P->opt.reserved[3] == 0;     // reserved[3] = 1 disables programmatic dependent launch
     // reserved[4]: host-buffer path bits - 1 = K1 reads y from mapped host memory, 2 = K3 publishes
-    // results + completion tags to mapped host memory (default), 4 = y travels in the launch parameters
-    P->host_path = P->opt.reserved[4] > 0 ? (P->opt.reserved[4] & 7) : 2;
+    // results + completion tags to mapped host memory, 4 = y travels in the launch parameters (plain
+    // launches, no graph; default - measured on config 2: 86 us per call against 90-95 us for the
+    // graph replays with a copy node in front, tools/latency.py)
+    P->host_path = P->opt.reserved[4] > 0 ? (P->opt.reserved[4] & 7) : 4;     // 8 = none of the bits
     P->beam_ptr.assign(beam_ptr, beam_ptr + nb + 1);
     CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -684,11 +697,9 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         DISPATCH_IW(IW, { DISPATCH_W1(W, {
             if (P->x_in_smem) {
                 auto kern = k1_dose_penalty<VT, AT, true, W, IW>;
-                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
                 CU(launch_pdl(kern, P->k1_grid, P->k1_threads, P->k1_smem, st, P->pdl, a1));
             } else {
                 auto kern = k1_dose_penalty<VT, AT, false, W, IW>;
-                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k1_smem));
                 CU(launch_pdl(kern, P->k1_grid, P->k1_threads, P->k1_smem, st, P->pdl, a1));
             }
         }); });
@@ -704,7 +715,6 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a2.trace = P->tracing ? P->trace.as<unsigned long long>() + (size_t)P->k1_grid * kTraceSlots : nullptr;
         DISPATCH_IW(IW, {   // always launched (even with an empty task list): it also folds the objective partials
             auto kern2 = k2_beamlet_grad<VT, AT, kW2, IW>;
-            CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->k2_smem));
             CU(launch_pdl(kern2, P->k2_grid, (kW2 + 1) * 32, P->k2_smem, st, P->pdl, a2));
         });
     }
