@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--index-bytes", type=int, default=0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--dump", default="", help="write the raw stamps of every repetition to this .npz")
     args = ap.parse_args()
     case = make_config(args.workload)
     plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, index_bytes=args.index_bytes)
@@ -33,12 +34,16 @@ def main():
     y = rng.random(case.nb)
     for _ in range(20):
         plan.eval(y)
-    for _ in range(args.reps):
+    raw = {}
+    for rep in range(args.reps):
         k1, k2 = plan.trace_eval()
+        raw[f"k1_{rep}"], raw[f"k2_{rep}"] = k1, k2
         out = dict(workload=args.workload, unit="us since the first stamp; [min, median, max] over CTAs")
         out.update(summary("k1", k1))
         out.update(summary("k2", k2))
         print(json.dumps(out))
+    if args.dump:
+        np.savez(args.dump, **raw)
     plan.close()
 
 
