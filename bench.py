@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--k2-threads", type=int, default=0)
     ap.add_argument("--k1-threads", type=int, default=0)
     ap.add_argument("--index-bytes", type=int, default=0, help="4 forces int32 column indices (default: uint16 when they fit)")
+    ap.add_argument("--claim-lead", type=int, default=0, help="dose kernel: stages before a super-slice's end at which the next is claimed (tuning; 0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -213,7 +214,7 @@ def main():
         rows, D, thr, over, under = slab_of(case, rank, world)
     plan = DosePlan(D, case.beam_ptr, thr, over, under, device=local, store=args.store, acc=args.acc,
                     tile_voxels=args.tile, k2_tasks=args.k2_tasks, k2_threads=args.k2_threads,
-                    k1_threads=args.k1_threads, index_bytes=args.index_bytes)
+                    k1_threads=args.k1_threads, index_bytes=args.index_bytes, claim_lead=args.claim_lead)
     if args.workload in DEVICE_WORKLOADS:      # the CSR copies are no longer needed: the plan holds its own layouts
         case.csr = None
         del D

@@ -264,7 +264,7 @@ struct StreamDesc {
 // 4 (several CTAs per SM, each with its own copy of x) on request; chosen per plan (vmat_plan::W1)
 constexpr int kW2 = 4;      // ... of the transposed kernel
 constexpr int kTailCapDefault = 0, kTailPctDefault = 25;   // dose-kernel tail: finer super-slices (0 = off)
-constexpr int kClaimAheadDefault = 0;     // measured on config 2: 65.5 us per evaluation against 68.5 us with two claims ahead
+constexpr int kClaimLeadDefault = 8;
 
 // dynamic shared memory limit of a kernel = what the device allows next to the kernel's static part
 template <typename Kern>
@@ -685,7 +685,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.d = P->d.as<AT>(); a1.vg = P->vg.as<AT>(); a1.fpart = P->fpart.as<double>();
         a1.counter = P->counter.as<unsigned int>();
         a1.nb = P->nb;
-        a1.claim_ahead = P->opt.reserved[6] > 0 ? std::min(2, P->opt.reserved[6] - 1) : kClaimAheadDefault;
+        a1.claim_lead = P->opt.reserved[6] > 0 ? P->opt.reserved[6] : kClaimLeadDefault;
         a1.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
         if (host_mode && (P->host_path & 4) && P->nb <= kInlineY && P->x_in_smem) {
             a1.y_inline_n = P->nb;

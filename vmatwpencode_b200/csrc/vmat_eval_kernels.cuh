@@ -168,7 +168,7 @@ struct K1Args {
     // diagnostics (vmat_trace_eval): per CTA, globaltimer at [entry, x staged + predecessor done,
     // first stage landed, consumers done, producer done]; nullptr = off
     unsigned long long* trace;
-    int32_t claim_ahead;          // 0, 1 or 2 super-slices claimed before they are needed
+    int32_t claim_lead;           // stages before the end of a super-slice at which the next one is claimed
 };
 
 // four consecutive elements with one (float) or two (double) 16-byte loads
@@ -269,34 +269,47 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
             RingPos pos;
             const unsigned int ns = (unsigned)a.nss;
             // super-slices 0 .. gridDim-1 (the longest) are assigned statically, the rest are
-            // claimed from the counter `claim_ahead` super-slices before use (0 = when needed: the
-            // ring hides the claim's latency, and a CTA never sits on work others could take -
-            // the traced spread of CTA finish times shrinks with it)
+            // claimed from the counter while the last `claim_lead` stages of the current one are
+            // being pushed: late enough that no CTA sits on work others could take (the traced
+            // spread of CTA finish times halves against claiming two super-slices ahead), early
+            // enough that the claim and the offset loads are back before the producer needs them
             const unsigned int G = gridDim.x;
-            const int depth = a.claim_ahead;
-            unsigned int cur = blockIdx.x, q[2] = {0u, 0u};
-            int qn = 0;
+            const int lead = a.claim_lead;
+            unsigned int cur = blockIdx.x;
             bool first = true;
+            int64_t o0 = 0, o1 = 0;
+            int tpr = 1;
+            if (cur < ns) { o0 = a.ss_off[cur]; o1 = a.ss_off[cur + 1]; tpr = a.ss_tpr[cur]; }
             while (cur < ns) {
-                const int64_t o0 = a.ss_off[cur], o1 = a.ss_off[cur + 1];
-                const int tpr = a.ss_tpr[cur];
-                if (!first) while (qn < depth) q[qn++] = G + atomicAdd(a.counter, 1u);
                 const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
+                unsigned int nxt = 0u;
+                int64_t n0 = 0, n1 = 0;
+                int ntpr = 1;
+                bool claimed = false, loaded = false;
+                const int c_claim = max(0, nch - lead), c_load = min(c_claim + 4, max(0, nch - 1));
                 ring_push(ring, SB, full, empty, sinfo, pos, nst,
                           StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0), 0, tpr},
                           a.sell + o0, W * HU * 16, pol);
                 const uint4* data = a.sell + o0 + W * HU;
-                for (int c = 0; c < nch; ++c)
+                for (int c = 0; c < nch; ++c) {
+                    if (!first) {
+                        if (c == c_claim) { nxt = G + atomicAdd(a.counter, 1u); claimed = true; }
+                        if (c == c_load && claimed) {
+                            if (nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; ntpr = a.ss_tpr[nxt]; }
+                            loaded = true;
+                        }
+                    }
                     ring_push(ring, SB, full, empty, sinfo, pos, nst,
                               StageInfo{(int32_t)cur, c == nch - 1 ? kStageLast : 0, 0, tpr},
                               data + (int64_t)c * W * KU, W * KU * 16, pol);
+                }
                 if (first) {
                     pdl_wait();                       // the counter was reset by the previous evaluation's K2
                     first = false;
-                    while (qn < depth) q[qn++] = G + atomicAdd(a.counter, 1u);
                 }
-                if (depth == 0) cur = G + atomicAdd(a.counter, 1u);
-                else { cur = q[0]; q[0] = q[1]; --qn; }
+                if (!claimed) nxt = G + atomicAdd(a.counter, 1u);
+                if (!loaded && nxt < ns) { n0 = a.ss_off[nxt]; n1 = a.ss_off[nxt + 1]; ntpr = a.ss_tpr[nxt]; }
+                cur = nxt; o0 = n0; o1 = n1; tpr = ntpr;
             }
             ring_push(ring, SB, full, empty, sinfo, pos, nst, StageInfo{-1, 0, 0, 0}, nullptr, 0, pol);
             if (trace) trace[4] = global_timer_ns();
@@ -309,12 +322,11 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     RingPos pos;
     AT acc = (AT)0, t = (AT)0, ov = (AT)0, un = (AT)0;
     int32_t row = -1;
-    bool first = true;
+    if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }    // outside the hot loop
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
-        if (first) { first = false; if (trace && tid == 0) trace[2] = global_timer_ns(); }
         StageInfo info = sinfo[pos.stage];
-        if (info.ss < 0) { if (trace && tid == 0) trace[3] = global_timer_ns(); break; }
+        if (info.ss < 0) break;
         if (info.flags & kStageHeader) {
             const unsigned char* hp = ring + (size_t)pos.stage * SB + warp * (HU * 16);
             row = reinterpret_cast<const int32_t*>(hp)[lane];
@@ -347,6 +359,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
         }
         pos.advance(nst);
     }
+    if (trace && tid == 0) trace[3] = global_timer_ns();
 }
 
 // ---------------------------------------------------------------------------------
@@ -458,12 +471,11 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     AT acc = (AT)0;
     int32_t row = -1;
     uint32_t tparity = 0;
-    bool first = true;
+    if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }    // outside the hot loop
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
-        if (first) { first = false; if (trace && tid == 0) trace[2] = global_timer_ns(); }
         StageInfo info = sinfo[pos.stage];
-        if (info.ss < 0) { if (trace && tid == 0) trace[3] = global_timer_ns(); break; }
+        if (info.ss < 0) break;
         if (info.flags & kStageHeader) {
             const unsigned char* sp = ring + (size_t)pos.stage * SB;
             if (info.tile != cur_tile) {
@@ -497,6 +509,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
         }
         pos.advance(nst);
     }
+    if (trace && tid == 0) trace[3] = global_timer_ns();
 }
 
 // ---------------------------------------------------------------------------------
