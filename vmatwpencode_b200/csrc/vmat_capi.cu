@@ -210,8 +210,6 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
 // lanes per row, where tpr is the smallest power of two that keeps the slice within `cap` chunks.
 struct StreamDesc {
     int32_t W, HU, units, cap;
-    int32_t tail_cap = 0;        // > 0: chunk cap for the last tail_pct % of a group's work, so that the
-    int32_t tail_pct = 0;        // dynamically scheduled dose kernel ends on small super-slices
     std::vector<int64_t> ss_off{0}, seg_start;
     std::vector<uint8_t> ss_tpr;
     std::vector<int32_t> seg_len, seg_cb, rows, ss_tile;
@@ -222,15 +220,11 @@ struct StreamDesc {
     void add_group(const std::vector<Item>& items, int32_t colbase, int32_t tile,
                    const double* thr, const double* over, const double* under) {
         size_t pos = 0;
-        int64_t total_chunks = 0, done_chunks = 0;
-        for (const Item& it : items) total_chunks += (it.len + 3) / 4;
-        const int64_t tail_from = tail_cap > 0 ? total_chunks - total_chunks * tail_pct / 100 : total_chunks + 1;
         while (pos < items.size()) {
             const int32_t maxlen = items[pos].len;
             const int64_t nch1 = (maxlen + 3) / 4;
-            const int64_t cap_here = done_chunks >= tail_from ? tail_cap : cap;
             int tpr = 1;
-            while ((nch1 + tpr - 1) / tpr > cap_here && tpr < 32) tpr *= 2;
+            while ((nch1 + tpr - 1) / tpr > cap && tpr < 32) tpr *= 2;
             const int64_t nch = (nch1 + tpr - 1) / tpr;
             const size_t rows_per_slice = 32 / tpr, rows_per_ss = rows_per_slice * W;
             const size_t base_slot = seg_start.size();
@@ -241,7 +235,6 @@ struct StreamDesc {
             if (thr) { t_s.resize(base_slot + (size_t)32 * W, 0.0); o_s.resize(base_slot + (size_t)32 * W, 0.0); u_s.resize(base_slot + (size_t)32 * W, 0.0); }
             for (size_t r = 0; r < rows_per_ss && pos < items.size(); ++r, ++pos) {
                 const Item& it = items[pos];
-                done_chunks += (it.len + 3) / 4;
                 const size_t w = r / rows_per_slice, q = r % rows_per_slice;
                 for (int part = 0; part < tpr; ++part) {
                     const size_t slot = base_slot + w * 32 + q * tpr + part;
@@ -263,7 +256,14 @@ struct StreamDesc {
 // consumer warps (slices per super-slice) of the dose kernel: 16 with one CTA per SM by default,
 // 4 (several CTAs per SM, each with its own copy of x) on request; chosen per plan (vmat_plan::W1)
 constexpr int kW2 = 4;      // ... of the transposed kernel
-constexpr int kTailCapDefault = 0, kTailPctDefault = 25;   // dose-kernel tail: finer super-slices (0 = off)
+// chunks per lane and super-slice (more lanes per row beyond that).  Measured (configs 2 and 3): the
+// dynamically scheduled dose kernel likes long super-slices (less padding: 140 -> 134 us on config 3
+// from 24 to 48), the statically partitioned transposed kernel short ones (finer piece boundaries)
+constexpr int kChunkCapK1 = 48, kChunkCapK2 = 24;
+// voxels per tile of the transposed layout: larger tiles mean longer beamlet segments (less padding)
+// and fewer tile partials for K3, but one CTA less per SM.  Measured: config 2 (300k voxels) 65.2 us
+// with 4096 against 66.2 us with 6144; config 3 (1M) 273 against 268 us; config 4 (4M) 434 against 446 evals/s
+static int32_t default_tile_voxels(int64_t V) { return V > 500000 ? 6144 : 4096; }
 constexpr int kClaimLeadDefault = 8;
 
 // dynamic shared memory limit of a kernel = what the device allows next to the kernel's static part
@@ -373,7 +373,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaDeviceGetAttribute(&P->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaStream_t st = P->stream;
     {   // index width: uint16 when every stored index fits (x index < B; K2 indices are tile-local, < T)
-        const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : 4096;
+        const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V);
         const bool fits16 = B <= 65536 && ((T0 + 63) / 64 * 64) <= 65536;
         P->iw = (P->opt.reserved[5] == 4 || !fits16) ? 4 : 2;      // reserved[5] = 4 forces int32 indices
     }
@@ -452,10 +452,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - (h_vrow[v + 1] - h_vrow[v])]++] = (int32_t)v;
         }
         const int32_t W = P->W1, HU = 8 + 3 * (32 * es / 16);
-        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2] : 24;
+        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2] : kChunkCapK1;
         StreamDesc sd{W, HU, units, cap};
-        sd.tail_cap = P->opt.reserved[7] > 0 ? P->opt.reserved[7] : (P->opt.reserved[7] < 0 ? 0 : kTailCapDefault);
-        sd.tail_pct = P->opt.reserved[8] > 0 ? std::min(100, P->opt.reserved[8]) : kTailPctDefault;
         std::vector<StreamDesc::Item> items(V);
         for (int64_t pos = 0; pos < V; ++pos) {
             const int32_t v = order[pos];
@@ -490,7 +488,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
     // ---- K2 layout: column tiles of T voxels; per tile, beamlet segments sorted by length
     {
-        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : 4096;
+        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V);
         T = (T + 63) / 64 * 64;
         const int32_t W = kW2, HU = 8;
         P->W2 = W;
@@ -511,7 +509,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         CU(cudaStreamSynchronize(st));
         d_seg.alloc(0);
 
-        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2] : 24;
+        const int32_t cap = P->opt.reserved[7] > 0 ? P->opt.reserved[7] : kChunkCapK2;
         StreamDesc sd{W, HU, units, cap};
         std::vector<StreamDesc::Item> items;
         for (int32_t t = 0; t < nt; ++t) {
@@ -527,8 +525,12 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const std::vector<int64_t>& ss_cost = sd.ss_cost;
         const std::vector<int32_t>& ss_tile = sd.ss_tile;
         P->nss2 = (int32_t)ss_cost.size(); P->nslices2 = P->nss2 * W; P->units2 = sd.ss_off.back();
-        // Persistent CTAs: the (tile, length)-ordered super-slice sequence is cut into G pieces of
-        // equal work; a piece that crosses a tile boundary becomes two tasks of the same CTA.
+        // Persistent CTAs, static partition: every CTA gets the same number of ring stages.  Within a
+        // tile the super-slices run from long rows (up to cap+1 stages each) to short ones (a few
+        // stages), so a CTA takes long ones from the front of the tile's range while they fit and
+        // tops up with short ones from the back: piece sizes then differ by a few stages instead of
+        // by a whole long super-slice (60..99 stages around a mean of 85 on config 2 before).  A CTA
+        // that exhausts a tile continues in the next one (one more vg tile load).
         int occ = 1;
         if (int rc = k2_occupancy(P, &occ)) return rc;
         const int64_t G = P->opt.k2_tasks > 0 ? P->opt.k2_tasks : (int64_t)P->sm_count * occ;
@@ -538,23 +540,30 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         std::vector<K2Task> tasks;
         std::vector<int32_t> cta_ptr(P->k2_grid + 1, 0);
         {
-            int32_t cur = 0;
-            int64_t acc = 0;
             const int32_t nss = P->nss2;
+            int32_t f = 0, bk = 0, tend = 0;         // unassigned super-slices of the current tile: [f, bk); the tile ends at tend
+            auto next_tile = [&]() {
+                f = tend;
+                while (tend < nss && ss_tile[tend] == ss_tile[f]) ++tend;
+                bk = tend;
+            };
+            next_tile();
+            int64_t assigned = 0;
             for (int c = 0; c < P->k2_grid; ++c) {
                 cta_ptr[c] = (int32_t)tasks.size();
+                const bool last = c == P->k2_grid - 1;
                 const int64_t goal = total_w * (c + 1) / P->k2_grid;
-                int32_t end = cur;
-                while (end < nss && acc < goal) { acc += ss_cost[end]; ++end; }
-                if (c == P->k2_grid - 1) end = nss;
-                int32_t b0 = cur;
-                while (b0 < end) {              // split at tile boundaries
-                    int32_t b1 = b0;
-                    while (b1 < end && ss_tile[b1] == ss_tile[b0]) ++b1;
-                    tasks.push_back(K2Task{ss_tile[b0], b0, b1, 0});
-                    b0 = b1;
+                while (f < nss && (last || assigned < goal)) {
+                    const int32_t tile = ss_tile[f], f0 = f, b0 = bk;
+                    while (f < bk && (last || assigned + ss_cost[f] <= goal)) assigned += ss_cost[f++];
+                    while (f < bk && (last || assigned + ss_cost[bk - 1] <= goal)) assigned += ss_cost[--bk];
+                    // nothing fits any more: take the smallest remaining one only if that ends closer to the goal
+                    if (f < bk && assigned < goal && 2 * (goal - assigned) > ss_cost[bk - 1]) assigned += ss_cost[--bk];
+                    if (f > f0) tasks.push_back(K2Task{tile, f0, f, 0});
+                    if (bk < b0) tasks.push_back(K2Task{tile, bk, b0, 0});
+                    if (f < bk) break;               // goal reached inside this tile
+                    next_tile();                     // tile exhausted: continue in the next one
                 }
-                cur = end;
             }
             cta_ptr[P->k2_grid] = (int32_t)tasks.size();
         }
