@@ -334,7 +334,7 @@ static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaS
 }
 
 static int capture_graph(vmat_plan* P);
-static int launch_eval(vmat_plan* P, cudaStream_t st, int phase, bool host_mode = false);
+static int launch_eval(vmat_plan* P, cudaStream_t st, int phase, bool host_mode = false, bool inline_y = false);
 
 extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_t B, int32_t nb,
                                 const int32_t* beam_ptr,
@@ -672,7 +672,7 @@ extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layou
 // evaluation
 // ---------------------------------------------------------------------------------
 template <typename VT, typename AT>
-static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mode) {
+static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mode, bool inline_y) {
     cudaEvent_t* ev = nullptr;
     if (P->timing && phase == 0) {
         ev = &P->tev[(P->tcount % vmat_plan::kTimingSlots) * 4];
@@ -696,7 +696,8 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.nb = P->nb;
         a1.claim_lead = P->opt.reserved[6] > 0 ? P->opt.reserved[6] : kClaimLeadDefault;
         a1.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
-        if (host_mode && (P->host_path & 4) && P->nb <= kInlineY && P->x_in_smem) {
+        if (inline_y) {              // the intensities travel in the launch parameters; CTA 0 mirrors them into P->y
+            a1.y_mirror = P->y.as<double>();
             a1.y_inline_n = P->nb;
             std::memcpy(a1.y_inline, P->h_y, (size_t)P->nb * 8);
         }
@@ -751,9 +752,9 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
     return 0;
 }
 
-static int launch_eval(vmat_plan* P, cudaStream_t st, int phase, bool host_mode) {
+static int launch_eval(vmat_plan* P, cudaStream_t st, int phase, bool host_mode, bool inline_y) {
     DISPATCH_STORE(P->opt.store_dtype, VT, {
-        DISPATCH_ACC(P->opt.acc_dtype, AT, { return launch_eval_t<VT, AT>(P, st, phase, host_mode); });
+        DISPATCH_ACC(P->opt.acc_dtype, AT, { return launch_eval_t<VT, AT>(P, st, phase, host_mode, inline_y); });
     });
     return 0;
 }
@@ -807,8 +808,10 @@ extern "C" int vmat_set_intensities(vmat_plan_t* P, const double* y) {
     return VMAT_OK;
 }
 
+// A timed-out exchange returns NaN results (k3_reduce_exchange); only then is the device-side error
+// word worth a synchronous read.
 static int check_comm(vmat_plan* P) {
-    if (P->comm_nranks <= 1) return 0;
+    if (P->comm_nranks <= 1 || P->h_res[0] == P->h_res[0]) return 0;
     int32_t st[16];
     CU(cudaMemcpy(st, P->comm_state.p, 64, cudaMemcpyDeviceToHost));
     if (st[8] != 0) return fail(VMAT_E_CUDA, "multi-GPU exchange timed out: a peer rank did not evaluate in lock step");
@@ -820,14 +823,14 @@ extern "C" int vmat_eval(vmat_plan_t* P, const double* y, double* f, double* g) 
     CU(cudaSetDevice(P->device));
     std::memcpy(P->h_y, y, P->nb * 8);
     const bool multi = P->comm_nranks > 1;            // fused exchange: plain copies, no host tags
-    const bool inline_y = (P->host_path & 4) && !multi && P->nb <= kInlineY && P->x_in_smem;
+    const bool inline_y = (P->host_path & 4) && P->nb <= kInlineY && P->x_in_smem;
     const bool zc_y = ((P->host_path & 1) && !multi) || inline_y, zc_res = (P->host_path & 2) && !multi;
     const unsigned long long expect = ++P->host_seq;
     if (P->graph_exec && !multi && !inline_y) {
         CU(cudaGraphLaunch(P->graph_exec, P->stream));
     } else {
         if (!zc_y) CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
-        if (int rc = launch_eval(P, P->stream, 0, !multi)) return rc;
+        if (int rc = launch_eval(P, P->stream, 0, !multi, inline_y)) return rc;
         if (!zc_res) CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream));
     }
     if (!zc_res) {

@@ -257,9 +257,9 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     // (read-only data into its own ring) and waits only before it touches the counter
     if (warp < W) pdl_wait();
     if (trace && tid == 0) trace[1] = global_timer_ns();
-    if (a.seq != nullptr && blockIdx.x == 0 && warp < W) {
-        if (XS) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
-        if (tid == 0) atomicAdd(a.seq, 1ull);
+    if (blockIdx.x == 0 && warp < W) {
+        if (XS && a.y_mirror != nullptr) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
+        if (a.seq != nullptr && tid == 0) atomicAdd(a.seq, 1ull);
     }
 
     if (warp == W) {
