@@ -104,6 +104,22 @@ def colgen_fixture(name, case, C, kappasize, max_iter, elimination=False, module
     print(name, "iterations", len(hist), "sequence", [h["idx"] for h in hist])
 
 
+def colgen_files_fixture(name, seed, C, kappasize, max_iter):
+    """Files -> the reference's own loader -> the reference's own greedy loop, on a synthetic
+    CORT-format data set the tests regenerate from `seed` (oracle/cort_fixture.py)."""
+    import tempfile
+    from oracle.cort_fixture import write_cort_like
+    cfg = write_cort_like(tempfile.mkdtemp(), seed=seed)
+    hist, _ = R.ref_colgen_loaded(cfg, C, kappasize, max_iter=max_iter)
+    out = dict(seed=np.int64(seed), C=np.float64(C), kappasize=np.int64(kappasize), max_iter=np.int64(max_iter),
+               idx=np.asarray([h["idx"] for h in hist], dtype=np.int64),
+               l=np.asarray([h["l"] for h in hist], dtype=np.int64), r=np.asarray([h["r"] for h in hist], dtype=np.int64),
+               pstar=np.asarray([h["pstar"] for h in hist]), x=np.asarray([h["x"] for h in hist]),
+               fun=np.asarray([h["fun"] for h in hist]))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "iterations", len(hist), "sequence", [h["idx"] for h in hist])
+
+
 def kmedoids_fixture():
     """The reference's only embedded known answer: the hard-coded kappa list
     (greedyVMAT.py:28) equals givemewholelist(range(6,178,11), range(178)); plus small runs
@@ -218,6 +234,7 @@ def main():
     dvh_fixture()
     ingest_fixture("ingest_A", seed=1)
     ingest_fixture("ingest_B", seed=2)
+    colgen_files_fixture("colgen_files", seed=3, C=0.01, kappasize=3, max_iter=6)
     kmedoids_fixture()
 
 

@@ -204,12 +204,14 @@ def ref_colgen(ns, case, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vma
     return history
 
 
-def run_reference_loader(cfg: dict, module: str = "greedyVMATsampling"):
+def run_reference_loader(cfg: dict, module: str = "greedyVMATsampling", with_functions: bool = False):
     """Execute the reference's own loader - the TOP-LEVEL statements of the script between
     ``start = time.time()`` and the quadHelper loops (greedyVMATsampling.py:286-576), plus the
     class definitions they need - on a data set written by oracle/cort_fixture.py.  The hard-coded
     path / priority / gantry-range assignments are dropped and replaced by `cfg`.
-    Returns the namespace (``data``, ``DlistT``, ``quadHelper*``, ``N``, ``M``, ...)."""
+    Returns the namespace (``data``, ``DlistT``, ``quadHelper*``, ``N``, ``M``, ...).  With
+    `with_functions` the reference's hot-path functions are defined in the same namespace, so the
+    greedy loop can then run on what the reference's loader produced (``ref_colgen_loaded``)."""
     import glob
     import scipy.io as sio
     path = os.path.join(REFERENCE_ROOT, module + ".py")
@@ -223,6 +225,8 @@ def run_reference_loader(cfg: dict, module: str = "greedyVMATsampling"):
     keep = []
     for n in tree.body:
         if isinstance(n, ast.ClassDef) and n.name in ("region", "apertureList", "vmat_class"):
+            keep.append(n)
+        elif with_functions and isinstance(n, ast.FunctionDef) and n.name in _HOT:
             keep.append(n)
         elif first <= n.lineno <= last:
             if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") in seeded:
@@ -241,6 +245,28 @@ def run_reference_loader(cfg: dict, module: str = "greedyVMATsampling"):
     finally:
         os.chdir(cwd)
     return ns
+
+
+def ref_colgen_loaded(cfg: dict, C, kappasize, max_iter=None, **kw):
+    """Files -> the reference's loader -> the reference's greedy loop: the aperture sequence a user of
+    the reference gets from a data set written by oracle/cort_fixture.py."""
+    import types
+    ns = run_reference_loader(cfg, with_functions=True)
+    data = ns["data"]
+    M, N = len(data.xinter), len(data.yinter)
+    data.llist = [[-1] * M for _ in range(data.numbeams)]
+    data.rlist = [[N + 1] * M for _ in range(data.numbeams)]
+    data.openApertureMaps = [[] for _ in range(data.numbeams)]
+    data.diagmakers = [[] for _ in range(data.numbeams)]
+    data.strengths = [[] for _ in range(data.numbeams)]
+    data.currentIntensities = np.zeros(data.numbeams)
+    data.notinC = ns["apertureList"]()
+    data.caligraphicC = ns["apertureList"]()
+    data.listIndexofAperturesRemovedEachStep = []
+    data.pointtoAngle = list(data.pointtoAngle)
+    ns["penalizationweights"] = [None] * data.numbeams
+    shape = types.SimpleNamespace(nb=data.numbeams, N=N, M=M)
+    return ref_colgen(ns, shape, C, kappasize, max_iter=max_iter, **kw), ns
 
 
 def ref_printresults(dose, full_mask, numstructs):

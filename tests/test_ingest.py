@@ -68,17 +68,42 @@ def test_ingest_matches_reference_live(tmp_path):
     assert np.array_equal(case.fullMaskValue, data.fullMaskValue)
 
 
+def test_files_to_aperture_sequence_oracle_matches_reference_fixture(tmp_path):
+    """Data set on disk -> load_cort -> the oracle's greedy loop, against what the reference's own
+    loader and loop produced from the same files (fixture colgen_files): bit for bit."""
+    from oracle import vmat_oracle as O
+    z = np.load(os.path.join(GOLDEN, "colgen_files.npz"))
+    cfg, case = _load(tmp_path, int(z["seed"]))
+    hist = O.col_gen(O.OracleState(case), C=float(z["C"]), kappasize=int(z["kappasize"]), max_iter=int(z["max_iter"]))
+    assert [h["idx"] for h in hist] == list(z["idx"]) and len(hist) > 0
+    for h, l, r, p, x, fun in zip(hist, z["l"], z["r"], z["pstar"], z["x"], z["fun"]):
+        assert h["l"] == list(l) and h["r"] == list(r)
+        assert h["pstar"] == p and h["fun"] == fun and np.array_equal(h["x"], x)
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference not mounted")
+def test_files_to_aperture_sequence_live(tmp_path):
+    from oracle import vmat_oracle as O
+    cfg, case = _load(tmp_path, 5)
+    ref, _ = R.ref_colgen_loaded(cfg, 0.01, 3, max_iter=5)
+    hist = O.col_gen(O.OracleState(case), C=0.01, kappasize=3, max_iter=5)
+    assert [(h["idx"], h["l"], h["r"], h["pstar"], h["fun"]) for h in hist] == \
+           [(h["idx"], h["l"], h["r"], h["pstar"], h["fun"]) for h in ref]
+
+
 @pytest.mark.gpu
 def test_loaded_case_runs_the_greedy_loop(tmp_path):
-    """A loaded case binds like a synthetic one and the greedy loop matches the oracle on it
-    (ragged beamlet rows come from the grid cut here, not from the generator)."""
-    from oracle import vmat_oracle as O
+    """Data set on disk -> load_cort -> bind -> colGen on the GPU: the aperture sequence the
+    reference's own loader and loop produced from the same files (fixture colgen_files; ragged
+    beamlet rows come from the grid cut here, not from the generator)."""
     from vmatwpencode_b200 import VMATlibrary as vl
-    cfg, case = _load(tmp_path, 3)
-    want = O.col_gen(O.OracleState(case), C=0.01, kappasize=3, max_iter=4, clean=True)
+    z = np.load(os.path.join(GOLDEN, "colgen_files.npz"))
+    cfg, case = _load(tmp_path, int(z["seed"]))
     data = vl.bind(case, store="f64", acc="f64")
-    vl.colGen(0.01, False, 3, max_iter=4)
-    assert [h["idx"] for h in data.history] == [h["idx"] for h in want] and len(want) > 0
-    for a, b in zip(data.history, want):
-        assert a["l"] == b["l"] and a["r"] == b["r"]
+    vl.colGen(float(z["C"]), False, int(z["kappasize"]), max_iter=int(z["max_iter"]))
+    hist = data.history
+    assert [h["idx"] for h in hist] == list(z["idx"]) and len(hist) > 0
+    for h, l, r, p, fun in zip(hist, z["l"], z["r"], z["pstar"], z["fun"]):
+        assert h["l"] == list(l) and h["r"] == list(r)          # bit-exact leaf positions
+        assert abs(h["pstar"] - p) <= 1e-9 * abs(p) and abs(h["fun"] - fun) <= 1e-9 * abs(fun)
     data.plan.close()
