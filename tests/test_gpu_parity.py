@@ -260,15 +260,19 @@ def test_pricing_before_any_evaluation_is_an_error():
     data.plan.close()
 
 
-def test_greedy_loop_vs_oracle_medium_case():
-    """A config-1-like case (smaller V) end to end: same aperture sequence as the oracle."""
-    case = make_case(V=8000, nb=36, M=7, N=8, density=0.01, seed=1001, gastep=10)
-    want = O.col_gen(O.OracleState(case), C=0.01, kappasize=16, max_iter=12, clean=True)
+def test_greedy_loop_config1_to_completion_vs_oracle():
+    """BASELINE.json configs[0] (20k voxels x 2 016 beamlets, 36 control points): the whole greedy
+    run, until every control point has an aperture or pricing finds nothing: same aperture
+    sequence, leaf for leaf, as the oracle."""
+    case = make_config("cfg1")
+    want = O.col_gen(O.OracleState(case), C=0.01, kappasize=16, max_iter=40, clean=True)
     data = vl.bind(case, store="f32", acc="f64")
-    vl.colGen(0.01, False, 16, max_iter=12)
+    vl.colGen(0.01, False, 16, max_iter=40)
+    assert len(want) >= 30
     assert [h["idx"] for h in data.history] == [h["idx"] for h in want]
     for a, b in zip(data.history, want):
         assert a["l"] == b["l"] and a["r"] == b["r"]
+        assert abs(a["fun"] - b["fun"]) <= 1e-6 * abs(b["fun"])
     data.plan.close()
 
 
