@@ -40,7 +40,7 @@ typedef struct vmat_options {
     int32_t acc_dtype;      /* VMAT_F32 | VMAT_F64: accumulation, and dtype of x, dose, vg     */
     int32_t tile_voxels;    /* voxels per column tile of the transposed layout (0 = default)   */
     int32_t k1_threads;     /* threads per CTA of the dose kernel (0 = default)                */
-    int32_t k2_threads;     /* threads per CTA of the transposed kernel (0 = default)          */
+    int32_t k2_threads;     /* transposed kernel: >= 512 -> 16 consumer warps per CTA, >= 256 -> 8, else 4 (default) */
     int32_t k2_tasks;       /* CTAs of the transposed kernel (0 = default)                     */
     int32_t use_graph;      /* 1: replay the three-kernel evaluation as one CUDA graph         */
     int32_t reserved[9];    /* [5]: 4 forces int32 column indices (default: uint16 whenever they fit) */

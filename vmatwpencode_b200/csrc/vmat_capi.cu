@@ -255,7 +255,9 @@ struct StreamDesc {
 
 // consumer warps (slices per super-slice) of the dose kernel: 16 with one CTA per SM by default,
 // 4 (several CTAs per SM, each with its own copy of x) on request; chosen per plan (vmat_plan::W1)
-constexpr int kW2 = 4;      // ... of the transposed kernel
+// ... of the transposed kernel: 4 by default (five CTAs per SM), 8 or 16 on request (vmat_plan::W2)
+#define DISPATCH_W2(W, ...)                                                  \
+    if (P->W2 == 16) { constexpr int W = 16; __VA_ARGS__; } else if (P->W2 == 8) { constexpr int W = 8; __VA_ARGS__; } else { constexpr int W = 4; __VA_ARGS__; }
 // chunks per lane and super-slice (more lanes per row beyond that).  Measured (configs 2 and 3): the
 // dynamically scheduled dose kernel likes long super-slices (less padding: 140 -> 134 us on config 3
 // from 24 to 48), the statically partitioned transposed kernel short ones (finer piece boundaries)
@@ -277,13 +279,13 @@ static cudaError_t allow_max_smem(Kern kern, int smem_optin) {
 
 template <typename VT, typename AT>
 static int k2_occupancy_t(vmat_plan* P, int* occ) {
-    DISPATCH_IW(IW, {
-        auto kern = k2_beamlet_grad<VT, AT, kW2, IW>;
+    DISPATCH_IW(IW, { DISPATCH_W2(W2c, {
+        auto kern = k2_beamlet_grad<VT, AT, W2c, IW>;
         // the device maximum, set once per plan: every plan asks for the same value, so plans of
         // different shapes never shrink each other's limit and launches need no further set-up
         CU(allow_max_smem(kern, P->smem_optin));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, (kW2 + 1) * 32, P->k2_smem));
-    });
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, (W2c + 1) * 32, P->k2_smem));
+    }); });
     if (*occ < 1) return fail(VMAT_E_ARG, "transposed kernel does not fit on an SM with these options");
     return 0;
 }
@@ -490,7 +492,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     {
         int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V);
         T = (T + 63) / 64 * 64;
-        const int32_t W = kW2, HU = 8;
+        const int32_t W = P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = 8;
         P->W2 = W;
         P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
         P->nstages2 = P->opt.reserved[1] > 0 ? std::max(2, std::min(16, P->opt.reserved[1])) : 8;
@@ -724,8 +726,10 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a2.fpart = P->fpart.as<double>(); a2.fblock = P->fblock.as<double>(); a2.nfpart = P->nslices1;
         a2.trace = P->tracing ? P->trace.as<unsigned long long>() + (size_t)P->k1_grid * kTraceSlots : nullptr;
         DISPATCH_IW(IW, {   // always launched (even with an empty task list): it also folds the objective partials
-            auto kern2 = k2_beamlet_grad<VT, AT, kW2, IW>;
-            CU(launch_pdl(kern2, P->k2_grid, (kW2 + 1) * 32, P->k2_smem, st, P->pdl, a2));
+            DISPATCH_W2(W2c, {
+                auto kern2 = k2_beamlet_grad<VT, AT, W2c, IW>;
+                CU(launch_pdl(kern2, P->k2_grid, (W2c + 1) * 32, P->k2_smem, st, P->pdl, a2));
+            });
         });
     }
     if (ev) CU(cudaEventRecord(ev[2], st));
