@@ -39,12 +39,22 @@ typedef struct vmat_options {
     int32_t store_dtype;    /* VMAT_F32 | VMAT_BF16 | VMAT_F64: how D is kept in HBM          */
     int32_t acc_dtype;      /* VMAT_F32 | VMAT_F64: accumulation, and dtype of x, dose, vg     */
     int32_t tile_voxels;    /* voxels per column tile of the transposed layout (0 = default)   */
-    int32_t k1_threads;     /* threads per CTA of the dose kernel (0 = default)                */
+    int32_t k1_threads;     /* dose kernel: 1..511 -> 4 consumer warps per CTA, else 16 (default) */
     int32_t k2_threads;     /* transposed kernel: >= 512 -> 16 consumer warps per CTA, >= 256 -> 8, else 4 (default) */
-    int32_t k2_tasks;       /* CTAs of the transposed kernel (0 = default)                     */
-    int32_t use_graph;      /* 1: replay the three-kernel evaluation as one CUDA graph         */
-    int32_t reserved[9];    /* [5]: 4 forces int32 column indices (default: uint16 whenever they fit) */
-                            /* [2]: chunk cap per slice (longer rows get several lanes); 0 = default */
+    int32_t k2_tasks;       /* CTAs of the transposed kernel (0 = SM count x resident CTAs per SM) */
+    int32_t use_graph;      /* 1: capture the evaluation as a CUDA graph (used by vmat_eval when y
+                               cannot travel in the launch parameters)                          */
+    int32_t reserved[9];    /* tuning, 0 = default everywhere:
+                               [0] ring stages of the dose kernel      [1] ring stages of the transposed kernel
+                               [2] chunk cap of the dose layout        [7] chunk cap of the transposed layout
+                                   (chunks of 4 nonzeros per lane and super-slice; longer rows get more lanes)
+                               [3] 1 = no programmatic dependent launch
+                               [4] host-buffer path of vmat_eval, bits: 1 y read from mapped host memory,
+                                   2 results + completion tags written to mapped host memory,
+                                   4 y inside the launch parameters (default), 8 none (copy nodes)
+                               [5] 4 = int32 column indices (default: uint16 whenever they fit)
+                               [6] stages before a super-slice's end at which the dose kernel claims the next
+                               [8] unused */
 } vmat_options_t;
 
 /* Library / build identification. */
