@@ -265,7 +265,8 @@ constexpr int kChunkCapK1 = 48, kChunkCapK2 = 24;
 // voxels per tile of the transposed layout: larger tiles mean longer beamlet segments (less padding)
 // and fewer tile partials for K3, but one CTA less per SM.  Measured: config 2 (300k voxels) 65.2 us
 // with 4096 against 66.2 us with 6144; config 3 (1M) 273 against 268 us; config 4 (4M) 434 against 446 evals/s
-static int32_t default_tile_voxels(int64_t V) { return V > 500000 ? 6144 : 4096; }
+// The same tile bytes with double accumulation (half the voxels): config 2 93 -> 88 us, config 3 344 -> 330 us.
+static int32_t default_tile_voxels(int64_t V, size_t acc_size) { return (int32_t)((V > 500000 ? 6144 : 4096) * 4 / acc_size); }
 constexpr int kClaimLeadDefault = 8;
 
 // dynamic shared memory limit of a kernel = what the device allows next to the kernel's static part
@@ -375,7 +376,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaDeviceGetAttribute(&P->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaStream_t st = P->stream;
     {   // index width: uint16 when every stored index fits (x index < B; K2 indices are tile-local, < T)
-        const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V);
+        const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
         const bool fits16 = B <= 65536 && ((T0 + 63) / 64 * 64) <= 65536;
         P->iw = (P->opt.reserved[5] == 4 || !fits16) ? 4 : 2;      // reserved[5] = 4 forces int32 indices
     }
@@ -490,7 +491,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
     // ---- K2 layout: column tiles of T voxels; per tile, beamlet segments sorted by length
     {
-        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V);
+        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
         T = (T + 63) / 64 * 64;
         const int32_t W = P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = 8;
         P->W2 = W;
