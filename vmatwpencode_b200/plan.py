@@ -36,10 +36,11 @@ class _DeviceArray:
 class DosePlan:
     """One rank's plan: D (its voxel slab) x all beamlets, penalty tables, aperture weights."""
 
-    def __init__(self, D, beam_ptr, thr, over, under, device: int = 0, store: str = "f32",
-                 acc: str = "f32", tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0,
-                 k2_tasks: int = 0, use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0, index_bytes: int = 0,
-                 k1_stages: int = 0, k2_stages: int = 0, claim_lead: int = 0, k2_chunk_cap: int = 0):
+    def __init__(self, D, beam_ptr, thr, over, under, device: int = 0, store: str = "f32", acc: str = "f32",
+                 tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0, k2_tasks: int = 0,
+                 use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0,
+                 index_bytes: int = 0, k1_stages: int = 0, k2_stages: int = 0, claim_lead: int = 0,
+                 k2_chunk_cap: int = 0):
         """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
         {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
         lib = _lib.load()
