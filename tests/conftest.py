@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the reference's own code (np.matrix, np.in1d) and the np.matrix the drop-in API returns, like it
+    config.addinivalue_line("filterwarnings", "ignore:the matrix subclass:PendingDeprecationWarning")
+    config.addinivalue_line("filterwarnings", "ignore:`in1d` is deprecated:DeprecationWarning")
 
 
 def pytest_collection_modifyitems(config, items):
