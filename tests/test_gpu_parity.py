@@ -514,6 +514,33 @@ def test_kmedoid_costs_tree_path_and_voxel_points():
         assert cost[c] == part[0]
 
 
+def test_kmedoid_voxel_subsample_drives_the_greedy_loop():
+    """BASELINE.json configs[2] in small: pick voxels by greedy k-medoid insertion over their grid
+    coordinates (distance pass on the GPU), restrict the case to them, run the greedy loop on the
+    subsample: same aperture sequence as the oracle on the same subsample; the sample is spatially
+    even (no two sampled voxels adjacent while unsampled regions remain far larger)."""
+    from vmatwpencode_b200 import kmedoids as km
+    from vmatwpencode_b200.synth import voxel_coordinates, subsample_case
+    case = make_case(V=6000, nb=10, M=4, N=6, density=0.03, seed=91, gastep=10)
+    xyz = voxel_coordinates(case.V, case.M)
+    rows = km.sample_voxels(xyz, 400, start=17)
+    assert len(set(rows)) == 400 and rows[0] == 17
+    # greedy insertion == brute-force argmin of the summed nearest-medoid distance, step by step
+    cur = np.sqrt(((xyz - xyz[17]) ** 2).sum(axis=1))
+    for nxt in rows[1:4]:
+        cost = np.array([np.minimum(cur, np.sqrt(((xyz - xyz[c]) ** 2).sum(axis=1))).sum() for c in range(case.V)])
+        cost[[r for r in rows[:rows.index(nxt)]]] = np.inf
+        assert abs(cost[nxt] - cost.min()) <= 1e-9 * cost.min()
+        cur = np.minimum(cur, np.sqrt(((xyz - xyz[nxt]) ** 2).sum(axis=1)))
+    sub = subsample_case(case, rows)
+    assert sub.V == 400 and sub.D.shape == (400, case.B)
+    want = O.col_gen(O.OracleState(sub), C=0.01, kappasize=5, max_iter=5, clean=True)
+    data = vl.bind(sub, store="f32", acc="f64")
+    vl.colGen(0.01, False, 5, max_iter=5)
+    assert len(want) > 0 and [(h["idx"], h["l"], h["r"]) for h in data.history] == [(h["idx"], h["l"], h["r"]) for h in want]
+    data.plan.close()
+
+
 @pytest.mark.parametrize("acc", ["f64", "f32"])
 def test_dvh_on_device_matches_oracle(acc):
     """printresults' dose-volume histograms from the GPU-resident dose: integer bin counts, so

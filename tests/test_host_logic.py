@@ -188,3 +188,23 @@ def test_quad_helpers_vs_oracle():
     b = O.quad_helpers(fd, regions, nv, prio)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_subsample_case_keeps_rows_and_rescales_weights():
+    from vmatwpencode_b200.synth import subsample_case, voxel_coordinates
+    case = make_case(V=900, nb=4, M=3, N=4, density=0.05, seed=12)
+    xyz = voxel_coordinates(case.V, case.M)
+    assert xyz.shape == (900, 3) and len({tuple(p) for p in xyz}) == 900 and np.array_equal(xyz, np.round(xyz))
+    same = subsample_case(case, np.arange(case.V)[::-1])          # every voxel, any order given
+    assert np.array_equal(same.over, case.over) and np.array_equal(same.under, case.under)
+    assert (same.D != case.D.tocsr()).nnz == 0
+    rows = np.arange(0, case.V, 3)
+    sub = subsample_case(case, rows)
+    assert sub.V == len(rows) and np.array_equal(sub.thr, case.thr[rows])
+    D = case.D.tocsr()
+    assert (sub.D != D[rows]).nnz == 0
+    for s in np.unique(case.struct_id):
+        full, kept = (case.struct_id == s).sum(), (sub.struct_id == s).sum()
+        if kept:
+            sel = sub.struct_id == s
+            assert np.allclose(sub.over[sel], case.over[rows][sel] * full / kept, rtol=1e-15)

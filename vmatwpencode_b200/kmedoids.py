@@ -86,3 +86,10 @@ def givemewholelist(kappa, ba, device: int = 0, group=None, limit=None):
     while len(kappa) < stop:
         kappa = insertnewelement(kappa, ba, device, state, group)
     return kappa
+
+
+def sample_voxels(coords, k: int, start: int = 0, device: int = 0, group=None):
+    """The first k medoids of the greedy insertion over voxel coordinates (n, 3), starting from voxel
+    `start`: a spatially even voxel subsample.  With a torch.distributed `group` every rank prices the
+    candidates against its share of the voxels and the costs are all-reduced."""
+    return givemewholelist([int(start)], np.asarray(coords, dtype=np.float64), device=device, group=group, limit=k)

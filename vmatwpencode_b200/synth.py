@@ -117,6 +117,31 @@ def phantom_grid(V: int, M: int):
     return nxy, nxy, nz
 
 
+def voxel_coordinates(V: int, M: int) -> np.ndarray:
+    """(V, 3) grid indices of the phantom's voxels (integers, so distances between them are exact in
+    float64): the point set of the k-medoid voxel subsampling."""
+    nx, ny, _ = phantom_grid(V, M)
+    v = np.arange(V, dtype=np.int64)
+    return np.stack([v % nx, (v // nx) % ny, v // (nx * ny)], axis=1).astype(np.float64)
+
+
+def subsample_case(case: "Case", rows) -> "Case":
+    """The case restricted to the voxels `rows` (ascending order kept): their rows of D and their
+    penalty entries, the weights rescaled per structure by (voxels in structure) / (sampled voxels in
+    structure) so that objective values stay comparable with the full case.  (The reference samples
+    control points, not voxels; this is the voxel subsampling BASELINE.json's third configuration names.)"""
+    rows = np.sort(np.asarray(rows, dtype=np.int64))
+    sid = np.asarray(case.struct_id)
+    full = np.bincount(sid, minlength=256).astype(np.float64)
+    kept = np.bincount(sid[rows], minlength=256).astype(np.float64)
+    scale = np.divide(full, kept, out=np.ones(256), where=kept > 0)[sid[rows]]
+    D = case.D.tocsr()[rows]
+    return Case(V=len(rows), nb=case.nb, M=case.M, N=case.N, beam_ptr=case.beam_ptr, angles=list(case.angles),
+                xinter=case.xinter, yinter=case.yinter, xdirection=case.xdirection, ydirection=case.ydirection,
+                D=D, thr=case.thr[rows].copy(), over=case.over[rows] * scale, under=case.under[rows] * scale,
+                struct_id=sid[rows].copy(), val_dtype=case.val_dtype, meta=dict(case.meta, subsampled_from=case.V))
+
+
 def structures(V: int, M: int, device="cpu", rich: bool = False):
     """struct_id[V] plus the per-structure (threshold, over, under) table.
 
