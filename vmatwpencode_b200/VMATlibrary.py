@@ -98,8 +98,8 @@ class apertureList:
 
 class _LazyDZdK:
     """Stand-in for the reference's dense V x numbeams ``dZdK`` (:246,251).  It is never
-    formed on the GPU path (11.5 GB at 4M voxels x 360 control points); ``toarray()`` builds
-    it on demand from the beamlet weights for anyone who really wants it."""
+    formed on the GPU path (11.5 GB at 4M voxels x 360 control points): aperturegradient comes
+    from the beamlet gradient instead, and asking for the dense matrix is an error."""
 
     def __init__(self, owner):
         self._owner = owner
@@ -199,8 +199,11 @@ class vmat_class:
                 self.plan.set_aperture(i, None, None)
                 del self._uploaded[i]
         for i in self.caligraphicC.loc:
-            key = (id(self.openApertureMaps[i]), id(self.diagmakers[i]), id(self.strengths[i]))
-            if self._uploaded.get(i) == key:
+            # what was uploaded is remembered by object (holding the references, so an address cannot
+            # be recycled for new arrays): colGen assigns fresh objects whenever an aperture changes
+            key = (self.openApertureMaps[i], self.diagmakers[i], self.strengths[i])
+            old = self._uploaded.get(i)
+            if old is not None and all(a is b for a, b in zip(old, key)):
                 continue
             nbl = int(self.beam_ptr[i + 1] - self.beam_ptr[i])
             w_dose = np.zeros(nbl)
