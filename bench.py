@@ -300,7 +300,10 @@ def main():
                              % (nnz_local * (sv + info["index_bytes"]) // 1_000_000),
                        "scale": args.scale},
             "e2e": {"value": K / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": case.nb * 8,
-                    "d2h_bytes_per_step": (case.nb + 1) * 8, "ms_per_step": 1e3 * e2e_s / K},
+                    "d2h_bytes_per_step": (case.nb + 1) * 8, "ms_per_step": 1e3 * e2e_s / K,
+                    "how": "vmat_eval(y, &f, g) per step with host buffers: y (nb f64) goes to the device inside the "
+                           "dose kernel's launch parameters (a 1.4 KB H2D copy when nb > 384), f and g (nb+1 f64) come "
+                           "back with one D2H copy into pinned memory and a stream synchronisation"},
             "gpu_launches": (info["launches_per_eval"] + (1 if world > 1 else 0)) * K,
             "clocks": clocks,
             "check": {"f": f_res, "g_norm": float(np.linalg.norm(g_res))},
