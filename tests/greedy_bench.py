@@ -4,7 +4,8 @@
 the best aperture, re-optimise with scipy L-BFGS-B) on the GPU path - with the sparse kernels
 only and with solveRMC's dense column cache - against the CPU oracle running the same loop
 (reference arithmetic restated; 'literal' is the reference's own operation order).  The aperture
-sequences must be identical.  Prints one JSON line."""
+sequences must be identical.  Prints one JSON line.  (Lives under tests/ because it runs the
+oracle as the CPU side of the comparison; pytest does not collect it.)"""
 import argparse
 import json
 import os
