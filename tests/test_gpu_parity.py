@@ -142,7 +142,9 @@ def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol):
                                   dict(k1_threads=128), dict(k2_threads=128, k2_tasks=1000), dict(pdl=False), dict(host_path=3), dict(host_path=4), dict(host_path=6),
                                   dict(chunk_cap=2), dict(chunk_cap=1000), dict(index_bytes=4), dict(tile_voxels=64, chunk_cap=1),
                                   dict(k2_chunk_cap=1, k2_tasks=5), dict(k2_chunk_cap=3, tile_voxels=128), dict(claim_lead=1), dict(claim_lead=100),
-                                  dict(k2_threads=256, k2_stages=6), dict(k2_threads=512, k2_stages=4, tile_voxels=256)])
+                                  dict(k2_threads=256, k2_stages=6), dict(k2_threads=512, k2_stages=4, tile_voxels=256),
+                                  dict(index_bytes=1), dict(index_bytes=1, chunk_cap=2, k2_chunk_cap=3), dict(index_bytes=1, tile_voxels=64, k2_tasks=7),
+                                  dict(index_bytes=1, k1_threads=128, k2_threads=256)])
 def test_plan_options_do_not_change_results(opts):
     case = make_case(V=9000, nb=8, M=4, N=6, density=0.02, seed=71)
     st = O.OracleState(case)
@@ -157,6 +159,50 @@ def test_plan_options_do_not_change_results(opts):
     plan.eval_async()
     f2, g2 = plan.fetch_result()
     assert f2 == f and np.array_equal(g2, g)
+    plan.close()
+
+
+@pytest.mark.parametrize("store,acc,tol", [("f32", "f64", 1e-11), ("f32", "f32", 1e-5), ("f64", "f64", 1e-11), ("bf16", "f32", 1e-5)])
+def test_byte_delta_indices_bridge_large_gaps(store, acc, tol):
+    """index_bytes=1 stores column indices as byte deltas.  A matrix far too sparse for that (70 000
+    beamlets, ~30 nonzeros per voxel row: gaps in the thousands, bridged by several zero entries
+    each; also more beamlets than 16 bits address) still evaluates to the oracle's numbers."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(21)
+    V, nb, per = 3000, 10, 7000
+    B = nb * per
+    nnz = 90_000
+    rows, cols = rng.integers(0, V, nnz), rng.integers(0, B, nnz)
+    rows[:200] = 5; cols[:200] = np.arange(200) * 2 + 11            # one long dense-ish row: no bridges
+    cols[200:260] = rng.choice([0, 255, 256, 510, 511, 512, 69_999], 60); rows[200:260] = np.arange(60) % 3 + 7   # exact gap edges
+    vals = np.float32(0.05 + rng.random(nnz)).astype(np.float64)
+    if store == "bf16":
+        import torch
+        vals = torch.tensor(vals, dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
+    D = sp.csr_matrix((vals, (rows, cols)), shape=(V, B))
+    D.sum_duplicates()
+    if store == "bf16":
+        import torch
+        D.data = torch.tensor(D.data, dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
+    else:
+        D.data = np.float32(D.data).astype(np.float64)
+    beam_ptr = np.arange(nb + 1, dtype=np.int32) * per
+    thr = rng.random(V); over = rng.random(V) / V; under = rng.random(V) / V
+    y = rng.random(nb) * 2
+    w_dose = (rng.random(B) > 0.5) * rng.random(B); w_grad = (rng.random(B) > 0.5) * 1.0
+    x = np.repeat(y, per) * w_dose
+    d0 = D @ x
+    o, u = np.maximum(d0 - thr, 0), np.maximum(thr - d0, 0)
+    f0 = float((over * o * o + under * u * u).sum())
+    vg0 = 4 * (over * o - under * u)
+    gb0 = D.T @ vg0
+    g0 = (gb0 * w_grad).reshape(nb, per).sum(axis=1)
+    plan = DosePlan(D, beam_ptr, thr, over, under, store=store, acc=acc, index_bytes=1)
+    assert plan.info()["index_bytes"] == 1
+    plan.set_weights(w_dose, w_grad)
+    f, g = plan.eval(y)
+    assert abs(f - f0) <= tol * abs(f0) and relerr(g, g0) <= tol
+    assert relerr(plan.dose(), d0) <= tol and relerr(plan.beamlet_grad(), gb0) <= tol
     plan.close()
 
 

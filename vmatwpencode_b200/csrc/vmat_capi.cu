@@ -135,7 +135,7 @@ extern "C" void vmat_default_options(vmat_options_t* o) {
         default: return fail(VMAT_E_ARG, "bad store dtype");                 \
     }
 #define DISPATCH_IW(IW, ...)                                                 \
-    if (P->iw == 2) { constexpr int IW = 2; __VA_ARGS__; } else { constexpr int IW = 4; __VA_ARGS__; }
+    if (P->iw == 2) { constexpr int IW = 2; __VA_ARGS__; } else if (P->iw == 1) { constexpr int IW = 1; __VA_ARGS__; } else { constexpr int IW = 4; __VA_ARGS__; }
 #define DISPATCH_ACC(dt, AT, ...)                                            \
     switch (dt) {                                                            \
         case VMAT_F32: { using AT = float; __VA_ARGS__; break; }             \
@@ -215,7 +215,7 @@ struct StreamDesc {
     std::vector<int32_t> seg_len, seg_cb, rows, ss_tile;
     std::vector<int64_t> ss_cost;                 // ring stages (header + chunks) of each super-slice
     std::vector<double> t_s, o_s, u_s;            // penalty tables in slot order (K1 only)
-    struct Item { int32_t len, id; int64_t start; };
+    struct Item { int32_t len, id; int64_t start; int32_t src_len; };   // len: slots the row needs (nonzeros + bridge entries), src_len: nonzeros
     // `items` sorted by len descending; appends the super-slices of one group (all voxels / one tile)
     void add_group(const std::vector<Item>& items, int32_t colbase, int32_t tile,
                    const double* thr, const double* over, const double* under) {
@@ -238,7 +238,7 @@ struct StreamDesc {
                 const size_t w = r / rows_per_slice, q = r % rows_per_slice;
                 for (int part = 0; part < tpr; ++part) {
                     const size_t slot = base_slot + w * 32 + q * tpr + part;
-                    seg_start[slot] = it.start; seg_len[slot] = it.len; seg_cb[slot] = colbase;
+                    seg_start[slot] = it.start; seg_len[slot] = it.src_len; seg_cb[slot] = colbase;
                     if (part == 0) {
                         rows[slot] = it.id;
                         if (thr) { t_s[slot] = thr[it.id]; o_s[slot] = over[it.id]; u_s[slot] = under[it.id]; }
@@ -378,12 +378,13 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     {   // index width: uint16 when every stored index fits (x index < B; K2 indices are tile-local, < T)
         const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
         const bool fits16 = B <= 65536 && ((T0 + 63) / 64 * 64) <= 65536;
-        P->iw = (P->opt.reserved[5] == 4 || !fits16) ? 4 : 2;      // reserved[5] = 4 forces int32 indices
+        // reserved[5]: 4 forces int32 indices, 1 selects byte deltas (any B: a lane's start index is a u32 in the header)
+        P->iw = P->opt.reserved[5] == 1 ? 1 : (P->opt.reserved[5] == 4 || !fits16) ? 4 : 2;
     }
     {   // dose-kernel CTA shape
         const size_t as0 = P->acc_size;
         const size_t xy = (((size_t)B * as0 + 127) & ~(size_t)127) + (((size_t)nb * 8 + 127) & ~(size_t)127);
-        const int hu1 = 8 + 3 * (32 * (int)as0 / 16);
+        const int hu1 = 8 + 3 * (32 * (int)as0 / 16) + header_base_units(P->iw);
         const size_t stage4 = (size_t)4 * std::max<int>(store_units(P->opt.store_dtype, P->iw), hu1) * 16;
         const bool fits2 = 2 * (xy + 8 * stage4 + 2048) <= (size_t)P->smem_optin;
         // measured on config 2: one 16-warp CTA per SM (48.8 us) beats three 4-warp CTAs (52.0 us)
@@ -411,12 +412,15 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     const int64_t* d_brow = browptr;
     if (location == VMAT_HOST) {
         CU(up_vcol.alloc(nnz * 4)); CU(up_vval.alloc(nnz * sv));
-        CU(cudaMemcpy(up_vcol.p, vcol, nnz * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(up_vval.p, vval, nnz * sv, cudaMemcpyHostToDevice));
+        // on the plan's stream: a synchronous cudaMemcpy from pageable memory may return while the DMA is
+        // still in flight, and the (non-blocking) plan stream is not ordered behind the default stream
+        CU(cudaMemcpyAsync(up_vcol.p, vcol, nnz * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(up_vval.p, vval, nnz * sv, cudaMemcpyHostToDevice, st));
         d_vcol = up_vcol.as<int32_t>(); d_vval = up_vval.p;
     }
 
     DevBuf csr_flag, up_vrow;
+    std::vector<int32_t> vpads;            // per voxel row (byte-delta layout only)
     CU(csr_flag.alloc(4)); CU(cudaMemsetAsync(csr_flag.p, 0, 4, st));
     auto check_csr = [&](int64_t nrows, int64_t ncols, int sorted, const int64_t* d_rowptr, const int32_t* d_col,
                          const char* what) -> int {
@@ -434,10 +438,19 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const int64_t* d_vrow = vrowptr;
         if (location == VMAT_HOST) {
             CU(up_vrow.alloc((V + 1) * 8));
-            CU(cudaMemcpy(up_vrow.p, vrowptr, (V + 1) * 8, cudaMemcpyHostToDevice));
+            CU(cudaMemcpyAsync(up_vrow.p, vrowptr, (V + 1) * 8, cudaMemcpyHostToDevice, st));
             d_vrow = up_vrow.as<int64_t>();
         }
-        if (int rc = check_csr(V, B, 0, d_vrow, d_vcol, "voxel-major")) return rc;
+        if (int rc = check_csr(V, B, P->iw == 1 ? 1 : 0, d_vrow, d_vcol, "voxel-major")) return rc;
+        if (P->iw == 1 && nnz > 0) {      // byte deltas: slots a row needs = nonzeros + bridge entries over gaps > 255
+            DevBuf d_pads;
+            CU(d_pads.alloc(V * 4));
+            k_count_pads<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, d_vrow, d_vcol, d_pads.as<int32_t>());
+            CU(cudaGetLastError());
+            vpads.resize(V);
+            CU(cudaMemcpyAsync(vpads.data(), d_pads.p, V * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
         up_vrow.alloc(0);
     }
 
@@ -445,22 +458,23 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     const int units = store_units(P->opt.store_dtype, P->iw);
     const int es = (int)P->acc_size;
     {
-        std::vector<int32_t> order(V);
+        std::vector<int32_t> order(V), slots(V);      // slots: entries the row occupies in the stream
+        for (int64_t v = 0; v < V; ++v) slots[v] = (int32_t)(h_vrow[v + 1] - h_vrow[v]) + (vpads.empty() ? 0 : vpads[v]);
         {
             int64_t maxlen = 0;
-            for (int64_t v = 0; v < V; ++v) maxlen = std::max(maxlen, h_vrow[v + 1] - h_vrow[v]);
+            for (int64_t v = 0; v < V; ++v) maxlen = std::max<int64_t>(maxlen, slots[v]);
             std::vector<int64_t> cnt(maxlen + 2, 0);
-            for (int64_t v = 0; v < V; ++v) cnt[maxlen - (h_vrow[v + 1] - h_vrow[v]) + 1]++;
+            for (int64_t v = 0; v < V; ++v) cnt[maxlen - slots[v] + 1]++;
             for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
-            for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - (h_vrow[v + 1] - h_vrow[v])]++] = (int32_t)v;
+            for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - slots[v]]++] = (int32_t)v;
         }
-        const int32_t W = P->W1, HU = 8 + 3 * (32 * es / 16);
+        const int32_t W = P->W1, HU = 8 + 3 * (32 * es / 16) + header_base_units(P->iw);
         const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2] : kChunkCapK1;
         StreamDesc sd{W, HU, units, cap};
         std::vector<StreamDesc::Item> items(V);
         for (int64_t pos = 0; pos < V; ++pos) {
             const int32_t v = order[pos];
-            items[pos] = StreamDesc::Item{(int32_t)(h_vrow[v + 1] - h_vrow[v]), v, h_vrow[v]};
+            items[pos] = StreamDesc::Item{slots[v], v, h_vrow[v], (int32_t)(h_vrow[v + 1] - h_vrow[v])};
         }
         sd.add_group(items, 0, 0, thr, over, under);
         const int32_t nss = (int32_t)sd.ss_tpr.size();
@@ -482,9 +496,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
     if (location == VMAT_HOST) {
         CU(up_bcol.alloc(nnz * 4)); CU(up_bval.alloc(nnz * sv)); CU(up_brow.alloc((B + 1) * 8));
-        CU(cudaMemcpy(up_bcol.p, bcol, nnz * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(up_bval.p, bval, nnz * sv, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(up_brow.p, browptr, (B + 1) * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(up_bcol.p, bcol, nnz * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(up_bval.p, bval, nnz * sv, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(up_brow.p, browptr, (B + 1) * 8, cudaMemcpyHostToDevice, st));
         d_bcol = up_bcol.as<int32_t>(); d_bval = up_bval.p; d_brow = up_brow.as<int64_t>();
     }
     if (int rc = check_csr(B, V, 1, d_brow, d_bcol, "beamlet-major")) return rc;
@@ -493,7 +507,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     {
         int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
         T = (T + 63) / 64 * 64;
-        const int32_t W = P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = 8;
+        const int32_t W = P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = header_units_k2(P->iw);
         P->W2 = W;
         P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
         P->nstages2 = P->opt.reserved[1] > 0 ? std::max(2, std::min(16, P->opt.reserved[1])) : 8;
@@ -509,6 +523,17 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         CU(cudaGetLastError());
         std::vector<int64_t> segstart(nseg);
         CU(cudaMemcpyAsync(segstart.data(), d_seg.p, nseg * 8, cudaMemcpyDeviceToHost, st));
+        std::vector<int32_t> spads;            // per (beamlet, tile) segment (byte-delta layout only)
+        if (P->iw == 1 && nnz > 0) {
+            DevBuf d_pads;
+            CU(d_pads.alloc(nseg * 4));
+            CU(cudaMemsetAsync(d_pads.p, 0, nseg * 4, st));
+            k_count_pads<<<(unsigned)((nseg - 1 + 255) / 256), 256, 0, st>>>(nseg - 1, d_seg.as<int64_t>(), d_bcol, d_pads.as<int32_t>());
+            CU(cudaGetLastError());
+            spads.resize(nseg);
+            CU(cudaMemcpyAsync(spads.data(), d_pads.p, nseg * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
         CU(cudaStreamSynchronize(st));
         d_seg.alloc(0);
 
@@ -519,7 +544,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             items.clear();
             for (int32_t b = 0; b < (int32_t)B; ++b) {
                 const int64_t s0 = segstart[(int64_t)b * (nt + 1) + t], s1 = segstart[(int64_t)b * (nt + 1) + t + 1];
-                if (s1 > s0) items.push_back(StreamDesc::Item{(int32_t)(s1 - s0), b, s0});
+                if (s1 > s0) items.push_back(StreamDesc::Item{(int32_t)(s1 - s0) + (spads.empty() ? 0 : spads[(int64_t)b * (nt + 1) + t]), b, s0, (int32_t)(s1 - s0)});
             }
             std::stable_sort(items.begin(), items.end(),
                              [](const StreamDesc::Item& a, const StreamDesc::Item& b) { return a.len > b.len; });
@@ -792,15 +817,17 @@ extern "C" int vmat_set_aperture(vmat_plan_t* P, int32_t beam, const double* w_d
         if (as == 4) {
             std::vector<float> tmp(n);
             for (int k = 0; k < n; ++k) tmp[k] = (float)w_dose[k];
-            CU(cudaMemcpy(P->w_dose.as<char>() + (size_t)lo * 4, tmp.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpyAsync(P->w_dose.as<char>() + (size_t)lo * 4, tmp.data(), (size_t)n * 4, cudaMemcpyHostToDevice, P->stream));
+            CU(cudaStreamSynchronize(P->stream));        // tmp goes out of scope
         } else {
-            CU(cudaMemcpy(P->w_dose.as<char>() + (size_t)lo * 8, w_dose, (size_t)n * 8, cudaMemcpyHostToDevice));
+            CU(cudaMemcpyAsync(P->w_dose.as<char>() + (size_t)lo * 8, w_dose, (size_t)n * 8, cudaMemcpyHostToDevice, P->stream));
         }
     } else {
-        CU(cudaMemset(P->w_dose.as<char>() + (size_t)lo * as, 0, (size_t)n * as));
+        CU(cudaMemsetAsync(P->w_dose.as<char>() + (size_t)lo * as, 0, (size_t)n * as, P->stream));
     }
-    if (w_grad) CU(cudaMemcpy(P->w_grad.as<double>() + lo, w_grad, (size_t)n * 8, cudaMemcpyHostToDevice));
-    else CU(cudaMemset(P->w_grad.as<double>() + lo, 0, (size_t)n * 8));
+    if (w_grad) CU(cudaMemcpyAsync(P->w_grad.as<double>() + lo, w_grad, (size_t)n * 8, cudaMemcpyHostToDevice, P->stream));
+    else CU(cudaMemsetAsync(P->w_grad.as<double>() + lo, 0, (size_t)n * 8, P->stream));
+    CU(cudaStreamSynchronize(P->stream));      // the caller's buffers may go away; later launches see the new weights
     return VMAT_OK;
 }
 
@@ -1181,7 +1208,7 @@ extern "C" int vmat_rmp_eval(vmat_plan_t* P, const double* y, double* f, double*
     for (int32_t k = 0; k < ncols; ++k) yk[k] = y[P->rmp_cols[k]];
     std::memcpy(P->h_res, yk.data(), std::min<size_t>(ncols, P->nb + 1) * 8);       // pinned staging
     if ((size_t)ncols <= (size_t)P->nb + 1) CU(cudaMemcpyAsync(P->rmp_yk.p, P->h_res, ncols * 8, cudaMemcpyHostToDevice, P->stream));
-    else CU(cudaMemcpy(P->rmp_yk.p, yk.data(), ncols * 8, cudaMemcpyHostToDevice));
+    else { CU(cudaMemcpyAsync(P->rmp_yk.p, yk.data(), ncols * 8, cudaMemcpyHostToDevice, P->stream)); CU(cudaStreamSynchronize(P->stream)); }
     CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
     DISPATCH_ACC(P->opt.acc_dtype, AT, { if (int rc = rmp_eval_t<AT>(P)) return rc; });
     CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream));
@@ -1206,7 +1233,7 @@ extern "C" int vmat_dose_max(vmat_plan_t* P, double* out) {
     if (!P || !out) return fail(VMAT_E_ARG, "null");
     CU(cudaSetDevice(P->device)); CU(cudaDeviceSynchronize());
     DevBuf m;
-    CU(m.alloc(8)); CU(cudaMemset(m.p, 0, 8));
+    CU(m.alloc(8)); CU(cudaMemsetAsync(m.p, 0, 8, P->stream));
     DISPATCH_ACC(P->opt.acc_dtype, AT, {
         k7_dose_max<AT><<<P->sm_count * 4, 256, 0, P->stream>>>(P->V, P->d.as<AT>(), m.as<unsigned long long>());
     });
@@ -1226,9 +1253,9 @@ extern "C" int vmat_dvh_histogram(vmat_plan_t* P, const uint64_t* full_mask, int
     DevBuf dm, de, dh;
     const size_t nh = (size_t)nstructs * (nedges - 1);
     CU(dm.alloc(P->V * 8)); CU(de.alloc((size_t)nedges * 8)); CU(dh.alloc(nh * 8));
-    CU(cudaMemcpy(dm.p, full_mask, P->V * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(de.p, edges, (size_t)nedges * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemset(dh.p, 0, nh * 8));
+    CU(cudaMemcpyAsync(dm.p, full_mask, P->V * 8, cudaMemcpyHostToDevice, P->stream));
+    CU(cudaMemcpyAsync(de.p, edges, (size_t)nedges * 8, cudaMemcpyHostToDevice, P->stream));
+    CU(cudaMemsetAsync(dh.p, 0, nh * 8, P->stream));
     DISPATCH_ACC(P->opt.acc_dtype, AT, {
         k7_dvh_hist<AT><<<P->sm_count * 4, 256, 0, P->stream>>>(P->V, P->d.as<AT>(), dm.as<unsigned long long>(), nstructs,
                                                                  de.as<double>(), nedges, dh.as<unsigned long long>());

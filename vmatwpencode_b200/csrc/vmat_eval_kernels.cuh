@@ -29,20 +29,32 @@ constexpr int kStageLast = 2;       // last stage of the super-slice: run the ep
 struct StageInfo { int32_t ss, flags, tile, tpr; };
 
 // header units (16 B) per warp: 32 row ids (+ thr, over, under as AT for K1)
-template <typename AT> __host__ __device__ constexpr int header_units_k1() { return 8 + 3 * (32 * (int)sizeof(AT) / 16); }
-constexpr int kHeaderUnitsK2 = 8;
+// (+ with IW == 1 the 32 lanes' start indices as u32: the chunks then hold byte deltas)
+__host__ __device__ constexpr int header_base_units(int IW) { return IW == 1 ? 8 : 0; }
+template <typename AT> __host__ __device__ constexpr int header_units_k1(int IW) { return 8 + 3 * (32 * (int)sizeof(AT) / 16) + header_base_units(IW); }
+__host__ __device__ constexpr int header_units_k2(int IW) { return 8 + header_base_units(IW); }
 
 // one chunk of one warp, as it sits in a ring stage: 4 indices and 4 values per lane
 template <typename AT> struct ChunkRegs { uint32_t i[4]; AT v[4]; };
 
+// IW == 1: the index word holds four byte deltas; `cur` is the lane's running index (set from the
+// header's start index, advanced here).  Gaps of 256 or more were bridged with zero-valued entries
+// when the stream was built.
 template <typename VT, typename AT, int IW>
-__device__ __forceinline__ void chunk_load(const unsigned char* __restrict__ cp, int lane, ChunkRegs<AT>& c) {
+__device__ __forceinline__ void chunk_load(const unsigned char* __restrict__ cp, int lane, ChunkRegs<AT>& c, uint32_t& cur) {
     if constexpr (IW == 4) {
         const uint4 idx = *reinterpret_cast<const uint4*>(cp + lane * 16);
         c.i[0] = idx.x; c.i[1] = idx.y; c.i[2] = idx.z; c.i[3] = idx.w;
-    } else {
+    } else if constexpr (IW == 2) {
         const uint2 idx = *reinterpret_cast<const uint2*>(cp + lane * 8);
         c.i[0] = idx.x & 0xffffu; c.i[1] = idx.x >> 16; c.i[2] = idx.y & 0xffffu; c.i[3] = idx.y >> 16;
+    } else {
+        const uint32_t d = *reinterpret_cast<const uint32_t*>(cp + lane * 4);
+        c.i[0] = cur + (d & 0xffu);
+        c.i[1] = c.i[0] + ((d >> 8) & 0xffu);
+        c.i[2] = c.i[1] + ((d >> 16) & 0xffu);
+        c.i[3] = c.i[2] + (d >> 24);
+        cur = c.i[3];
     }
     const unsigned char* vp = cp + idx_units(IW) * 16;
     if constexpr (sizeof(VT) == 4) {
@@ -90,9 +102,9 @@ __device__ __forceinline__ void ring_push(unsigned char* ring, int stage_bytes, 
 template <typename VT, typename AT, int IW, typename Gather>
 __device__ __forceinline__ void consume_data(const unsigned char* ring, int SB, int warp_off, uint64_t* full,
                                              uint64_t* empty, const StageInfo* sinfo, RingPos& pos, int nst,
-                                             StageInfo& info, int lane, AT& acc, Gather g) {
+                                             StageInfo& info, int lane, AT& acc, uint32_t& cur, Gather g) {
     ChunkRegs<AT> A;
-    chunk_load<VT, AT, IW>(ring + (size_t)pos.stage * SB + warp_off, lane, A);
+    chunk_load<VT, AT, IW>(ring + (size_t)pos.stage * SB + warp_off, lane, A, cur);
     if (info.flags & kStageLast) {
         AT x0 = g(A.i[0]), x1 = g(A.i[1]), x2 = g(A.i[2]), x3 = g(A.i[3]);
         __syncwarp();
@@ -106,7 +118,7 @@ __device__ __forceinline__ void consume_data(const unsigned char* ring, int SB, 
     mbar_wait(&full[nx.stage], nx.phase);
     const StageInfo info2 = sinfo[nx.stage];
     ChunkRegs<AT> Bc;
-    chunk_load<VT, AT, IW>(ring + (size_t)nx.stage * SB + warp_off, lane, Bc);
+    chunk_load<VT, AT, IW>(ring + (size_t)nx.stage * SB + warp_off, lane, Bc, cur);
     AT x0 = g(A.i[0]), x1 = g(A.i[1]), x2 = g(A.i[2]), x3 = g(A.i[3]);
     AT y0 = g(Bc.i[0]), y1 = g(Bc.i[1]), y2 = g(Bc.i[2]), y3 = g(Bc.i[3]);
     __syncwarp();
@@ -191,7 +203,7 @@ __device__ __forceinline__ void store4(double* p, double a, double b, double c, 
 
 template <typename VT, typename AT, bool XS, int W, int IW>
 __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_constant__ K1Args<AT> a) {
-    constexpr int KU = chunk_units<VT, IW>(), HU = header_units_k1<AT>();
+    constexpr int KU = chunk_units<VT, IW>(), HU = header_units_k1<AT>(IW);
     constexpr int kMaxStages = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages];
@@ -322,6 +334,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     RingPos pos;
     AT acc = (AT)0, t = (AT)0, ov = (AT)0, un = (AT)0;
     int32_t row = -1;
+    uint32_t cur = 0;
     if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }    // outside the hot loop
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
@@ -333,11 +346,12 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
             t  = reinterpret_cast<const AT*>(hp + 128)[lane];
             ov = reinterpret_cast<const AT*>(hp + 128 + 32 * sizeof(AT))[lane];
             un = reinterpret_cast<const AT*>(hp + 128 + 64 * sizeof(AT))[lane];
+            if constexpr (IW == 1) cur = reinterpret_cast<const uint32_t*>(hp + (HU - 8) * 16)[lane];
             acc = (AT)0;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[pos.stage]);
         } else {
-            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, gather);
+            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, cur, gather);
         }
         if (info.flags & kStageLast) {
             for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // tpr lanes of a row
@@ -393,7 +407,7 @@ struct K2Args {
 
 template <typename VT, typename AT, int W, int IW>
 __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT> a) {
-    constexpr int KU = chunk_units<VT, IW>(), HU = kHeaderUnitsK2;
+    constexpr int KU = chunk_units<VT, IW>(), HU = header_units_k2(IW);
     constexpr int kMaxStages = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tilebar;
@@ -470,6 +484,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     RingPos pos;
     AT acc = (AT)0;
     int32_t row = -1;
+    uint32_t cur = 0;
     uint32_t tparity = 0;
     if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }    // outside the hot loop
     while (true) {
@@ -497,11 +512,12 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
                 tile_pending = false;
             }
             row = reinterpret_cast<const int32_t*>(sp + warp * (HU * 16))[lane];
+            if constexpr (IW == 1) cur = reinterpret_cast<const uint32_t*>(sp + warp * (HU * 16) + (HU - 8) * 16)[lane];
             acc = (AT)0;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[pos.stage]);
         } else {
-            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, gather);
+            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, cur, gather);
         }
         if (info.flags & kStageLast) {
             for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -756,6 +772,21 @@ __global__ void k_check_csr(int64_t nrows, int64_t ncols, int sorted, const int6
     if (bad) atomicOr(flag, bad);
 }
 
+// byte-delta layout: bridge entries a segment needs (one per 255 of every index gap above 255);
+// segment k spans CSR positions bounds[k*stride] .. bounds[k*stride + 1] (stride 1 = plain rows)
+__global__ void k_count_pads(int64_t nseg, const int64_t* __restrict__ bounds, const int32_t* __restrict__ col,
+                             int32_t* __restrict__ pads) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nseg) return;
+    const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+    int32_t n = 0;
+    for (int64_t p = p0 + 1; p < p1; ++p) {
+        const int32_t gap = col[p] - col[p - 1];
+        if (gap > 255) n += (gap - 1) / 255;
+    }
+    pads[k] = n;
+}
+
 // first position in each beamlet row whose voxel id is >= t*T, for t = 0..ntiles
 __global__ void k_segment_bounds(int32_t B, int32_t ntiles, int32_t T, const int64_t* __restrict__ browptr,
                                  const int32_t* __restrict__ bcol, int64_t* __restrict__ segstart) {
@@ -811,8 +842,60 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
     }
     const int64_t st = seg_start[slot];
     const int32_t len = seg_len[slot], cb = seg_colbase[slot];
-    const int tpr = ss_tpr[ss], part = lane % tpr;      // the row's nonzeros go round-robin (4 at a time) over its lanes
+    const int tpr = ss_tpr[ss], part = lane % tpr;
     uint4* data = sell + off + (int64_t)W * HU;
+    if constexpr (IW == 1) {
+        // Byte-delta indices.  The row is first expanded: a gap of 256 or more to the previous
+        // index is bridged by zero-valued entries 255 apart (k_count_pads sized the row for them).
+        // Lane `part` of the row then owns the expanded entries [part*4*nch, (part+1)*4*nch): a
+        // contiguous block, so in-lane deltas are plain neighbour gaps; its first entry's index goes
+        // into the header, its delta is 0.  Entries past the row's end repeat the last index with value 0.
+        const int64_t first = (int64_t)part * 4 * nch, last = first + (int64_t)4 * nch;
+        int32_t e = 0;                               // next source element
+        int32_t pads_left = 0;                       // bridge entries still to emit before element e
+        int32_t idx = 0;                             // index of the entry emitted last
+        uint32_t base = 0, prev = 0, word = 0;
+        VT vv[4];
+        for (int64_t s = 0; s < last; ++s) {
+            VT v = StoreCvt<VT>::cvt(0.0f);
+            if (e < len) {
+                if (pads_left > 0) { idx += 255; --pads_left; }
+                else {
+                    idx = col[st + e] - cb;
+                    v = StoreCvt<VT>::cvt(val[st + e]);
+                    ++e;
+                    if (e < len) {
+                        const int32_t gap = (col[st + e] - cb) - idx;
+                        pads_left = gap > 255 ? (gap - 1) / 255 : 0;
+                    }
+                }
+            }                                         // past the end: the last index again, value 0
+            if (s < first) continue;
+            const int k = (int)((s - first) & 3);
+            if (s == first) { base = (uint32_t)idx; prev = base; }
+            if (k == 0) word = 0;
+            word |= ((uint32_t)idx - prev) << (8 * k);
+            vv[k] = v;
+            prev = (uint32_t)idx;
+            if (k == 3) {
+                uint4* chunk = data + ((s - first) >> 2) * W * KU + (int64_t)w * KU;
+                reinterpret_cast<uint32_t*>(chunk)[lane] = word;
+                if constexpr (sizeof(VT) == 4) {
+                    float4 f = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    chunk[IU + lane] = *reinterpret_cast<uint4*>(&f);
+                } else if constexpr (sizeof(VT) == 2) {
+                    __nv_bfloat16 h[4] = {vv[0], vv[1], vv[2], vv[3]};
+                    reinterpret_cast<uint2*>(chunk + IU)[lane] = *reinterpret_cast<uint2*>(h);
+                } else {
+                    double2 a2 = make_double2(vv[0], vv[1]), b2 = make_double2(vv[2], vv[3]);
+                    chunk[IU + lane] = *reinterpret_cast<uint4*>(&a2);
+                    chunk[IU + 32 + lane] = *reinterpret_cast<uint4*>(&b2);
+                }
+            }
+        }
+        reinterpret_cast<uint32_t*>(hp + (HU - 8) * 16)[lane] = base;
+    } else {
+    // absolute indices: the row's nonzeros go round-robin (4 at a time) over its lanes
     for (int c = 0; c < nch; ++c) {
         uint4* chunk = data + ((int64_t)c * W + w) * KU;
         int32_t ix[4];
@@ -840,6 +923,7 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
             chunk[IU + lane] = *reinterpret_cast<uint4*>(&a2);
             chunk[IU + 32 + lane] = *reinterpret_cast<uint4*>(&b2);
         }
+    }
     }
 }
 

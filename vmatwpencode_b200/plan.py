@@ -62,7 +62,7 @@ class DosePlan:
         opt.reserved[4] = host_path
         opt.reserved[6] = claim_lead           # dose kernel: stages before a super-slice's end at which the next is claimed (0 = default)
         opt.reserved[7] = k2_chunk_cap         # chunk cap of the transposed layout (chunk_cap is the dose layout's)
-        opt.reserved[5] = index_bytes          # 4 forces int32 column indices; 0 = uint16 whenever they fit
+        opt.reserved[5] = index_bytes          # 4 forces int32 column indices, 1 byte deltas; 0 = uint16 whenever they fit
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         over = np.ascontiguousarray(over, dtype=np.float64)
