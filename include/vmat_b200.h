@@ -52,7 +52,7 @@ typedef struct vmat_options {
                                [4] host-buffer path of vmat_eval, bits: 1 y read from mapped host memory,
                                    2 results + completion tags written to mapped host memory,
                                    4 y inside the launch parameters (default), 8 none (copy nodes)
-                               [5] 4 = int32 column indices (default: uint16 whenever they fit)
+                               [5] 4 = int32 column indices, 1 = byte deltas (default: uint16 whenever they fit)
                                [6] stages before a super-slice's end at which the dose kernel claims the next
                                [8] unused */
 } vmat_options_t;
