@@ -54,7 +54,7 @@ typedef struct vmat_options {
                                    4 y inside the launch parameters (default), 8 none (copy nodes)
                                [5] 4 = int32 column indices, 1 = byte deltas (default: uint16 whenever they fit)
                                [6] stages before a super-slice's end at which the dose kernel claims the next
-                               [8] 1 = transposed kernel claims its pieces at run time (double-buffered vg tile) */
+                               [8] unused */
 } vmat_options_t;
 
 /* Library / build identification. */

@@ -144,9 +144,7 @@ def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol):
                                   dict(k2_chunk_cap=1, k2_tasks=5), dict(k2_chunk_cap=3, tile_voxels=128), dict(claim_lead=1), dict(claim_lead=100),
                                   dict(k2_threads=256, k2_stages=6), dict(k2_threads=512, k2_stages=4, tile_voxels=256),
                                   dict(index_bytes=1), dict(index_bytes=1, chunk_cap=2, k2_chunk_cap=3), dict(index_bytes=1, tile_voxels=64, k2_tasks=7),
-                                  dict(index_bytes=1, k1_threads=128, k2_threads=256),
-                                  dict(k2_dynamic=True), dict(k2_dynamic=True, tile_voxels=64, k2_tasks=7), dict(k2_dynamic=True, tile_voxels=128, k2_stages=3),
-                                  dict(k2_dynamic=True, index_bytes=1, k2_threads=256, k2_stages=4)])
+                                  dict(index_bytes=1, k1_threads=128, k2_threads=256)])
 def test_plan_options_do_not_change_results(opts):
     case = make_case(V=9000, nb=8, M=4, N=6, density=0.02, seed=71)
     st = O.OracleState(case)

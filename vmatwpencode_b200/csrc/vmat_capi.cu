@@ -59,7 +59,6 @@ struct vmat_plan {
     // K2 layout
     DevBuf sell2, off2, tpr2, tasks2, cta_ptr2;
     int k2_grid = 1;
-    bool k2_dynamic = false;       // pieces claimed at run time, double-buffered vg tile (reserved[8] = 1)
     int32_t nslices2 = 0, nss2 = 0, ntasks2 = 0, ntiles = 0, T = 0, W2 = 4, nstages2 = 8, stage_bytes2 = 0;
     int64_t units2 = 0;
     // state
@@ -513,8 +512,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
         P->nstages2 = P->opt.reserved[1] > 0 ? std::max(2, std::min(16, P->opt.reserved[1])) : 8;
         const size_t tile_bytes = ((size_t)T * P->acc_size + 127) & ~(size_t)127;
-        P->k2_dynamic = P->opt.reserved[8] == 1;
-        P->k2_smem = (P->k2_dynamic ? 2 : 1) * tile_bytes + (size_t)P->nstages2 * P->stage_bytes2;
+        P->k2_smem = tile_bytes + (size_t)P->nstages2 * P->stage_bytes2;
         if (P->k2_smem + 2048 > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
         const int32_t nt = (int32_t)((V + T - 1) / T);
         P->T = T; P->ntiles = nt;
@@ -569,20 +567,6 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         for (int64_t c : ss_cost) total_w += c;
         std::vector<K2Task> tasks;
         std::vector<int32_t> cta_ptr(P->k2_grid + 1, 0);
-        if (P->k2_dynamic) {
-            // single-tile pieces of about a quarter of a CTA's share, in stream order; CTA c starts with
-            // piece c, the rest are claimed at run time
-            const int64_t target = std::max<int64_t>(1, total_w / ((int64_t)P->k2_grid * 4));
-            const int32_t nss = P->nss2;
-            int32_t b0 = 0;
-            while (b0 < nss) {
-                int32_t b1 = b0;
-                int64_t acc = 0;
-                while (b1 < nss && ss_tile[b1] == ss_tile[b0] && acc < target) acc += ss_cost[b1++];
-                tasks.push_back(K2Task{ss_tile[b0], b0, b1, 0});
-                b0 = b1;
-            }
-        } else
         {
             const int32_t nss = P->nss2;
             int32_t f = 0, bk = 0, tend = 0;         // unassigned super-slices of the current tile: [f, bk); the tile ends at tend
@@ -766,7 +750,6 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a2.V = P->V; a2.B = (int32_t)P->B; a2.T = P->T; a2.nstages = P->nstages2; a2.stage_bytes = P->stage_bytes2;
         a2.k1_counter = P->counter.as<unsigned int>();
         a2.fpart = P->fpart.as<double>(); a2.fblock = P->fblock.as<double>(); a2.nfpart = P->nslices1;
-        a2.dynamic = P->k2_dynamic ? 1 : 0; a2.ntasks = P->ntasks2; a2.claim = P->counter.as<unsigned int>() + 1;
         a2.trace = P->tracing ? P->trace.as<unsigned long long>() + (size_t)P->k1_grid * kTraceSlots : nullptr;
         DISPATCH_IW(IW, {   // always launched (even with an empty task list): it also folds the objective partials
             DISPATCH_W2(W2c, {

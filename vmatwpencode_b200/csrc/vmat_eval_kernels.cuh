@@ -26,7 +26,6 @@ namespace vmat {
 
 constexpr int kStageHeader = 1;     // stage carries the super-slice header
 constexpr int kStageLast = 2;       // last stage of the super-slice: run the epilogue
-constexpr int kStageBuf = 4;        // K2, dynamic pieces: the super-slice's vg tile sits in tile buffer 1
 struct StageInfo { int32_t ss, flags, tile, tpr; };
 
 // header units (16 B) per warp: 32 row ids (+ thr, over, under as AT for K1)
@@ -269,7 +268,6 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     // done: consumers wait here; the producer first streams its statically assigned super-slice
     // (read-only data into its own ring) and waits only before it touches the counter
     if (warp < W) pdl_wait();
-    if (blockIdx.x == 0 && tid == 0) a.counter[1] = 0u;      // the transposed kernel's piece counter (dynamic pieces)
     if (trace && tid == 0) trace[1] = global_timer_ns();
     if (blockIdx.x == 0 && warp < W) {
         if (XS && a.y_mirror != nullptr) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
@@ -405,10 +403,6 @@ struct K2Args {
     double* fblock;               // [gridDim.x] ... folded here into one fixed-order sum per CTA
     int32_t nfpart;
     unsigned long long* trace;    // diagnostics, as in K1Args: [entry, K1 done, first stage, consumers done, producer done]
-    // dynamic pieces: `tasks` are ntasks single-tile pieces; CTA c starts with piece c and claims the
-    // next from `claim` (reset by K1); vg tiles are double-buffered, the producer prefetches the next one
-    int32_t dynamic, ntasks;
-    unsigned int* claim;
 };
 
 template <typename VT, typename AT, int W, int IW>
@@ -416,13 +410,11 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     constexpr int KU = chunk_units<VT, IW>(), HU = header_units_k2(IW);
     constexpr int kMaxStages = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tile_full[2], tile_empty[2];
+    __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tilebar;
     __shared__ StageInfo sinfo[kMaxStages];
     const int tbytes = (a.T * (int)sizeof(AT) + 127) & ~127;
-    AT* const vtb[2] = {reinterpret_cast<AT*>(smem_raw), reinterpret_cast<AT*>(smem_raw + tbytes)};
-    AT* vt = vtb[0];
-    unsigned char* ring = smem_raw + (a.dynamic ? 2 : 1) * tbytes;
-    uint64_t& tilebar = tile_full[0];
+    AT* vt = reinterpret_cast<AT*>(smem_raw);
+    unsigned char* ring = smem_raw + tbytes;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nst = a.nstages, SB = a.stage_bytes;
     unsigned long long* const trace = a.trace ? a.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
@@ -430,57 +422,16 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     if (tid == 0) {
         if (trace) trace[0] = global_timer_ns();
         for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
-        mbar_init(&tile_full[0], 1); mbar_init(&tile_full[1], 1);
-        mbar_init(&tile_empty[0], 1); mbar_init(&tile_empty[1], 1);
+        mbar_init(&tilebar, 1);
         fence_barrier_init();
     }
     __syncthreads();
-    const int t_begin = a.dynamic ? (int)blockIdx.x : a.cta_task_ptr[blockIdx.x];
-    const int t_end = a.dynamic ? ((int)blockIdx.x < a.ntasks ? t_begin + 1 : t_begin) : a.cta_task_ptr[blockIdx.x + 1];
+    const int t_begin = a.cta_task_ptr[blockIdx.x], t_end = a.cta_task_ptr[blockIdx.x + 1];
 
     if (warp == W) {     // the producer streams D (static data) right away; only consumers need K1's vg
         if (lane == 0) {
             const uint64_t pol = l2_evict_first_policy();
             RingPos pos;
-            if (a.dynamic) {
-                int piece = blockIdx.x, buf = 0, tile_now = -1;
-                uint32_t uses[2] = {0u, 0u};          // tile loads issued into each buffer so far
-                bool synced = false;                   // griddepcontrol.wait done (K1 finished: vg final, claim counter reset)
-                while (piece < a.ntasks) {
-                    const K2Task task = a.tasks[piece];
-                    if (tile_now < 0) { tile_now = task.tile; uses[0] = 1u; }     // the first tile is loaded by the consumers
-                    else if (task.tile != tile_now) {
-                        const int nb = buf ^ 1;
-                        // the consumers release a buffer when they switch away from it
-                        if (uses[nb] > 0u) mbar_wait(&tile_empty[nb], (uses[nb] - 1u) & 1u);
-                        if (!synced) { pdl_wait(); synced = true; }
-                        const int64_t base = (int64_t)task.tile * a.T;
-                        const int n = (int)min((int64_t)a.T, a.V - base);
-                        const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(AT) + 15) & ~(size_t)15);
-                        mbar_expect_tx(&tile_full[nb], bytes);
-                        tma_bulk_g2s(vtb[nb], a.vg + base, bytes, &tile_full[nb]);
-                        ++uses[nb]; buf = nb; tile_now = task.tile;
-                    }
-                    const int bflag = buf ? kStageBuf : 0;
-                    int64_t o0 = a.ss_off[task.ss_begin];
-                    for (int ss = task.ss_begin; ss < task.ss_end; ++ss) {
-                        const int64_t o1 = a.ss_off[ss + 1];
-                        const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
-                        const int tpr = a.ss_tpr[ss];
-                        ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                                  StageInfo{ss, kStageHeader | bflag | (nch == 0 ? kStageLast : 0), task.tile, tpr},
-                                  a.sell + o0, W * HU * 16, pol);
-                        const uint4* data = a.sell + o0 + W * HU;
-                        for (int c = 0; c < nch; ++c)
-                            ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                                      StageInfo{ss, bflag | (c == nch - 1 ? kStageLast : 0), task.tile, tpr},
-                                      data + (int64_t)c * W * KU, W * KU * 16, pol);
-                        o0 = o1;
-                    }
-                    if (!synced) { pdl_wait(); synced = true; }
-                    piece = (int)(gridDim.x + atomicAdd(a.claim, 1u));
-                }
-            } else
             for (int ti = t_begin; ti < t_end; ++ti) {
                 const K2Task task = a.tasks[ti];
                 int64_t o0 = a.ss_off[task.ss_begin];
@@ -534,8 +485,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     AT acc = (AT)0;
     int32_t row = -1;
     uint32_t cur = 0;
-    uint32_t fphase[2] = {0u, 0u};
-    int cur_buf = 0;
+    uint32_t tparity = 0;
     if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }    // outside the hot loop
     while (true) {
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
@@ -545,25 +495,20 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
             const unsigned char* sp = ring + (size_t)pos.stage * SB;
             if (info.tile != cur_tile) {
                 named_bar_sync(1, W * 32);            // all consumers are done with the previous tile
-                const int nb = (info.flags & kStageBuf) ? 1 : 0;
-                if (a.dynamic) {                      // the producer prefetched the tile into the other buffer
-                    if (tid == 0) mbar_arrive(&tile_empty[cur_buf]);
-                } else if (tid == 0) {
+                if (tid == 0) {
                     const int64_t base = (int64_t)info.tile * a.T;
                     const int n = (int)min((int64_t)a.T, a.V - base);
                     const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(AT) + 15) & ~(size_t)15);
                     mbar_expect_tx(&tilebar, bytes);
                     tma_bulk_g2s(vt, a.vg + base, bytes, &tilebar);
                 }
-                mbar_wait(&tile_full[nb], fphase[nb]);
-                fphase[nb] ^= 1u;
-                cur_buf = nb;
-                vt = vtb[nb];
+                mbar_wait(&tilebar, tparity);
+                tparity ^= 1u;
                 cur_tile = info.tile;
                 tile_pending = false;
             } else if (tile_pending) {
-                mbar_wait(&tile_full[0], fphase[0]);
-                fphase[0] ^= 1u;
+                mbar_wait(&tilebar, tparity);
+                tparity ^= 1u;
                 tile_pending = false;
             }
             row = reinterpret_cast<const int32_t*>(sp + warp * (HU * 16))[lane];
