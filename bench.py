@@ -7,7 +7,10 @@ One step = one evaluation of the hot path: x = y*w_dose, d = D x, penalty (objec
 voxel gradient), gb = D^T vg, aperture gradient g  (calcObjGrad, greedyVMATsampling.py:578-582
 plus the beamlet gradient PPsubroutine :646 needs).  Workload at N=1: BASELINE.json
 configs[1], the synthetic 300k-voxel x 10 080-beamlet x 180-control-point case at 1 % density.
-For N>1 the same case is voxel-sharded (strong scaling) with one all-reduce per evaluation.
+For N>1 the same case is voxel-sharded (strong scaling) with one exchange per evaluation, fused
+into the reduction kernel over NVLink peer memory.  After the timed legs the results are compared
+with the CPU oracle (`check`), and the largest case (BASELINE.json configs[3], 4M voxels,
+device-generated, voxel-sharded) is measured and checked in the same process (`largest_case`).
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -15,7 +18,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -24,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
+
+L2_BYTES = 126_000_000
 
 
 def measured_peaks():
@@ -37,54 +41,72 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi SM clocks and throttle reasons while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, sampled in-process through NVML on a thread while
+    the timed regions run (a 20-step run is over before `nvidia-smi -lms` prints its first line)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, index=0):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.sm, self.bits, self.marks = index, [], 0, []
+        self.stop_flag = threading.Event()
+        self.loaded = threading.Event()          # set while a timed region is running
+        self.nv = self.h = self.t = None
+        self.smax = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag.is_set():
+            if self.loaded.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.0002)
+            else:
+                time.sleep(0.0005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.stop_flag.set()
+        self.t.join(timeout=2)
+        reasons = [n for n, b in self.REASONS if self.bits & b]
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                "reasons": reasons, "samples": len(self.sm), "how": "NVML, sampled only while timed regions run"}
 
 
 DEVICE_WORKLOADS = ("cfg3", "cfg4")      # too large to build through scipy on the host
+
+
+def describe(name, V, B, nb, nnz):
+    """config.workload - the same string in both arms."""
+    return f"{name}: {V} voxels x {B} beamlets, {nb} control points, nnz {nnz}, 1 % dense geometric sparsity"
+
+
+def bench_weights(nb, M, N, beam_ptr, B):
+    """All control points selected with a centred open aperture; intensities in (0.5, 1.5)."""
+    w_dose = np.zeros(B)
+    w_grad = np.zeros(B)
+    for i in range(nb):
+        lo = int(beam_ptr[i])
+        for m in range(M):
+            w_dose[lo + m * N + 1: lo + (m + 1) * N - 1] = 1.0
+            w_grad[lo + m * N + 1: lo + (m + 1) * N - 1] = 1.0
+    y = 0.5 + (np.arange(nb) * 0.6180339887) % 1.0
+    return y, w_dose, w_grad
 
 
 def workload(name, scale, device=None):
@@ -93,15 +115,7 @@ def workload(name, scale, device=None):
         case = make_device_config(name, scale=scale, device=device)
     else:
         case = make_config(name, scale=scale)
-    # all control points selected with a centred open aperture; intensities in (0.5, 1.5)
-    w_dose = np.zeros(case.B)
-    w_grad = np.zeros(case.B)
-    for i in range(case.nb):
-        lo = int(case.beam_ptr[i])
-        for m in range(case.M):
-            w_dose[lo + m * case.N + 1: lo + (m + 1) * case.N - 1] = 1.0
-            w_grad[lo + m * case.N + 1: lo + (m + 1) * case.N - 1] = 1.0
-    y = 0.5 + (np.arange(case.nb) * 0.6180339887) % 1.0
+    y, w_dose, w_grad = bench_weights(case.nb, case.M, case.N, case.beam_ptr, case.B)
     return case, y, w_dose, w_grad
 
 
@@ -133,7 +147,7 @@ def cpu_port_rate(case, y, w_dose, w_grad, seconds=10.0, min_evals=3, threads=0)
         gb = Dt @ vg
         m += 1
     scipy_rate = m / (time.perf_counter() - t1)
-    return rate, nthreads, n, scipy_rate
+    return rate, nthreads, n, scipy_rate, co
 
 
 def run_reference(args):
@@ -147,9 +161,10 @@ def run_reference(args):
     from oracle.c_oracle import COracle
     co = COracle(case)
     threads = os.cpu_count() or 1
-    for _ in range(max(1, min(args.warmup, 3))):
+    warm = max(1, min(args.warmup, 3))            # a CPU evaluation is ~5 ms: a few are enough to warm caches
+    for _ in range(warm):
         co.eval(y, w_dose, w_grad, threads=threads)
-    steps = min(args.steps, 50)
+    steps = max(1, min(args.steps, 50))
     t0 = time.perf_counter()
     for _ in range(steps):
         co.eval(y, w_dose, w_grad, threads=threads)
@@ -157,15 +172,249 @@ def run_reference(args):
     val = steps / dt
     line = {
         "impl": "reference", "metric": "dose+gradient evaluations/s", "value": val, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "steps_requested": args.steps,
+        "warmup_requested": args.warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {case.V} voxels x {case.B} beamlets, {case.nb} control points, "
-                               f"nnz {case.nnz}", "scale": args.scale},
+        "config": {"workload": describe(args.workload, case.V, case.B, case.nb, case.nnz), "scale": args.scale},
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} full evaluations of the same case, oracle/vmat_oracle.c (OpenMP)"},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=float).ravel()
+    b = np.asarray(b, dtype=float).ravel()
+    den = float(np.abs(b).max()) if b.size else 0.0
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0)) if a.size else 0.0
+
+
+def sampled_device_check(plan, csr, thr, over, under, y, w_dose, w_grad, beam_ptr, f_dev, g_dev, rank, world, dist, torch,
+                         nrows=10000, ncols=1000):
+    """Check of a device-generated (possibly sharded) case without a host copy of D: sampled voxel rows of
+    the dose and sampled beamlets of the beamlet gradient are recomputed in float64 with torch index
+    arithmetic from the rank's CSR tensors (not the plan's layouts, not the plan's kernels), the
+    objective from the device dose, the aperture gradient from the device beamlet gradient."""
+    dev = csr["vval"].device
+    V = int(csr["vrowptr"].numel()) - 1
+    B = int(beam_ptr[-1])
+    x = torch.as_tensor(np.repeat(y, np.diff(beam_ptr)) * w_dose, device=dev)
+    d_dev = torch.as_tensor(plan.dose(), device=dev)
+    vg_dev = torch.as_tensor(plan.voxelgrad(), device=dev)
+    gb_dev = plan.beamlet_grad()
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+
+    def rows_dot(rowptr, col, val, rows, vec):
+        lo, hi = rowptr[rows], rowptr[rows + 1]
+        n = hi - lo
+        seg = torch.repeat_interleave(torch.arange(len(rows), device=dev), n)
+        pos = torch.arange(int(n.sum().item()), device=dev) - torch.repeat_interleave(torch.cumsum(n, 0) - n, n) + \
+            torch.repeat_interleave(lo, n)
+        out = torch.zeros(len(rows), dtype=torch.float64, device=dev)
+        out.index_add_(0, seg, val[pos].double() * vec[col[pos].long()])
+        return out
+
+    rows = torch.randperm(V, generator=gen)[:min(nrows, V)].to(dev)
+    d_ref = rows_dot(csr["vrowptr"], csr["vcol"], csr["vval"], rows, x)
+    t = torch.as_tensor(thr, device=dev)[rows]
+    ov = torch.as_tensor(over, device=dev)[rows]
+    un = torch.as_tensor(under, device=dev)[rows]
+    o = torch.clamp(d_ref - t, min=0)
+    u = torch.clamp(t - d_ref, min=0)
+    vg_ref = 2 * (2 * o * ov - 2 * u * un)
+    err_d = float((d_dev[rows] - d_ref).abs().max() / d_dev.abs().max().clamp(min=1e-300))
+    err_vg = float((vg_dev[rows] - vg_ref).abs().max() / vg_dev.abs().max().clamp(min=1e-300))
+    # objective from the whole device dose (this rank's slab), summed over ranks
+    tt, oo, uu = (torch.as_tensor(a, device=dev) for a in (thr, over, under))
+    o = torch.clamp(d_dev - tt, min=0)
+    u = torch.clamp(tt - d_dev, min=0)
+    f_ref = (o * o * oo + u * u * uu).sum().reshape(1)
+    cols = torch.randperm(B, generator=torch.Generator(device="cpu").manual_seed(99))[:min(ncols, B)].to(dev)
+    gb_ref = rows_dot(csr["browptr"], csr["bcol"], csr["bval"], cols, vg_dev)
+    if world > 1:
+        dist.all_reduce(f_ref)
+        dist.all_reduce(gb_ref)
+    gb_s = torch.as_tensor(gb_dev, device=dev)
+    err_gb = float((gb_s[cols] - gb_ref).abs().max() / gb_s.abs().max().clamp(min=1e-300))
+    g_ref = np.add.reduceat(gb_dev * w_grad, np.asarray(beam_ptr[:-1], dtype=np.int64))
+    errs = torch.tensor([err_d, err_vg], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    return {"rel_err_f": abs(f_dev - float(f_ref.item())) / abs(float(f_ref.item())),
+            "rel_err_g": relerr(g_dev, g_ref), "rel_err_gb": err_gb,
+            "rel_err_d": float(errs[0].item()), "rel_err_vg": float(errs[1].item()),
+            "against": f"float64 torch recomputation from the ranks' CSR tensors: {len(rows)} random voxel rows of d and vg "
+                       f"per rank, {len(cols)} random beamlets of gb (summed over ranks), f from the device dose, "
+                       "g from the device gb"}
+
+
+def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, headline):
+    """Build the plan of workload `name` on this rank's slab, time the resident and the host-buffer legs,
+    time the kernels, check the results.  Returns the measurement dict (meaningful on rank 0)."""
+    from vmatwpencode_b200.plan import DosePlan
+    from vmatwpencode_b200.dist import ShardedEvaluator, slab_of, slab_of_device
+    device_case = name in DEVICE_WORKLOADS
+    case, y, w_dose, w_grad = workload(name, args.scale, device=f"cuda:{local}")
+    if device_case:
+        D, thr, over, under = slab_of_device(case, rank, world)
+        if world > 1:
+            case.csr = None
+        torch.cuda.empty_cache()
+    else:
+        rows, D, thr, over, under = slab_of(case, rank, world)
+    plan = DosePlan(D, case.beam_ptr, thr, over, under, device=local, store=args.store, acc=args.acc, **opts)
+    plan.set_weights(w_dose, w_grad)
+    info = plan.info()
+    ev = ShardedEvaluator(plan)
+    stream = torch.cuda.current_stream().cuda_stream
+    assert stream != 0
+    plan.set_intensities(y)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident throughput (`value`): y already in HBM, results left in HBM ----------
+    for _ in range(W):
+        ev.eval_async(stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.loaded.set()
+    e0.record()
+    for _ in range(K):
+        ev.eval_async(stream)
+    e1.record()
+    barrier()
+    sampler.loaded.clear()
+    ms = maxr(e0.elapsed_time(e1))
+    # second pass of the same K steps with a CUDA event after every kernel: the per-kernel
+    # durations behind `roofline` (events between kernels serialise the launches, so this pass
+    # is a little slower than the one `value` comes from)
+    plan.set_timing(True)
+    sampler.loaded.set()
+    for _ in range(K):
+        ev.eval_async(stream)
+    barrier()
+    sampler.loaded.clear()
+    kt = plan.get_timing()
+    plan.set_timing(False)
+    f_res, g_res = plan.fetch_result()
+
+    # ---- end to end (`e2e`): host y in, host (f, g) out through the C ABI each step --------
+    for _ in range(W):
+        plan.eval(y)
+    barrier()
+    sampler.loaded.set()
+    t0 = time.perf_counter()
+    for k in range(K):
+        yk = y if (k & 1) == 0 else y * 1.0000001
+        plan.eval(yk)
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0)
+    sampler.loaded.clear()
+    if headline:
+        # sustained leg for the clock sample only (not reported as a rate): ~0.2 s of back-to-back evaluations
+        n_sus = max(K, int(0.2 / max(ms / K * 1e-3, 1e-6)))
+        sampler.loaded.set()
+        for _ in range(min(n_sus, 20000)):
+            ev.eval_async(stream)
+        barrier()
+        sampler.loaded.clear()
+        plan.set_intensities(y)
+        ev.eval_async(stream)
+        barrier()
+        f_res, g_res = plan.fetch_result()
+
+    # ---- check (outside every timed region) ---------------------------------------------------
+    check = {"f": f_res, "g_norm": float(np.linalg.norm(g_res))}
+    if device_case:
+        check.update(sampled_device_check(plan, D, thr, over, under, y, w_dose, w_grad, case.beam_ptr, f_res, g_res,
+                                          rank, world, dist, torch))
+    elif rank == 0:
+        from oracle.c_oracle import COracle
+        co = COracle(case)
+        f0, g0 = co.eval(y, w_dose, w_grad, threads=os.cpu_count() or 1)
+        check.update({"rel_err_f": abs(f_res - f0) / abs(f0), "rel_err_g": relerr(g_res, g0),
+                      "rel_err_gb": relerr(plan.beamlet_grad(), co.gb),
+                      "against": "oracle/vmat_oracle.c (float64) on the full case, after the timed legs"})
+        if world == 1:
+            check["rel_err_d"] = relerr(plan.dose(), co.d)
+            check["rel_err_vg"] = relerr(plan.voxelgrad(), co.vg)
+    errs = [v for k, v in check.items() if k.startswith("rel_err")]
+    if errs:
+        check["tolerance"] = 1e-5 if args.acc == "f32" else 1e-10
+        check["ok"] = bool(max(errs) <= check["tolerance"])
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        sv = {"f32": 4, "bf16": 2, "f64": 8}[args.store]
+        si = info["index_bytes"]
+        nnz_local = info["nnz"]
+        slab_mb = nnz_local * (sv + si) / 1e6
+        fits = 2 * slab_mb * 1e6 <= L2_BYTES
+        out = {
+            "workload": describe(name, case.V, case.B, case.nb, case.nnz if not device_case else int(case.nnz)),
+            "value": K / (ms * 1e-3), "ms_per_step": ms / K, "steps": K, "warmup": W,
+            "e2e": {"value": K / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": case.nb * 8,
+                    "d2h_bytes_per_step": (case.nb + (2 if world > 1 else 1)) * 8, "ms_per_step": 1e3 * e2e_s / K,
+                    "how": "vmat_eval(y, &f, g) per step with host buffers on every rank: y (nb f64) goes to the device "
+                           "inside the dose kernel's launch parameters (a 1.4 KB H2D copy when nb > 384), f and g "
+                           "(nb+1 f64) come back with one D2H copy into pinned memory and one stream synchronisation"},
+            "plan": {"nnz_this_rank": nnz_local, "store_dtype": args.store, "acc_dtype": args.acc, "index_bytes": si,
+                     "sharding": f"voxel slabs x{world}", "exchange": "push all-reduce fused into the reduction kernel "
+                     "(NVLink peer memory)" if world > 1 else "none",
+                     "l2": ("both layouts of this rank's slab (2 x %.0f MB) FIT the 126 MB L2: steps after the first "
+                            "stream from L2, not HBM; no flush between steps" % slab_mb) if fits else
+                           ("both layouts of this rank's slab (2 x %.0f MB) exceed the 126 MB L2; no flush between steps"
+                            % slab_mb)},
+            "gpu_launches": info["launches_per_eval"] * K,
+            "check": check,
+        }
+        # dominant kernel of this rank: whichever of K1 (dose+penalty) / K2 (transposed) is slower
+        if kt["n"] > 0:
+            k1_bytes = nnz_local * (sv + si) + 4 * (plan.V + 1) + 12 * plan.V + 8 * plan.V + 4 * plan.B
+            k2_bytes = nnz_local * (sv + si) + 4 * plan.V + 4 * (plan.B + 1) + 4 * plan.B
+            kname, kms, kb = ("k2_beamlet_grad", kt["k2_ms"], k2_bytes) if kt["k2_ms"] >= kt["k1_ms"] else \
+                             ("k1_dose_penalty", kt["k1_ms"], k1_bytes)
+            ach = kb / (kms * 1e-3) / 1e9
+            traffic = None      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
+            tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+            if os.path.isfile(tpath) and world == 1 and args.scale == 1.0:
+                tj = json.load(open(tpath))
+                key = f"{name}/{args.store}/{args.acc}/{si}"
+                traffic = tj.get("dram_bytes_per_launch", {}).get(key, {}).get(kname)
+            out["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
+                               "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                               "algorithmic_bytes_per_launch": kb, "launch_ms": kms,
+                               "scope": "rank 0's slab" if world > 1 else "whole case",
+                               "note": ("slab fits L2: not an HBM measurement" if fits else None)}
+            out["kernels_ms"] = {k: kt[k] for k in ("k1_ms", "k2_ms", "k3_ms", "eval_ms")}
+            algo = info["algorithmic_bytes_per_eval"]
+            ach_eval = algo / (ms / K * 1e-3) / 1e9
+            out["roofline_eval"] = {"achieved": ach_eval, "peak": peak, "unit": "GB/s", "frac": ach_eval / peak,
+                                    "frac_of_8TBps": ach_eval / 8000.0, "frac_of_read_peak_7090": ach_eval / 7090.0,
+                                    "algorithmic_bytes_per_eval": algo,
+                                    "layout_bytes_per_eval": info["layout_bytes_per_eval"],
+                                    "scope": "rank 0's slab per evaluation" if world > 1 else "whole case"}
+        out["_case"] = (case, y, w_dose, w_grad)
+    barrier()
+    plan.close()
+    del plan, D
+    if device_case:
+        case.csr = None
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -185,14 +434,14 @@ def main():
     ap.add_argument("--index-bytes", type=int, default=0, help="4 forces int32 column indices (default: uint16 when they fit)")
     ap.add_argument("--claim-lead", type=int, default=0, help="dose kernel: stages before a super-slice's end at which the next is claimed (tuning; 0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--largest", default="cfg4", help="workload of the `largest_case` block ('none' skips it)")
+    ap.add_argument("--largest-steps", type=int, default=200)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from vmatwpencode_b200.plan import DosePlan
-    from vmatwpencode_b200.dist import ShardedEvaluator, slab_of
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -204,141 +453,49 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = max(3, args.warmup)
     K = args.steps
-
-    case, y, w_dose, w_grad = workload(args.workload, args.scale, device=f"cuda:{local}")
-    if args.workload in DEVICE_WORKLOADS:
-        from vmatwpencode_b200.dist import slab_of_device
-        D, thr, over, under = slab_of_device(case, rank, world)
-        torch.cuda.empty_cache()
-    else:
-        rows, D, thr, over, under = slab_of(case, rank, world)
-    plan = DosePlan(D, case.beam_ptr, thr, over, under, device=local, store=args.store, acc=args.acc,
-                    tile_voxels=args.tile, k2_tasks=args.k2_tasks, k2_threads=args.k2_threads,
-                    k1_threads=args.k1_threads, index_bytes=args.index_bytes, claim_lead=args.claim_lead)
-    if args.workload in DEVICE_WORKLOADS:      # the CSR copies are no longer needed: the plan holds its own layouts
-        case.csr = None
-        del D
-        torch.cuda.empty_cache()
-    plan.set_weights(w_dose, w_grad)
-    info = plan.info()
-    ev = ShardedEvaluator(plan)
+    opts = dict(tile_voxels=args.tile, k2_tasks=args.k2_tasks, k2_threads=args.k2_threads, k1_threads=args.k1_threads,
+                index_bytes=args.index_bytes, claim_lead=args.claim_lead)
     # a side stream: the library treats stream 0 as "use the plan's own stream", and the CUDA
-    # events below must sit on the stream the kernels are launched on
+    # events must sit on the stream the kernels are launched on
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
-    stream = side.cuda_stream
-    assert stream != 0
-    plan.set_intensities(y)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- resident throughput (`value`): y already in HBM, results left in HBM ----------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(W):
-        ev.eval_async(stream)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        ev.eval_async(stream)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # second pass of the same K steps with a CUDA event after every kernel: the per-kernel
-    # durations behind `roofline` (events between kernels serialise the launches, so this pass
-    # is a little slower than the one `value` comes from)
-    kt = None
-    if world == 1:
-        plan.set_timing(True)
-        for _ in range(K):
-            ev.eval_async(stream)
-        barrier()
-        kt = plan.get_timing()
-        plan.set_timing(False)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    f_res, g_res = plan.fetch_result()
 
-    # ---- end to end (`e2e`): host y in, host (f, g) out through the C ABI each step --------
-    for _ in range(W):
-        ev.eval(y) if world > 1 else plan.eval(y)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        yk = y if (k & 1) == 0 else y * 1.0000001
-        f_e, g_e = ev.eval(yk) if world > 1 else plan.eval(yk)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-
+    head = run_case(args, args.workload, K, W, rank, local, world, dist, torch, sampler, opts, headline=True)
+    largest = None
+    if args.largest != "none" and args.largest != args.workload and args.scale == 1.0:
+        largest = run_case(args, args.largest, max(1, args.largest_steps), W, rank, local, world, dist, torch, sampler,
+                           opts, headline=False)
     clocks = sampler.stop() if rank == 0 else None
+
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        value = K / (ms * 1e-3)
-        sv = {"f32": 4, "bf16": 2, "f64": 8}[args.store]
-        nnz_local = info["nnz"]
+        case, y, w_dose, w_grad = head.pop("_case")
         line = {
-            "metric": "dose+gradient evaluations/s", "value": value, "unit": "evals/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "metric": "dose+gradient evaluations/s", "value": head["value"], "unit": "evals/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.acc, "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {case.V} voxels x {case.B} beamlets, {case.nb} control points, "
-                                   f"nnz {case.nnz} ({100.0 * case.nnz / (case.V * case.B):.2f} % dense), geometric sparsity",
-                       "nnz_this_rank": nnz_local,
-                       "store_dtype": args.store, "acc_dtype": args.acc, "index_bytes": info["index_bytes"], "sharding": f"voxel slabs x{world}",
-                       "l2": "both layouts of D (2 x ~%d MB) exceed the 126 MB L2; no flush between steps"
-                             % (nnz_local * (sv + info["index_bytes"]) // 1_000_000),
-                       "scale": args.scale},
-            "e2e": {"value": K / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": case.nb * 8,
-                    "d2h_bytes_per_step": (case.nb + 1) * 8, "ms_per_step": 1e3 * e2e_s / K,
-                    "how": "vmat_eval(y, &f, g) per step with host buffers: y (nb f64) goes to the device inside the "
-                           "dose kernel's launch parameters (a 1.4 KB H2D copy when nb > 384), f and g (nb+1 f64) come "
-                           "back with one D2H copy into pinned memory and a stream synchronisation"},
-            "gpu_launches": (info["launches_per_eval"] + (1 if world > 1 else 0)) * K,
-            "clocks": clocks,
-            "check": {"f": f_res, "g_norm": float(np.linalg.norm(g_res))},
+            "config": {"workload": head["workload"], "scale": args.scale},
+            "plan": head["plan"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "clocks": clocks, "check": head["check"],
         }
-        algo = info["algorithmic_bytes_per_eval"]
-        if kt is not None and kt["n"] > 0:
-            # dominant kernel: whichever of K1 (dose+penalty) / K2 (transposed) is slower
-            si = info["index_bytes"]
-            k1_bytes = nnz_local * (sv + si) + 4 * (plan.V + 1) + 12 * plan.V + 8 * plan.V + 4 * plan.B
-            k2_bytes = nnz_local * (sv + si) + 4 * plan.V + 4 * (plan.B + 1) + 4 * plan.B
-            name, kms, kb = ("k2_beamlet_grad", kt["k2_ms"], k2_bytes) if kt["k2_ms"] >= kt["k1_ms"] else \
-                            ("k1_dose_penalty", kt["k1_ms"], k1_bytes)
-            ach = kb / (kms * 1e-3) / 1e9
-            traffic = None      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-            if os.path.isfile(tpath) and args.workload == "cfg2" and args.scale == 1.0 and \
-                    (args.store, args.acc, info["index_bytes"]) == ("f32", "f32", json.load(open(tpath)).get("index_bytes", 4)):
-                traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(name)
-            line["roofline"] = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                                "algorithmic_bytes_per_launch": kb, "launch_ms": kms}
-            line["kernels_ms"] = {k: kt[k] for k in ("k1_ms", "k2_ms", "k3_ms", "eval_ms")}
-            ach_eval = algo / (ms / K * 1e-3) / 1e9
-            line["roofline_eval"] = {"achieved": ach_eval, "peak": peak, "unit": "GB/s", "frac": ach_eval / peak,
-                                     "frac_of_8TBps": ach_eval / 8000.0, "algorithmic_bytes_per_eval": algo,
-                                     "layout_bytes_per_eval": info["layout_bytes_per_eval"]}
+        for k in ("roofline", "kernels_ms", "roofline_eval"):
+            if k in head:
+                line[k] = head[k]
+        if largest is not None:
+            largest.pop("_case")
+            largest["scaling"] = "strong"
+            line["largest_case"] = largest
         if world == 1 and not args.no_cpu and args.workload not in DEVICE_WORKLOADS:
-            rate, cores, n, scipy_rate = cpu_port_rate(case, y, w_dose, w_grad)
+            rate, cores, n, scipy_rate, _ = cpu_port_rate(case, y, w_dose, w_grad)
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} full evaluations of the same case (oracle/vmat_oracle.c, f64, OpenMP)",
                                     "scipy_1core_value": scipy_rate}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    plan.close()
 
 
 if __name__ == "__main__":

@@ -135,12 +135,24 @@ int vmat_reduce_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);
 /*
  * Multi-GPU exchange without NCCL: every rank exports the CUDA IPC handle of its comm buffer
  * (vmat_comm_handle, 64 bytes), the caller gathers the handles of all ranks (any transport) and
- * hands them to vmat_comm_attach.  From then on vmat_eval_async(phase 0) / vmat_eval run the
- * reduction kernel fused with a one-shot all-reduce over peer memory (NVLink), summing the ranks
- * in rank order, and phases 1/2 are not needed.  All ranks must evaluate in lock step.
+ * hands them to vmat_comm_attach (at most 16 ranks).  From then on vmat_eval_async(phase 0) /
+ * vmat_eval run the reduction kernel fused with a push all-reduce over peer memory (NVLink): the CTA
+ * of control point i stores its partial beamlet gradient into every rank's buffer, publishes an
+ * epoch flag, waits for the peers' flags of the same control point in its own memory and adds the
+ * ranks in rank order - identical bits on every rank; phases 1/2 are not needed.  All ranks must
+ * attach before any of them evaluates, and must evaluate in lock step.  A peer that does not deliver
+ * within the time-out (default 20 s, vmat_comm_set_timeout) makes the evaluation return VMAT_E_CUDA
+ * with NaN results; the peers then fail the same way in their next evaluation.
+ * This replaces the reference's only parallelism, the process pool of greedyVMATsampling.py:836-841.
+ *
+ * vmat_comm_attach_local is the same for plans that live in ONE process (plans[q] = rank q's plan,
+ * plans[rank] == plan): on different devices with peer access, or - for tests - on the same device
+ * (the reduction kernels of all "ranks" must then be able to run concurrently: small plans only).
  */
 int vmat_comm_handle(vmat_plan_t* plan, void* handle_out /* 64 bytes */);
 int vmat_comm_attach(vmat_plan_t* plan, int32_t rank, int32_t nranks, const void* handles /* nranks*64 bytes */);
+int vmat_comm_attach_local(vmat_plan_t* plan, int32_t rank, int32_t nranks, vmat_plan_t* const* plans /* nranks */);
+int vmat_comm_set_timeout(vmat_plan_t* plan, double seconds);
 
 /* Device buffers for callers that keep the optimisation loop on the GPU: the intensities the
  * next vmat_eval_async reads (f64[nb]) and the result the last one wrote (f64[nb+1]: f then g). */

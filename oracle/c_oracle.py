@@ -36,6 +36,24 @@ class COracle:
         self.x = np.zeros(self.B); self.d = np.zeros(self.V); self.vg = np.zeros(self.V)
         self.ft = np.zeros(self.V); self.gb = np.zeros(self.B); self.g = np.zeros(self.nb)
 
+    @classmethod
+    def from_arrays(cls, V, B, nb, beam_ptr, vrowptr, vcol, vval, browptr, bcol, bval, thr, over, under):
+        """The same checker on CSR arrays that already exist in both orientations (e.g. copied back from a
+        device-generated case): no scipy conversion, values widened to float64."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.V, self.B, self.nb = int(V), int(B), int(nb)
+        self.beam_ptr = np.ascontiguousarray(beam_ptr, dtype=np.int32)
+        self.a = [np.ascontiguousarray(vrowptr, dtype=np.int64), np.ascontiguousarray(vcol, dtype=np.int32),
+                  np.ascontiguousarray(vval, dtype=np.float64),
+                  np.ascontiguousarray(browptr, dtype=np.int64), np.ascontiguousarray(bcol, dtype=np.int32),
+                  np.ascontiguousarray(bval, dtype=np.float64),
+                  np.ascontiguousarray(thr, dtype=np.float64), np.ascontiguousarray(over, dtype=np.float64),
+                  np.ascontiguousarray(under, dtype=np.float64)]
+        self.x = np.zeros(self.B); self.d = np.zeros(self.V); self.vg = np.zeros(self.V)
+        self.ft = np.zeros(self.V); self.gb = np.zeros(self.B); self.g = np.zeros(self.nb)
+        return self
+
     def max_threads(self):
         return int(self.lib.oracle_max_threads())
 

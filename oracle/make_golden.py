@@ -144,6 +144,23 @@ def kmedoids_fixture():
     print("kmedoids fixtures written")
 
 
+def kmedoids_perm_fixture():
+    """The reference's functions on 1-D point lists that are NOT 0..n-1 in order: its candidates are the
+    values of `ba`, visited in `ba`'s order, and double as row indices (kmedoids.py:50-53)."""
+    ns = R.extract("kmedoids")
+    out = {}
+    rng = np.random.default_rng(21)
+    for n, start in ((19, [2, 9]), (26, [0])):
+        ba = [int(v) for v in rng.permutation(n)]
+        with R.quiet():
+            order = ns["givemewholelist"](list(start), ba)
+        out[f"ba_n{n}"] = np.asarray(ba, dtype=np.int64)
+        out[f"start_n{n}"] = np.asarray(start, dtype=np.int64)
+        out[f"order_n{n}"] = np.asarray(order, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, "kmedoids_perm.npz"), **out)
+    print("kmedoids permutation fixtures written")
+
+
 def ingest_fixture(name, seed):
     """What the reference's own loader statements (greedyVMATsampling.py:286-576) produce for a
     synthetic CORT-format data set (oracle/cort_fixture.py, regenerated from `seed` by the tests)."""
@@ -236,6 +253,7 @@ def main():
     ingest_fixture("ingest_B", seed=2)
     colgen_files_fixture("colgen_files", seed=3, C=0.01, kappasize=3, max_iter=6)
     kmedoids_fixture()
+    kmedoids_perm_fixture()
 
 
 if __name__ == "__main__":

@@ -347,6 +347,13 @@ def test_kmedoids_known_answer():
         assert km.distancemin(start, range(0, n)) == float(z[f"dmin_n{n}"])
     # the one known answer the reference embeds (greedyVMAT.py:28)
     assert km.givemewholelist(list(range(6, 178, 11)), range(0, 178)) == list(z["kappa178"])
+    # 1-D lists that are not 0..n-1: the reference's candidates are the VALUES of ba, in ba's order
+    zp = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmedoids_perm.npz"))
+    for n in (19, 26):
+        ba = [int(v) for v in zp[f"ba_n{n}"]]
+        assert km.givemewholelist([int(v) for v in zp[f"start_n{n}"]], ba) == list(zp[f"order_n{n}"])
+    with pytest.raises(IndexError):
+        km.givemewholelist([0], [0.5, 1.5, 7.0])
     # coordinates in 3-D (voxel use): against the oracle
     rng = np.random.default_rng(4)
     P = rng.random((300, 3))
@@ -381,6 +388,55 @@ def test_full_size_config2_properties(acc):
     # aperture gradient is the w_grad-weighted beamlet gradient
     assert relerr(g, np.add.reduceat(w_grad * gb, case.beam_ptr[:-1].astype(np.int64))) <= tol
     plan.close()
+
+
+@pytest.mark.parametrize("acc", ["f32", "f64"])
+def test_full_size_config3_vs_c_oracle(acc):
+    """BASELINE.json configs[2]'s matrix at full size (1M voxels x 14 580 beamlets, ~142 M nnz, generated
+    on the device): every output against the C oracle run on the SAME arrays copied back to the host."""
+    import torch
+    from oracle.c_oracle import COracle
+    from vmatwpencode_b200.synth import make_device_config
+    case = make_device_config("cfg3", device="cuda:0")
+    rng = np.random.default_rng(17)
+    y, w_dose, w_grad = random_weights(case, rng, 0.5)
+    plan = DosePlan(case.csr, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc=acc)
+    plan.set_weights(w_dose, w_grad)
+    f, g = plan.eval(y)
+    d, vg, gb = plan.dose(), plan.voxelgrad(), plan.beamlet_grad()
+    plan.close()
+    h = {k: v.cpu().numpy() for k, v in case.csr.items()}
+    case.csr = None
+    torch.cuda.empty_cache()
+    co = COracle.from_arrays(case.V, case.B, case.nb, case.beam_ptr, h["vrowptr"], h["vcol"], h["vval"],
+                             h["browptr"], h["bcol"], h["bval"], case.thr, case.over, case.under)
+    f0, g0 = co.eval(y, w_dose, w_grad)
+    tol = TOL[acc]
+    assert abs(f - f0) <= tol * abs(f0)
+    assert relerr(g, g0) <= tol and relerr(d, co.d) <= tol and relerr(vg, co.vg) <= tol and relerr(gb, co.gb) <= tol
+
+
+def test_full_size_config4_sampled_check():
+    """BASELINE.json configs[3] (4M voxels x 29 160 beamlets, ~1.14 G nnz, device-generated): too large for a
+    host oracle in test time, so 10 000 random voxel rows of the dose / voxel gradient and 1 000 random
+    beamlets of the beamlet gradient are recomputed in float64 from the device CSR with plain torch index
+    arithmetic (bench.sampled_device_check - not the plan's layouts or kernels), the objective from the
+    device dose, the aperture gradient from the device beamlet gradient."""
+    import torch
+    import bench
+    from vmatwpencode_b200.synth import make_device_config
+    case = make_device_config("cfg4", device="cuda:0")
+    y, w_dose, w_grad = bench.bench_weights(case.nb, case.M, case.N, case.beam_ptr, case.B)
+    plan = DosePlan(case.csr, case.beam_ptr, case.thr, case.over, case.under, store="f32", acc="f32")
+    plan.set_weights(w_dose, w_grad)
+    f, g = plan.eval(y)
+    chk = bench.sampled_device_check(plan, case.csr, case.thr, case.over, case.under, y, w_dose, w_grad, case.beam_ptr,
+                                     f, g, 0, 1, None, torch)
+    plan.close()
+    case.csr = None
+    torch.cuda.empty_cache()
+    for k in ("rel_err_f", "rel_err_g", "rel_err_gb", "rel_err_d", "rel_err_vg"):
+        assert chk[k] <= 1e-5, (k, chk[k])
 
 
 def test_back_to_back_evaluations_do_not_race():

@@ -144,3 +144,65 @@ def test_sharded_kmedoid_voxel_sampling(tmp_path):
     P = np.round(rng.random((3000, 3)) * 64)
     single = km.givemewholelist([0, 7], P, limit=12)
     assert list(np.load(out)) == single
+
+
+def test_fused_exchange_two_ranks_on_one_device():
+    """The push exchange of the reduction kernel with both "ranks" living on one GPU (two plans of this
+    process attached to each other through vmat_comm_attach_local), so that the fused path is exercised
+    on a single-GPU box too.  The two evaluations are enqueued on the plans' own streams before either
+    result is fetched; the plans are kept small (short rings) so that the kernels of both can be resident
+    together - rank 0's reduction kernel spins until rank 1's has delivered."""
+    from oracle import vmat_oracle as O
+    from vmatwpencode_b200.synth import make_case
+    from vmatwpencode_b200.dist import slab_of
+    from vmatwpencode_b200.plan import DosePlan
+    from vmatwpencode_b200._lib import VmatError
+    case = make_case(V=50_000, nb=16, M=5, N=8, density=0.01, seed=93)
+    rng = np.random.default_rng(0)
+    wd = (rng.random(case.B) > 0.3) * 1.0
+    wg = (rng.random(case.B) > 0.3) * 1.0
+    ys = [rng.random(case.nb) * 2 for _ in range(3)]
+    st = O.OracleState(case)
+    for acc, tol in (("f64", 1e-11), ("f32", 1e-5)):
+        plans = []
+        for rank in range(2):
+            rows, D, thr, over, under = slab_of(case, rank, 2)
+            p = DosePlan(D, case.beam_ptr, thr, over, under, device=0, store="f32", acc=acc, k1_stages=3, k2_stages=4,
+                         k2_tasks=64)
+            p.set_weights(wd, wg)
+            plans.append(p)
+        for rank in range(2):
+            plans[rank].comm_attach_local(rank, plans)
+            plans[rank].comm_set_timeout(5.0)
+        seen = []
+        for k in range(6):                                   # both buffer parities, three times each
+            for p in plans:
+                p.set_intensities(ys[k % 3])
+            for p in plans:
+                p.eval_async(None, 0)
+            res = [np.concatenate([[f], g]) for f, g in (p.fetch_result() for p in plans)]
+            assert np.array_equal(res[0], res[1])            # rank order sums: identical bits on both ranks
+            f0, g0, d0, vg0, gb0 = O.calc_obj_grad_clean(st, ys[k % 3], wd, wg)
+            want = np.concatenate([[f0], g0])
+            assert np.abs(res[0] - want).max() <= tol * np.abs(want).max(), (acc, k)
+            seen.append(res[0])
+            for p in plans:
+                gb = p.beamlet_grad()
+                assert np.abs(gb - gb0).max() <= tol * np.abs(gb0).max()
+        assert np.array_equal(seen[0], seen[3]) and np.array_equal(seen[1], seen[4])
+        # a rank that evaluates alone is reported, not hung and not silently wrong
+        plans[0].comm_set_timeout(0.2)
+        with pytest.raises(VmatError, match="timed out"):
+            plans[0].eval(ys[0])
+        # ... and after attaching again the pair works as before
+        for rank in range(2):
+            plans[rank].comm_attach_local(rank, plans)
+            plans[rank].comm_set_timeout(5.0)
+        for p in plans:
+            p.set_intensities(ys[1])
+        for p in plans:
+            p.eval_async(None, 0)
+        res = [np.concatenate([[f], g]) for f, g in (p.fetch_result() for p in plans)]
+        assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], seen[1])
+        for p in plans:
+            p.close()

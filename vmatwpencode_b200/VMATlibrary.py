@@ -161,6 +161,9 @@ class vmat_class:
         self._fg = None
         self._vb_cache = {}
         self._price_static = {}
+        self.slab = None             # bind(shard=True): this rank's voxel rows (a slice); the plan holds only those
+        self.group = None
+        self.world = 1
         self._rmp_active = False     # solveRMC is running on the dense column cache
         self._gb_valid = False       # the plan's beamlet gradient belongs to the current dose
 
@@ -289,6 +292,8 @@ def bind(case, device: int = 0, store: str = "f32", acc: str = "f64", gpu: bool 
         rows, Dslab, thr, over, under = slab_of(case, rank, world)
         d.plan = DosePlan(Dslab, case.beam_ptr, thr, over, under, device=device, store=store, acc=acc, **plan_opts)
         d.slab = rows
+        d.group = group
+        d.world = world
         if world > 1:
             mine = torch.tensor(list(d.plan.comm_handle()), dtype=torch.uint8, device=f"cuda:{device}")
             allh = [torch.empty_like(mine) for _ in range(world)]
@@ -579,11 +584,22 @@ def printresults(iterationNumber, myfolder=None, Cvalue=None):
     if data.plan is None or data._fg is None:
         raise VmatError("printresults needs an evaluated plan: call data.calcDose() first")
     maxDose = data.plan.dose_max()
+    sharded = data.slab is not None and data.world > 1
+    if sharded:          # every rank holds a voxel slab: the maximum and the counts are combined over the ranks
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([maxDose], dtype=torch.float64, device=f"cuda:{data.plan.device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=data.group)
+        maxDose = float(t.item())
     dose_resln = 0.1
     dose_ub = maxDose + 10
     bin_center = np.arange(0, dose_ub, dose_resln)
     full = np.array([int(v) for v in data.fullMaskValue], dtype=np.uint64)
-    hist = data.plan.dvh_histogram(full, data.numstructs, bin_center)
+    hist = data.plan.dvh_histogram(full[data.slab] if data.slab is not None else full, data.numstructs, bin_center)
+    if sharded:
+        t = torch.as_tensor(hist, device=f"cuda:{data.plan.device}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=data.group)
+        hist = t.cpu().numpy()
     dvh_matrix = np.zeros((data.numstructs, len(bin_center)))
     for s in range(data.numstructs):
         if hist[s].sum() == 0 and not np.any(full & np.uint64(2 ** s)):
@@ -610,8 +626,14 @@ def saveResults(PIK, C, C2=1.0, C3=1.0, vmax=2.25, speedlim=0.83, RU=10.0, allNa
     thr = over = under = None
     if plan is not None:
         thr, over, under = data.case_thr, data.case_over, data.case_under
+    dose = data.currentDose
+    if data.slab is not None and data.world > 1:      # sharded: the bundle holds the whole dose, slabs in rank order
+        import torch.distributed as dist
+        parts = [None] * data.world
+        dist.all_gather_object(parts, np.asarray(dose), group=data.group)
+        dose = np.concatenate(parts)
     datasave = [data.numbeams, data.rmpres.x, C, C2, C3, vmax, speedlim, RU, RU / speedlim, M, N, data.llist, data.rlist,
-                data.fullMaskValue, data.currentDose, data.currentIntensities, data.numstructs,
+                data.fullMaskValue, dose, data.currentIntensities, data.numstructs,
                 list(allNames) if allNames is not None else [], data.objectiveValue, thr, over, under,
                 data.regionIndices, data.targets, data.oars]
     with open(PIK, "wb") as f:

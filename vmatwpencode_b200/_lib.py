@@ -62,6 +62,8 @@ SIGNATURES = {
     "vmat_reduce_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "vmat_comm_handle": (C.c_int, [_P, _P]),
     "vmat_comm_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "vmat_comm_attach_local": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "vmat_comm_set_timeout": (C.c_int, [_P, C.c_double]),
     "vmat_intensities_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "vmat_result_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "vmat_get_dose": (C.c_int, [_P, _P]),

@@ -9,6 +9,7 @@
 #include "vmat_rmp_kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -73,6 +74,9 @@ struct vmat_plan {
     DevBuf comm_buf, comm_ptrs, comm_state;
     std::vector<void*> comm_peers;        // opened IPC mappings (own slot = nullptr)
     int comm_rank = 0, comm_nranks = 1;
+    unsigned long long comm_epoch = 0;                 // fused evaluations launched so far (same on every rank)
+    unsigned long long comm_timeout_ns = 20000000000ull;
+    bool comm_ipc = false;                // peers were opened with cudaIpcOpenMemHandle (else: plain pointers)
     int host_path = 4;             // bit0: K1 reads y from mapped host memory; bit1: K3 publishes results + tags to host memory
     bool x_in_smem = true;
     bool pdl = true;               // programmatic dependent launch between the evaluation kernels
@@ -106,7 +110,7 @@ struct vmat_plan {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
         for (auto e : tev) cudaEventDestroy(e);
-        for (void* q : comm_peers) if (q) cudaIpcCloseMemHandle(q);
+        if (comm_ipc) for (void* q : comm_peers) if (q) cudaIpcCloseMemHandle(q);
         if (h_y) cudaFreeHost(h_y);
         if (h_res) cudaFreeHost(h_res);
         if (h_tags) cudaFreeHost(h_tags);
@@ -622,7 +626,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(P->partial.alloc((size_t)P->ntiles * B * as));
     CU(cudaMemset(P->partial.p, 0, (size_t)P->ntiles * B * as));
     CU(P->gbf.alloc((B + 1) * 8));     CU(cudaMemset(P->gbf.p, 0, (B + 1) * 8));
-    CU(P->result.alloc((nb + 1) * 8)); CU(cudaMemset(P->result.p, 0, (nb + 1) * 8));
+    CU(P->result.alloc((nb + 2) * 8)); CU(cudaMemset(P->result.p, 0, (nb + 2) * 8));   // f, g[nb], exchange status
     CU(P->counter.alloc(64));          CU(cudaMemset(P->counter.p, 0, 64));
     CU(P->fblock.alloc((size_t)std::max(1, P->k2_grid) * 8)); CU(cudaMemset(P->fblock.p, 0, (size_t)std::max(1, P->k2_grid) * 8));
     CU(P->scratch64.alloc(std::max<int64_t>(V, B) * 8));
@@ -634,12 +638,11 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         });
         if (rc) return VMAT_E_CUDA;
     }
-    CU(P->comm_buf.alloc((2 * (size_t)(B + 1) + 64) * 8));  CU(cudaMemset(P->comm_buf.p, 0, (2 * (size_t)(B + 1) + 64) * 8));
     CU(P->comm_state.alloc(64));         CU(cudaMemset(P->comm_state.p, 0, 64));
     CU(cudaHostAlloc(&P->h_y, nb * 8, cudaHostAllocMapped));
-    CU(cudaHostAlloc(&P->h_res, (nb + 1) * 8, cudaHostAllocMapped));
+    CU(cudaHostAlloc(&P->h_res, (nb + 2) * 8, cudaHostAllocMapped));
     CU(cudaHostAlloc(&P->h_tags, (nb + 1) * 8, cudaHostAllocMapped));
-    std::memset(P->h_y, 0, nb * 8); std::memset(P->h_res, 0, (nb + 1) * 8); std::memset(P->h_tags, 0, (nb + 1) * 8);
+    std::memset(P->h_y, 0, nb * 8); std::memset(P->h_res, 0, (nb + 2) * 8); std::memset(P->h_tags, 0, (nb + 1) * 8);
     CU(cudaHostGetDevicePointer(&P->d_hy, P->h_y, 0));
     CU(cudaHostGetDevicePointer(&P->d_hres, P->h_res, 0));
     CU(cudaHostGetDevicePointer(&P->d_htags, P->h_tags, 0));
@@ -768,8 +771,8 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
     if (P->comm_nranks > 1 && phase == 0) {
         CommArgs c{};
         c.peer_bufs = P->comm_ptrs.as<double*>(); c.rank = P->comm_rank; c.nranks = P->comm_nranks;
-        c.epoch = P->comm_state.as<unsigned long long>(); c.done = P->comm_state.as<unsigned int>() + 4;
-        c.error = P->comm_state.as<int32_t>() + 8;
+        c.epoch = ++P->comm_epoch; c.timeout_ns = P->comm_timeout_ns;
+        c.error = P->comm_state.as<int32_t>() + 8; c.status = P->result.as<double>() + P->nb + 1;
         CU(launch_pdl(k3_reduce_exchange<AT>, P->nb, 256, 0, st, P->pdl, a3, c));
         CU(cudaGetLastError());
         if (ev) CU(cudaEventRecord(ev[3], st));
@@ -840,14 +843,17 @@ extern "C" int vmat_set_intensities(vmat_plan_t* P, const double* y) {
     return VMAT_OK;
 }
 
-// A timed-out exchange returns NaN results (k3_reduce_exchange); only then is the device-side error
-// word worth a synchronous read.
+// A CTA of the fused exchange that gave up waiting for a peer sets the status word that travels
+// behind the results (result[nb+1]); it is cleared here so that the next evaluation reports afresh.
+// After a time-out this rank's caller sees an error while its peers carry on: they time out in
+// their next evaluation (nobody delivers this rank's part any more) and fail the same way.
 static int check_comm(vmat_plan* P) {
-    if (P->comm_nranks <= 1 || P->h_res[0] == P->h_res[0]) return 0;
-    int32_t st[16];
-    CU(cudaMemcpy(st, P->comm_state.p, 64, cudaMemcpyDeviceToHost));
-    if (st[8] != 0) return fail(VMAT_E_CUDA, "multi-GPU exchange timed out: a peer rank did not evaluate in lock step");
-    return 0;
+    if (P->comm_nranks <= 1 || P->h_res[P->nb + 1] == 0.0) return 0;
+    P->h_res[P->nb + 1] = 0.0;
+    CU(cudaMemsetAsync(P->result.as<double>() + P->nb + 1, 0, 8, P->stream));
+    CU(cudaMemsetAsync(P->comm_state.as<int32_t>() + 8, 0, 4, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    return fail(VMAT_E_CUDA, "multi-GPU exchange timed out: a peer rank did not evaluate in lock step");
 }
 
 extern "C" int vmat_eval(vmat_plan_t* P, const double* y, double* f, double* g) {
@@ -863,7 +869,7 @@ extern "C" int vmat_eval(vmat_plan_t* P, const double* y, double* f, double* g) 
     } else {
         if (!zc_y) CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, P->stream));
         if (int rc = launch_eval(P, P->stream, 0, !multi, inline_y)) return rc;
-        if (!zc_res) CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost, P->stream));
+        if (!zc_res) CU(cudaMemcpyAsync(P->h_res, P->result.p, (P->nb + (multi ? 2 : 1)) * 8, cudaMemcpyDeviceToHost, P->stream));
     }
     if (!zc_res) {
         CU(cudaStreamSynchronize(P->stream));
@@ -909,7 +915,7 @@ extern "C" int vmat_fetch_result(vmat_plan_t* P, double* f, double* g) {
     if (!P) return fail(VMAT_E_ARG, "null plan");
     CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(P->h_res, P->result.p, (P->nb + 1) * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(P->h_res, P->result.p, (P->nb + 2) * 8, cudaMemcpyDeviceToHost));
     if (int rc = check_comm(P)) return rc;
     if (f) *f = P->h_res[0];
     if (g) std::memcpy(g, P->h_res + 1, P->nb * 8);
@@ -979,22 +985,56 @@ extern "C" int vmat_reduce_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count
     return VMAT_OK;
 }
 
+// comm buffer: recv[2][kMaxRanks][B+1] doubles + flags[kMaxRanks][nb] u64, allocated on first use
+static int comm_buffer(vmat_plan* P) {
+    if (P->comm_buf.p) return 0;
+    const size_t bytes = (2 * (size_t)kMaxRanks * (size_t)(P->B + 1) + (size_t)kMaxRanks * P->nb) * 8;
+    CU(P->comm_buf.alloc(bytes));
+    CU(cudaMemset(P->comm_buf.p, 0, bytes));
+    return 0;
+}
+
 extern "C" int vmat_comm_handle(vmat_plan_t* P, void* handle_out) {
     if (!P || !handle_out) return fail(VMAT_E_ARG, "null");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CU(cudaSetDevice(P->device));
+    if (int rc = comm_buffer(P)) return rc;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, P->comm_buf.p));
     std::memcpy(handle_out, &h, 64);
     return VMAT_OK;
 }
 
+// common tail of the two attach entry points: `ptrs[q]` = rank q's comm buffer as seen from this device
+static int comm_finish_attach(vmat_plan* P, int32_t rank, int32_t nranks, const std::vector<double*>& ptrs) {
+    // every CTA of the reduction kernel waits for its peers' CTA of the same index, so all of them
+    // must be able to be resident at once
+    int occ = 0;
+    if (P->acc_size == 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_reduce_exchange<double>, 256, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_reduce_exchange<float>, 256, 0));
+    if ((int64_t)P->nb > (int64_t)occ * P->sm_count)
+        return fail(VMAT_E_UNSUPPORTED, "vmat_comm_attach: more control points than reduction CTAs that can be resident at once");
+    if (upload_vec(P->comm_ptrs, ptrs, P->stream)) return VMAT_E_CUDA;
+    CU(cudaMemset(P->comm_buf.p, 0, P->comm_buf.bytes));
+    CU(cudaMemset(P->comm_state.p, 0, 64));
+    CU(cudaMemset(P->result.as<double>() + P->nb + 1, 0, 8));
+    P->comm_rank = rank; P->comm_nranks = nranks; P->comm_epoch = 0;
+    // the captured graph (if any) holds the single-GPU reduction
+    if (P->graph_exec) { cudaGraphExecDestroy(P->graph_exec); P->graph_exec = nullptr; }
+    if (P->graph) { cudaGraphDestroy(P->graph); P->graph = nullptr; }
+    CU(cudaDeviceSynchronize());
+    return VMAT_OK;
+}
+
 extern "C" int vmat_comm_attach(vmat_plan_t* P, int32_t rank, int32_t nranks, const void* handles) {
-    if (!P || !handles || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return fail(VMAT_E_ARG, "vmat_comm_attach: bad argument");
+    if (!P || !handles || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
+        return fail(VMAT_E_ARG, "vmat_comm_attach: bad argument (at most 16 ranks)");
     CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());
-    for (void* q : P->comm_peers) if (q) cudaIpcCloseMemHandle(q);
+    if (int rc = comm_buffer(P)) return rc;
+    if (P->comm_ipc) for (void* q : P->comm_peers) if (q) cudaIpcCloseMemHandle(q);
     P->comm_peers.assign(nranks, nullptr);
+    P->comm_ipc = true;
     std::vector<double*> ptrs(nranks, nullptr);
     for (int q = 0; q < nranks; ++q) {
         if (q == rank) { ptrs[q] = P->comm_buf.as<double>(); continue; }
@@ -1005,14 +1045,43 @@ extern "C" int vmat_comm_attach(vmat_plan_t* P, int32_t rank, int32_t nranks, co
         P->comm_peers[q] = mapped;
         ptrs[q] = static_cast<double*>(mapped);
     }
-    if (upload_vec(P->comm_ptrs, ptrs, P->stream)) return VMAT_E_CUDA;
-    CU(cudaMemset(P->comm_buf.p, 0, P->comm_buf.bytes));
-    CU(cudaMemset(P->comm_state.p, 0, 64));
-    P->comm_rank = rank; P->comm_nranks = nranks;
-    // the captured graph (if any) holds the single-GPU reduction: rebuild it
-    if (P->graph_exec) { cudaGraphExecDestroy(P->graph_exec); P->graph_exec = nullptr; }
-    if (P->graph) { cudaGraphDestroy(P->graph); P->graph = nullptr; }
+    return comm_finish_attach(P, rank, nranks, ptrs);
+}
+
+extern "C" int vmat_comm_attach_local(vmat_plan_t* P, int32_t rank, int32_t nranks, vmat_plan_t* const* plans) {
+    if (!P || !plans || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks || plans[rank] != P)
+        return fail(VMAT_E_ARG, "vmat_comm_attach_local: bad argument (at most 16 ranks; plans[rank] must be the plan itself)");
+    for (int q = 0; q < nranks; ++q)
+        if (!plans[q] || plans[q]->B != P->B || plans[q]->nb != P->nb)
+            return fail(VMAT_E_ARG, "vmat_comm_attach_local: all plans must share the beamlet layout");
+    std::vector<double*> ptrs(nranks, nullptr);
+    for (int q = 0; q < nranks; ++q) {
+        CU(cudaSetDevice(plans[q]->device));
+        if (int rc = comm_buffer(plans[q])) return rc;
+        ptrs[q] = plans[q]->comm_buf.as<double>();
+    }
+    CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());
+    for (int q = 0; q < nranks; ++q) {
+        if (plans[q]->device == P->device) continue;
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, P->device, plans[q]->device));
+        if (!can) return fail(VMAT_E_UNSUPPORTED, "vmat_comm_attach_local: no peer access between the plans' devices");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(plans[q]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        (void)cudaGetLastError();
+    }
+    if (P->comm_ipc) for (void* q : P->comm_peers) if (q) cudaIpcCloseMemHandle(q);
+    P->comm_peers.clear();
+    P->comm_ipc = false;
+    // comm_finish_attach clears this plan's buffer only: a peer attaching later must not wipe flags this
+    // plan has already received, so all plans have to be attached before any of them evaluates
+    return comm_finish_attach(P, rank, nranks, ptrs);
+}
+
+extern "C" int vmat_comm_set_timeout(vmat_plan_t* P, double seconds) {
+    if (!P || !(seconds > 0.0)) return fail(VMAT_E_ARG, "vmat_comm_set_timeout: need a positive time");
+    P->comm_timeout_ns = (unsigned long long)(seconds * 1e9);
     return VMAT_OK;
 }
 
@@ -1023,7 +1092,7 @@ extern "C" int vmat_intensities_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* 
 }
 extern "C" int vmat_result_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count) {
     if (!P || !dev_ptr || !count) return fail(VMAT_E_ARG, "null");
-    *dev_ptr = P->result.p; *count = P->nb + 1;
+    *dev_ptr = P->result.p; *count = P->nb + 1;      // (one more word behind: the exchange status)
     return VMAT_OK;
 }
 
@@ -1072,6 +1141,27 @@ extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_bea
     CU(cudaSetDevice(P->device));
     const int32_t kmax = price_max_nodes(N);
     const size_t nrow = (size_t)ncand * M;
+    // the kernel sizes its node tables from N: every caller-supplied row descriptor must stay inside them
+    for (size_t k = 0; k < nrow; ++k) {
+        const vmat_price_row_t& R = rows[k];
+        if (R.n_l < 1 || R.n_l > N + 1 || !(R.l_first >= -1.0) || !(R.l_first + (double)(R.n_l - 1) <= (double)N))
+            return fail(VMAT_E_ARG, "vmat_price: a row has no left-leaf positions or leaves the grid (need 1 <= n_l <= N+1, -1 <= l <= N)");
+        if (R.n_r_mid < 1 || R.n_r_mid > 2 || !(R.r_hi <= (double)N) || R.vb_min < 0 || R.vb_min >= 64)
+            return fail(VMAT_E_ARG, "vmat_price: bad row descriptor (need n_r_mid in {1,2}, r_hi <= N, 0 <= vb_min < 64)");
+        if (R.vb_mask) {      // beamGrad entries the dose term may touch: [grad_offset - vb_min + lowest, ... + highest existing y]
+            const int32_t beam = cand_beam[k / M], nbl = P->beam_ptr[beam + 1] - P->beam_ptr[beam];
+            const int ylo = __builtin_ctzll(R.vb_mask), yhi = 63 - __builtin_clzll(R.vb_mask);
+            if ((int64_t)R.grad_offset - R.vb_min + ylo < 0 || (int64_t)R.grad_offset - R.vb_min + yhi >= nbl)
+                return fail(VMAT_E_ARG, "vmat_price: a row's beamlet gradient window leaves its control point");
+        }
+        int64_t total = 0;
+        for (int32_t q = 0; q < R.n_l; ++q) {
+            const double lval = R.l_first + (double)q;
+            const double r0 = std::ceil(std::fmax(lval + 1.0, R.r_lo)), r1 = std::floor(R.r_hi);
+            total += (r1 >= r0) ? (int64_t)(r1 - r0) + 1 : R.n_r_mid;
+        }
+        if (total < 1 || total > kmax) return fail(VMAT_E_ARG, "vmat_price: a row's node count exceeds the network size for this N");
+    }
     if ((size_t)ncand > P->price_cap_cand || nrow > P->price_cap_rows || nrow * kmax > P->price_cap_dad) {
         CU(P->price_cand.alloc(ncand * 4)); CU(P->price_p.alloc(ncand * 8));
         CU(P->price_rows.alloc(nrow * sizeof(vmat_price_row_t)));

@@ -643,28 +643,40 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
 }
 
 // ---------------------------------------------------------------------------------
-// K3 fused with the cross-GPU exchange (multi-GPU, one rank per GPU).  Every rank owns a
-// "comm buffer" in its HBM that all peers have mapped (CUDA IPC over NVLink):
-//     [parity 0: gb partial (B) | f partial] [parity 1: ...] [flags: one epoch counter per rank]
-// Each rank writes its local [gb | f] partial into its own buffer, publishes the evaluation's
-// epoch to every peer's flag slot (system-scope release), waits until all peers have published,
-// then every CTA reads the partials of all ranks for its beamlets straight from peer memory and
-// adds them in rank order - a one-shot all-reduce inside the reduction kernel: no NCCL launch,
-// identical bits on every rank.  Two parities make the buffer safe to rewrite in the next
-// evaluation while a slow peer may still be reading this one.
+// K3 fused with the cross-GPU exchange (multi-GPU, one rank per GPU): a push all-reduce inside
+// the reduction kernel.  Every rank owns a "comm buffer" in its HBM that all peers have mapped
+// (CUDA IPC over NVLink, or plain peer pointers inside one process):
+//     recv[parity 0..1][source rank 0..nranks-1][gb partial (B) | f partial]   doubles
+//     flags[source rank][control point 0..nb-1]                                 u64 epochs
+// CTA i (control point i) reduces this rank's tile partials for its beamlets and STORES them
+// into slot [parity][my rank] of every rank's buffer (remote stores are fire-and-forget, so the
+// NVLink latency is paid once, not once per peer), then publishes the evaluation's epoch in
+// flags[my rank][i] of every rank (system-scope release).  It then polls only its OWN flags -
+// local memory - until every rank has delivered control point i, and adds the nranks partials
+// from its own buffer in rank order: identical bits on every rank, no NCCL launch, no
+// rank-wide "last CTA" step (CTA i depends on the peers' CTA i only).  Two parities make a slot
+// safe to overwrite in the next evaluation: a rank can only be one evaluation ahead of a peer,
+// because finishing evaluation e needs every peer's push of e, which the peer issues after its
+// own reduction kernel of e-1 has completed (stream order).
 // ---------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+
 struct CommArgs {
     double* const* peer_bufs;     // [nranks] device pointers to every rank's comm buffer (own included)
     int32_t rank, nranks;
-    unsigned long long* epoch;    // completed evaluations on this rank
-    unsigned int* done;           // [2] block counters (reset by the last block)
-    int32_t* error;               // set when a peer did not show up within the time-out
+    unsigned long long epoch;     // this evaluation's epoch (1, 2, ...: counted by the host, same on all ranks)
+    unsigned long long timeout_ns;
+    int32_t* error;               // set when a peer did not deliver within the time-out
+    double* status;               // result[nb+1]: set to 1.0 by a CTA that timed out
 };
 
 __device__ __forceinline__ double ld_sys_f64(const double* p) {
     double v;
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_sys_f64(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
     unsigned long long v;
@@ -675,6 +687,45 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+// comm buffer geometry (doubles): data slot of (parity, source rank), then the flag words
+__device__ __forceinline__ size_t comm_slot(int parity, int src, int nranks, int B) {
+    return ((size_t)parity * nranks + src) * ((size_t)B + 1);
+}
+__device__ __forceinline__ unsigned long long* comm_flags(double* buf, int src, int nranks, int B, int nb) {
+    return reinterpret_cast<unsigned long long*>(buf + 2 * (size_t)nranks * ((size_t)B + 1)) + (size_t)src * nb;
+}
+
+// Publish "control point `cp` of this rank is delivered" to every rank (lanes 0..nranks-1 of the
+// calling warp; the data stores of the whole CTA must be ordered before by a CTA barrier), then wait
+// until every rank's delivery of `cp` has landed here.  Returns 0 on time-out (warp-uniform).
+__device__ __forceinline__ int comm_publish_and_wait(const CommArgs& c, int lane, int cp, int B, int nb) {
+    int ok = 1;
+    if (lane < c.nranks) {
+        __threadfence_system();
+        st_release_sys_u64(comm_flags(c.peer_bufs[lane], c.rank, c.nranks, B, nb) + cp, c.epoch);
+        const unsigned long long* mine = comm_flags(c.peer_bufs[c.rank], lane, c.nranks, B, nb) + cp;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
+        while (ld_acquire_sys_u64(mine) < c.epoch) {
+            if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > c.timeout_ns) { ok = 0; break; }
+        }
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
+// sum over the ranks, in rank order, of entry j of the (parity, rank) slots of this rank's own buffer
+__device__ __forceinline__ double comm_sum_ranks(const double* mybuf, int parity, int nranks, int B, size_t j) {
+    double v[kMaxRanks];
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+        if (q < nranks) v[q] = ld_sys_f64(mybuf + comm_slot(parity, q, nranks, B) + j);
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+        if (q < nranks) s += v[q];
+    return s;
+}
+
 template <typename AT>
 __global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, const CommArgs c) {
     __shared__ double sh[256];
@@ -683,53 +734,38 @@ __global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, co
     pdl_launch_dependents();
     const int lo = a.beam_ptr[blockIdx.x], hi = a.beam_ptr[blockIdx.x + 1];
     pdl_wait();
-    const unsigned long long e = *c.epoch + 1;
-    const size_t stride = (size_t)a.B + 1;
-    const size_t par_off = (size_t)(e & 1ull) * stride;
-    double* mine = c.peer_bufs[c.rank] + par_off;
-    // ---- A: this rank's partial for my beamlets (and the objective) into my comm buffer
+    const int parity = (int)(c.epoch & 1ull);
+    const size_t slot = comm_slot(parity, c.rank, c.nranks, a.B);
+    // ---- A: this rank's partial for my beamlets (and the objective), pushed to every rank
     if (blockIdx.x == 0) {
         double fv = strided_sum(a.fblock, tid, 256, a.nfblock);
         fv = block_sum_256(fv, sh);
-        if (tid == 0) mine[a.B] = fv;
+        if (tid < c.nranks) st_sys_f64(c.peer_bufs[tid] + slot + a.B, fv);
     }
     for (int j0 = lo; j0 < hi; j0 += 64) {
         const int j = j0 + (tid >> 2), q = tid & 3;
         double s = 0.0;
         if (j < hi) s = strided_sum(a.partial + j, (int64_t)q * a.B, (int64_t)4 * a.B, (int64_t)a.ntiles * a.B);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (j < hi && q == 0) mine[j] = s;
+        s += __shfl_xor_sync(0xffffffffu, s, 2);       // all four lanes hold the sum: lane q serves ranks q, q+4, ...
+        if (j < hi) for (int p = q; p < c.nranks; p += 4) st_sys_f64(c.peer_bufs[p] + slot + j, s);
     }
     __syncthreads();
-    // ---- B: the last CTA publishes this rank's epoch to every peer; everybody waits for all peers
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(&c.done[0], 1u) == gridDim.x - 1) {
-            __threadfence_system();
-            for (int q = 0; q < c.nranks; ++q) {
-                unsigned long long* flags = reinterpret_cast<unsigned long long*>(c.peer_bufs[q] + 2 * stride);
-                st_release_sys_u64(flags + c.rank, e);
-            }
+    // ---- B: publish, then wait for every rank's delivery of this control point (own memory only)
+    if (tid < 32) {
+        const int ok = comm_publish_and_wait(c, tid, blockIdx.x, a.B, a.nb);
+        if (tid == 0) {
+            ok_s = ok;
+            if (!ok) { atomicExch(c.error, 1); *c.status = 1.0; }
         }
-        const unsigned long long* myflags = reinterpret_cast<const unsigned long long*>(c.peer_bufs[c.rank] + 2 * stride);
-        int ok = 1;
-        const long long t0 = clock64();
-        for (int q = 0; q < c.nranks && ok; ++q) {
-            while (ld_acquire_sys_u64(myflags + q) < e) {
-                if (clock64() - t0 > 4000000000ll) { ok = 0; break; }      // ~2 s: a peer is gone
-            }
-        }
-        if (!ok) *c.error = 1;
-        ok_s = ok;
     }
     __syncthreads();
-    // ---- C: sum the partials of all ranks, in rank order, straight from peer memory
+    // ---- C: add the ranks' partials in rank order
+    const double* mybuf = c.peer_bufs[c.rank];
     double contrib = 0.0;
     if (ok_s) {
         for (int j = lo + tid; j < hi; j += 256) {
-            double s = 0.0;
-            for (int q = 0; q < c.nranks; ++q) s += ld_sys_f64(c.peer_bufs[q] + par_off + j);
+            const double s = comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)j);
             a.gbf[j] = s;
             contrib += a.w_grad[j] * s;
         }
@@ -737,18 +773,9 @@ __global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, co
     const double g = block_sum_256(contrib, sh);
     if (tid == 0) a.result[1 + blockIdx.x] = ok_s ? g : nan("");
     if (blockIdx.x == 0 && tid == 0) {
-        double f = 0.0;
-        for (int q = 0; q < c.nranks; ++q) f += ld_sys_f64(c.peer_bufs[q] + par_off + a.B);
+        const double f = ok_s ? comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)a.B) : nan("");
         a.gbf[a.B] = f;
-        a.result[0] = ok_s ? f : nan("");
-    }
-    // ---- the last CTA to leave closes the evaluation
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(&c.done[1], 1u) == gridDim.x - 1) {
-            *c.epoch = e;
-            c.done[0] = 0u; c.done[1] = 0u;
-        }
+        a.result[0] = f;
     }
 }
 

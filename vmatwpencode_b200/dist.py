@@ -14,15 +14,20 @@ import numpy as np
 
 def partition_voxels(indptr, nparts: int):
     """Slab boundaries [v_0=0, ..., v_nparts=V] with ~equal nonzeros per slab, multiples of 32
-    (so slabs keep whole slices) except the last."""
+    (so slabs keep whole slices) except the last.  Every slab gets at least 32 voxels: a case too small
+    for that raises here, on every rank alike and before any collective, instead of leaving one rank
+    with an empty plan while its peers wait in a barrier."""
     indptr = np.asarray(indptr, dtype=np.int64)
     V = len(indptr) - 1
+    if V < 32 * nparts:
+        raise ValueError(f"{V} voxels cannot be sharded over {nparts} ranks (at least 32 voxels per slab)")
     nnz = int(indptr[-1])
     bounds = [0]
     for k in range(1, nparts):
         target = nnz * k // nparts
         v = int(np.searchsorted(indptr, target, side="left"))
-        v = min(V, max(bounds[-1], (v + 16) // 32 * 32))
+        v = (v + 16) // 32 * 32
+        v = max(bounds[-1] + 32, min(v, (V - 32 * (nparts - k)) // 32 * 32))
         bounds.append(v)
     bounds.append(V)
     return bounds
@@ -71,6 +76,8 @@ class ShardedEvaluator:
         self.engine.eval_async(stream, 2)                 # aperture gradient from the summed gb
 
     def eval(self, y, stream=None):
+        if stream is None and (self.world == 1 or self.fused) and hasattr(self.engine, "eval"):
+            return self.engine.eval(y)                    # host buffers in and out, one synchronisation (vmat_eval)
         self.engine.set_intensities(y)
         self.eval_async(stream)
         return self.engine.fetch_result()

@@ -2,6 +2,14 @@
 the GPU.  Same three functions; `ba` may be the reference's 1-D list of beam-angle positions
 or an (n, d) array of coordinates (the voxel-sampling use of BASELINE.json's north star).
 
+Index semantics.  `kappa` holds ROW indices of the distance matrix, i.e. positions in `ba`.  The
+reference takes its candidates from ``listdiff(ba, kappa)`` - the VALUES of `ba` - and uses those
+values as row indices too (kmedoids.py:50-53), which only works when the values of a 1-D `ba` are
+integers in [0, len(ba)).  That is reproduced: for a 1-D `ba` the candidates are its values, visited in
+`ba`'s order (the first best wins, so the order matters), and candidate value i stands for the point
+``ba[i]``; values that cannot index the points raise IndexError as they do there.  For an (n, d)
+coordinate array (no counterpart in the reference) the candidates are the points 0..n-1 in order.
+
 The reference rebuilds the full pairwise distance matrix for every candidate (O(n^4) for a
 whole ordering); here one kernel launch prices all candidates of an insertion step against
 the running nearest-medoid distance.  Sums run in the reference's left-to-right order for
@@ -59,16 +67,38 @@ def _sharded_costs(P, cur, device, group):
     return t.cpu().numpy()
 
 
+def _candidate_order(kappa, ba, n):
+    """None when the candidates are simply the points 0..n-1 in order; else the list of candidate row indices in
+    the order the reference visits them (the values of a 1-D `ba`)."""
+    a = np.asarray(ba)
+    if a.ndim != 1:
+        return None
+    if a.shape[0] == n and np.array_equal(a, np.arange(n)):
+        return None
+    vals = [v for v in a.tolist()]
+    for v in vals:
+        if int(v) != v or not 0 <= int(v) < n:
+            raise IndexError(f"kmedoids: value {v} of a 1-D point list cannot index its {n} points "
+                             "(the reference uses the values of ba as row indices)")
+    return [int(v) for v in vals]
+
+
 def insertnewelement(kappa, ba, device: int = 0, _state=None, group=None):
     """Append the candidate that minimises distancemin; the first best wins (kmedoids.py:48-60).
     With a torch.distributed `group` the distance pass is sharded over the points."""
     P = _points(ba) if _state is None else _state["P"]
     cur = _nearest(P, kappa) if _state is None else _state["cur"]
     cost = kmedoid_costs(P, cur, device) if group is None else _sharded_costs(P, cur, device, group)
-    taken = np.zeros(P.shape[0], dtype=bool)
-    taken[list(kappa)] = True
-    cost = np.where(taken, np.inf, cost)
-    best = int(np.argmin(cost))          # first minimum == strict "<" scan in candidate order
+    order = _candidate_order(kappa, ba, P.shape[0]) if _state is None else _state["order"]
+    if order is None:
+        taken = np.zeros(P.shape[0], dtype=bool)
+        taken[list(kappa)] = True
+        cost = np.where(taken, np.inf, cost)
+        best = int(np.argmin(cost))          # first minimum == strict "<" scan in candidate order
+    else:                                    # 1-D ba that is not 0..n-1: candidates are its values, in its order
+        in_kappa = set(kappa)
+        cands = [c for c in order if c not in in_kappa]
+        best = cands[int(np.argmin(cost[cands]))]
     kappa.append(best)
     if _state is not None:
         diff = P - P[best]
@@ -81,7 +111,7 @@ def givemewholelist(kappa, ba, device: int = 0, group=None, limit=None):
     many medoids (voxel subsampling wants the first k, not the whole ordering)."""
     kappa = list(kappa)
     P = _points(ba)
-    state = {"P": P, "cur": _nearest(P, kappa)}
+    state = {"P": P, "cur": _nearest(P, kappa), "order": _candidate_order(kappa, ba, P.shape[0])}
     stop = P.shape[0] if limit is None else min(limit, P.shape[0])
     while len(kappa) < stop:
         kappa = insertnewelement(kappa, ba, device, state, group)

@@ -206,6 +206,16 @@ class DosePlan:
         check(self._lib.vmat_comm_attach(self._h, rank, nranks, buf), "vmat_comm_attach")
         self.fused_exchange = nranks > 1
 
+    def comm_attach_local(self, rank: int, plans):
+        """Same as comm_attach for plans of this process (`plans[rank] is self`): same device (tests) or
+        devices with peer access."""
+        arr = (C.c_void_p * len(plans))(*[p._h.value for p in plans])
+        check(self._lib.vmat_comm_attach_local(self._h, rank, len(plans), arr), "vmat_comm_attach_local")
+        self.fused_exchange = len(plans) > 1
+
+    def comm_set_timeout(self, seconds: float):
+        check(self._lib.vmat_comm_set_timeout(self._h, float(seconds)), "vmat_comm_set_timeout")
+
     def _device_view(self, fn):
         import torch
         p, n = C.c_void_p(), C.c_int64()
