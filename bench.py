@@ -372,6 +372,7 @@ def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, h
                            "inside the dose kernel's launch parameters (a 1.4 KB H2D copy when nb > 384), f and g "
                            "(nb+1 f64) come back with one D2H copy into pinned memory and one stream synchronisation"},
             "plan": {"nnz_this_rank": nnz_local, "store_dtype": args.store, "acc_dtype": args.acc, "index_bytes": si,
+                     "kernels_per_eval": info["launches_per_eval"],
                      "sharding": f"voxel slabs x{world}", "exchange": "push all-reduce fused into the reduction kernel "
                      "(NVLink peer memory)" if world > 1 else "none",
                      "l2": ("both layouts of this rank's slab (2 x %.0f MB) FIT the 126 MB L2: steps after the first "
@@ -387,6 +388,8 @@ def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, h
             k2_bytes = nnz_local * (sv + si) + 4 * plan.V + 4 * (plan.B + 1) + 4 * plan.B
             kname, kms, kb = ("k2_beamlet_grad", kt["k2_ms"], k2_bytes) if kt["k2_ms"] >= kt["k1_ms"] else \
                              ("k1_dose_penalty", kt["k1_ms"], k1_bytes)
+            if info["launches_per_eval"] == 1:      # the whole evaluation is one kernel: its bytes are the evaluation's
+                kname, kms, kb = "kf_eval", kt["eval_ms"], info["algorithmic_bytes_per_eval"]
             ach = kb / (kms * 1e-3) / 1e9
             traffic = None      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
             tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
@@ -434,6 +437,7 @@ def main():
     ap.add_argument("--index-bytes", type=int, default=0, help="4 forces int32 column indices (default: uint16 when they fit)")
     ap.add_argument("--claim-lead", type=int, default=0, help="dose kernel: stages before a super-slice's end at which the next is claimed (tuning; 0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fused", type=int, default=0, help="0 = fused evaluation kernel when it fits, 1 = the three kernels, 2 = fused or fail")
     ap.add_argument("--largest", default="cfg4", help="workload of the `largest_case` block ('none' skips it)")
     ap.add_argument("--largest-steps", type=int, default=200)
     args = ap.parse_args()
@@ -454,7 +458,7 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
     opts = dict(tile_voxels=args.tile, k2_tasks=args.k2_tasks, k2_threads=args.k2_threads, k1_threads=args.k1_threads,
-                index_bytes=args.index_bytes, claim_lead=args.claim_lead)
+                index_bytes=args.index_bytes, claim_lead=args.claim_lead, fused=args.fused)
     # a side stream: the library treats stream 0 as "use the plan's own stream", and the CUDA
     # events must sit on the stream the kernels are launched on
     side = torch.cuda.Stream()

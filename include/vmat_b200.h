@@ -54,7 +54,10 @@ typedef struct vmat_options {
                                    4 y inside the launch parameters (default), 8 none (copy nodes)
                                [5] 4 = int32 column indices, 1 = byte deltas (default: uint16 whenever they fit)
                                [6] stages before a super-slice's end at which the dose kernel claims the next
-                               [8] unused */
+                               [8] evaluation kernels: 0 = one fused persistent kernel (dose, transposed product,
+                                   reductions and exchange in a single launch) whenever its shared-memory budget
+                                   works out, 1 = the three kernels K1/K2/K3, 2 = fused or fail;
+                                   with the fused kernel k2_tasks is the grid size (default: one CTA per SM) */
 } vmat_options_t;
 
 /* Library / build identification. */

@@ -119,12 +119,13 @@ def random_weights(case, rng, frac_selected=0.5):
     dict(V=33, nb=2, M=1, N=3, density=0.3, seed=63),                       # tiny
     dict(V=20_000, nb=10, M=4, N=6, density=0.002, seed=64, model="uniform"),   # many empty voxel rows
 ])
-def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol):
+@pytest.mark.parametrize("fused", [2, 1])          # 2: the single fused evaluation kernel, 1: the three kernels K1/K2/K3
+def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol, fused):
     case = make_case(val_dtype=val_dtype, **shape)
     st = O.OracleState(case)
     rng = np.random.default_rng(shape["seed"])
     plan = DosePlan(case.D, case.beam_ptr, case.thr, case.over, case.under, store=store, acc=acc,
-                    tile_voxels=4096 if shape["V"] > 10_000 else 64)
+                    tile_voxels=4096 if shape["V"] > 10_000 else 64, fused=fused)
     for trial in range(3):
         y, w_dose, w_grad = random_weights(case, rng, frac_selected=[0.5, 1.0, 0.0][trial])
         plan.set_weights(w_dose, w_grad)
@@ -144,7 +145,14 @@ def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol):
                                   dict(k2_chunk_cap=1, k2_tasks=5), dict(k2_chunk_cap=3, tile_voxels=128), dict(claim_lead=1), dict(claim_lead=100),
                                   dict(k2_threads=256, k2_stages=6), dict(k2_threads=512, k2_stages=4, tile_voxels=256),
                                   dict(index_bytes=1), dict(index_bytes=1, chunk_cap=2, k2_chunk_cap=3), dict(index_bytes=1, tile_voxels=64, k2_tasks=7),
-                                  dict(index_bytes=1, k1_threads=128, k2_threads=256)])
+                                  dict(index_bytes=1, k1_threads=128, k2_threads=256),
+                                  # the fused evaluation kernel: grid sizes (fewer CTAs than control points, one CTA), short
+                                  # rings, one-chunk items, tiny tiles (many groups, tile buffers change with every item)
+                                  dict(fused=2), dict(fused=2, k2_tasks=3), dict(fused=2, k2_tasks=1, k1_stages=2),
+                                  dict(fused=2, k1_stages=3, tile_voxels=64, k2_tasks=5), dict(fused=2, chunk_cap=1, k2_chunk_cap=1),
+                                  dict(fused=2, chunk_cap=1000, k2_chunk_cap=1000, tile_voxels=128), dict(fused=2, index_bytes=4, claim_lead=1),
+                                  dict(fused=2, pdl=False, use_graph=False), dict(fused=2, tile_voxels=64, claim_lead=100, k2_tasks=200),
+                                  dict(fused=1), dict(fused=1, k2_tasks=7, tile_voxels=64)])
 def test_plan_options_do_not_change_results(opts):
     case = make_case(V=9000, nb=8, M=4, N=6, density=0.02, seed=71)
     st = O.OracleState(case)

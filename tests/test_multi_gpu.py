@@ -163,12 +163,16 @@ def test_fused_exchange_two_ranks_on_one_device():
     wg = (rng.random(case.B) > 0.3) * 1.0
     ys = [rng.random(case.nb) * 2 for _ in range(3)]
     st = O.OracleState(case)
-    for acc, tol in (("f64", 1e-11), ("f32", 1e-5)):
+    # three-kernel path (the exchange sits in the small reduction kernel) and the fused evaluation kernel with
+    # grids of 60 CTAs, so that both "ranks" fit on the 148 SMs at once
+    for acc, tol, opts in (("f64", 1e-11, dict(fused=1, k1_stages=3, k2_stages=4, k2_tasks=64)),
+                           ("f32", 1e-5, dict(fused=1, k1_stages=3, k2_stages=4, k2_tasks=64)),
+                           ("f64", 1e-11, dict(fused=2, k1_stages=4, k2_tasks=60)),
+                           ("f32", 1e-5, dict(fused=2, k1_stages=4, k2_tasks=60))):
         plans = []
         for rank in range(2):
             rows, D, thr, over, under = slab_of(case, rank, 2)
-            p = DosePlan(D, case.beam_ptr, thr, over, under, device=0, store="f32", acc=acc, k1_stages=3, k2_stages=4,
-                         k2_tasks=64)
+            p = DosePlan(D, case.beam_ptr, thr, over, under, device=0, store="f32", acc=acc, **opts)
             p.set_weights(wd, wg)
             plans.append(p)
         for rank in range(2):

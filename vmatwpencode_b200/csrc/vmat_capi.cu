@@ -4,6 +4,7 @@
 // host-buffer path), result transfer, cross-GPU exchange set-up, pricing, RMP column cache, DVH.
 #include "../../include/vmat_b200.h"
 #include "vmat_eval_kernels.cuh"
+#include "vmat_fused_kernel.cuh"
 #include "vmat_price_kernels.cuh"
 #include "vmat_kmedoid_kernels.cuh"
 #include "vmat_rmp_kernels.cuh"
@@ -62,6 +63,11 @@ struct vmat_plan {
     int k2_grid = 1;
     int32_t nslices2 = 0, nss2 = 0, ntasks2 = 0, ntiles = 0, T = 0, W2 = 4, nstages2 = 8, stage_bytes2 = 0;
     int64_t units2 = 0;
+    // fused single-kernel evaluation (vmat_fused_kernel.cuh): both streams ragged, W = 16, one item queue
+    bool fused = false;
+    DevBuf itemsF, syncF;
+    int32_t nF1 = 0, nF = 0, nstagesF = 0, stage_bytesF = 0, ngroupsF = 0, gridF = 0;
+    size_t smemF = 0;
     // state
     DevBuf y, beam_of, beam_ptr_d, w_dose, w_grad, xg, d, vg, fpart, fblock, partial, gbf, result, counter, scratch64;
     double* h_y = nullptr;       // pinned + mapped: K1 reads it directly on the host-buffer path
@@ -177,7 +183,8 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
                         const std::vector<int64_t>& seg_start,
                         const std::vector<int32_t>& seg_len, const std::vector<int32_t>& seg_colbase,
                         const std::vector<int32_t>& rows, const DevBuf* thr, const DevBuf* over, const DevBuf* under,
-                        int32_t es, const int32_t* d_col, const void* d_val, DevBuf& sell, DevBuf& off_d, DevBuf& tpr_d) {
+                        int32_t es, const int32_t* d_col, const void* d_val, DevBuf& sell, DevBuf& off_d, DevBuf& tpr_d,
+                        const std::vector<uint8_t>* ss_nch = nullptr) {
     const int32_t nslices = (int32_t)(rows.size() / 32);
     const int64_t units = ss_off.back();
     CU(sell.alloc((size_t)units * 16));
@@ -185,7 +192,9 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
     if (upload_vec(off_d, ss_off, P->stream)) return VMAT_E_CUDA;
     if (upload_vec(tpr_d, ss_tpr, P->stream)) return VMAT_E_CUDA;
     if (nslices == 0) return 0;
-    DevBuf dstart, dlen, dcb, drows;
+    DevBuf dstart, dlen, dcb, drows, dnch;
+    if (ss_nch && upload_vec(dnch, *ss_nch, P->stream)) return VMAT_E_CUDA;
+    const uint8_t* nchp = ss_nch ? dnch.as<uint8_t>() : nullptr;
     if (upload_vec(dstart, seg_start, P->stream)) return VMAT_E_CUDA;
     if (upload_vec(dlen, seg_len, P->stream)) return VMAT_E_CUDA;
     if (upload_vec(dcb, seg_colbase, P->stream)) return VMAT_E_CUDA;
@@ -199,11 +208,11 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
         if (src_dtype == VMAT_F32)
             k_fill_stream<VT, float, IW><<<(unsigned)blocks, threads, 0, P->stream>>>(
                 nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
-                tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const float*>(d_val), sell.as<uint4>());
+                tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const float*>(d_val), sell.as<uint4>(), nchp);
         else
             k_fill_stream<VT, double, IW><<<(unsigned)blocks, threads, 0, P->stream>>>(
                 nslices, W, HU, off_d.as<int64_t>(), dstart.as<int64_t>(), dlen.as<int32_t>(), dcb.as<int32_t>(),
-                tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const double*>(d_val), sell.as<uint4>());
+                tpr_d.as<uint8_t>(), drows.as<int32_t>(), t0, t1, t2, es, d_col, static_cast<const double*>(d_val), sell.as<uint4>(), nchp);
     }); });
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(P->stream));
@@ -214,6 +223,9 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
 // lanes per row, where tpr is the smallest power of two that keeps the slice within `cap` chunks.
 struct StreamDesc {
     int32_t W, HU, units, cap;
+    bool ragged = false;                          // fused kernel: every slice keeps its own chunk count
+    bool too_long = false;                        // ragged: a row needs more than 255 chunks per lane
+    std::vector<uint8_t> ss_nch;                  // [nss * W] (ragged only)
     std::vector<int64_t> ss_off{0}, seg_start;
     std::vector<uint8_t> ss_tpr;
     std::vector<int32_t> seg_len, seg_cb, rows, ss_tile;
@@ -231,7 +243,7 @@ struct StreamDesc {
             while ((nch1 + tpr - 1) / tpr > cap && tpr < 32) tpr *= 2;
             const int64_t nch = (nch1 + tpr - 1) / tpr;
             const size_t rows_per_slice = 32 / tpr, rows_per_ss = rows_per_slice * W;
-            const size_t base_slot = seg_start.size();
+            const size_t base_slot = seg_start.size(), first_item = pos;
             seg_start.resize(base_slot + (size_t)32 * W, 0);
             seg_len.resize(base_slot + (size_t)32 * W, 0);
             seg_cb.resize(base_slot + (size_t)32 * W, 0);
@@ -252,7 +264,20 @@ struct StreamDesc {
             ss_tpr.push_back((uint8_t)tpr);
             ss_tile.push_back(tile);
             ss_cost.push_back(nch + 1);
-            ss_off.push_back(ss_off.back() + (int64_t)W * HU + nch * (int64_t)W * units);
+            if (ragged) {     // the first row of a slice is its longest (items are sorted by length)
+                int64_t chunks = 0;
+                for (size_t w = 0; w < (size_t)W; ++w) {
+                    const size_t p0 = first_item + w * rows_per_slice;
+                    const int64_t n1w = p0 < items.size() ? (items[p0].len + 3) / 4 : 0;
+                    const int64_t nw = (n1w + tpr - 1) / tpr;
+                    if (nw > 255) too_long = true;         // chunk counts travel as bytes
+                    ss_nch.push_back((uint8_t)nw);
+                    chunks += nw;
+                }
+                ss_off.push_back(ss_off.back() + (int64_t)W * HU + chunks * (int64_t)units);
+            } else {
+                ss_off.push_back(ss_off.back() + (int64_t)W * HU + nch * (int64_t)W * units);
+            }
         }
     }
 };
@@ -340,6 +365,26 @@ static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaS
     return cudaLaunchKernelEx(&cfg, kern, arg, rest...);
 }
 
+#define DISPATCH_IWF(IW, ...)                                                \
+    if (P->iw == 2) { constexpr int IW = 2; __VA_ARGS__; } else { constexpr int IW = 4; __VA_ARGS__; }
+
+template <typename VT, typename AT>
+static int fused_occupancy_t(vmat_plan* P, int* occ) {
+    DISPATCH_IWF(IW, {
+        auto kern = kf_eval<VT, AT, IW>;
+        CU(allow_max_smem(kern, P->smem_optin));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kFThreads, P->smemF));
+    });
+    if (*occ < 1) return fail(VMAT_E_ARG, "fused evaluation kernel does not fit on an SM with these options");
+    return 0;
+}
+static int fused_occupancy(vmat_plan* P, int* occ) {
+    DISPATCH_STORE(P->opt.store_dtype, VT, {
+        DISPATCH_ACC(P->opt.acc_dtype, AT, { return fused_occupancy_t<VT, AT>(P, occ); });
+    });
+    return 0;
+}
+
 static int capture_graph(vmat_plan* P);
 static int launch_eval(vmat_plan* P, cudaStream_t st, int phase, bool host_mode = false, bool inline_y = false);
 
@@ -395,6 +440,32 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         P->W1 = (P->opt.k1_threads > 0 && P->opt.k1_threads < 512 && fits2) ? 4 : 16;
     }
 
+    // ---- one fused kernel or the three-kernel path --------------------------------------------------
+    // reserved[8]: 0 = the fused kernel whenever its shared-memory budget works out (x + y or two vg tiles
+    // next to at least 6 ring stages of 16 warps), 1 = the three kernels K1/K2/K3, 2 = fused or fail
+    int32_t T_plan = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
+    T_plan = (T_plan + 63) / 64 * 64;
+    {
+        const size_t as0 = P->acc_size;
+        const size_t xy = (((size_t)B * as0 + 127) & ~(size_t)127) + (((size_t)nb * 8 + 127) & ~(size_t)127);
+        const size_t tb = ((size_t)T_plan * as0 + 127) & ~(size_t)127;
+        const size_t U = std::max(xy, 2 * tb);
+        const int hu1 = 8 + 3 * (32 * (int)as0 / 16), hu2 = 8;
+        const size_t SB = (size_t)kFW * std::max<int>(store_units(P->opt.store_dtype, P->iw), std::max(hu1, hu2)) * 16;
+        const size_t room = (size_t)P->smem_optin > U + 2048 ? (size_t)P->smem_optin - U - 2048 : 0;
+        int nst = (int)std::min<size_t>(kFMaxStages, room / SB);
+        if (P->opt.reserved[0] > 0) nst = std::min(nst, std::max(2, P->opt.reserved[0]));
+        const bool can = P->iw != 1 && nst >= (P->opt.reserved[0] > 0 ? 2 : 6);
+        const int mode = P->opt.reserved[8];
+        if (mode == 2 && !can) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel does not fit this plan (beamlet vector too large for shared memory, or byte-delta indices)");
+        P->fused = can && mode != 1;
+        if (P->fused) {
+            P->W1 = kFW;
+            P->nstagesF = nst; P->stage_bytesF = (int32_t)SB;
+            P->smemF = U + (size_t)nst * SB;
+        }
+    }
+
     // ---- bring row pointers to the host, CSR payload to the device ----------------
     std::vector<int64_t> h_vrow(V + 1), h_brow(B + 1);
     const cudaMemcpyKind to_host = location == VMAT_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
@@ -424,6 +495,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     }
 
     DevBuf csr_flag, up_vrow;
+    std::vector<uint8_t> fused_nch1, fused_tpr1;          // fused plans: per dose item chunk counts, lanes per row,
+    std::vector<int32_t> fused_grp1, fused_grp_items;     // group, and the number of dose items per group
+    int32_t fused_grp_tiles = 1;
     std::vector<int32_t> vpads;            // per voxel row (byte-delta layout only)
     CU(csr_flag.alloc(4)); CU(cudaMemsetAsync(csr_flag.p, 0, 4, st));
     auto check_csr = [&](int64_t nrows, int64_t ncols, int sorted, const int64_t* d_rowptr, const int32_t* d_col,
@@ -473,14 +547,36 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - slots[v]]++] = (int32_t)v;
         }
         const int32_t W = P->W1, HU = 8 + 3 * (32 * es / 16) + header_base_units(P->iw);
-        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2] : kChunkCapK1;
-        StreamDesc sd{W, HU, units, cap};
+        // fused kernel: 16-warp stages per CTA if the work were spread evenly; small slabs get finer items
+        const int64_t per_cta = nnz / 2048 / std::max(1, P->sm_count);
+        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2]
+                          : P->fused ? (int32_t)std::min<int64_t>(kChunkCapK1, std::max<int64_t>(12, per_cta / 2)) : kChunkCapK1;
+        StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
+        sd.ragged = P->fused;
         std::vector<StreamDesc::Item> items(V);
         for (int64_t pos = 0; pos < V; ++pos) {
             const int32_t v = order[pos];
             items[pos] = StreamDesc::Item{slots[v], v, h_vrow[v], (int32_t)(h_vrow[v + 1] - h_vrow[v])};
         }
-        sd.add_group(items, 0, 0, thr, over, under);
+        if (!P->fused) {
+            sd.add_group(items, 0, 0, thr, over, under);
+        } else {
+            // groups of consecutive tiles: a transposed item of tile t can start as soon as the dose items of
+            // group(t) are done; inside a group the rows stay sorted by length
+            const int32_t nt = (int32_t)((V + T_plan - 1) / T_plan);
+            const int32_t gt = (nt + 11) / 12;                          // tiles per group: about 12 groups
+            const int32_t ng = (nt + gt - 1) / gt;
+            std::vector<std::vector<StreamDesc::Item>> by_group(ng);
+            for (const auto& it : items) by_group[it.id / T_plan / gt].push_back(it);
+            fused_grp_tiles = gt; P->ngroupsF = ng;
+            for (int32_t g = 0; g < ng; ++g) {
+                const size_t before = sd.ss_tpr.size();
+                sd.add_group(by_group[g], 0, g, thr, over, under);       // ss_tile carries the group here
+                fused_grp_items.push_back((int32_t)(sd.ss_tpr.size() - before));
+            }
+            fused_nch1 = sd.ss_nch; fused_tpr1 = sd.ss_tpr; fused_grp1 = sd.ss_tile;
+            if (sd.too_long) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel: a voxel row has more than 32 640 nonzeros (use reserved[8] = 1)");
+        }
         const int32_t nss = (int32_t)sd.ss_tpr.size();
         P->nslices1 = nss * W; P->nss1 = nss; P->W1 = W; P->units1 = sd.ss_off.back();
         DevBuf thr_s, over_s, under_s;
@@ -493,7 +589,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         if (rc) return VMAT_E_CUDA;
         if (int rc2 = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, sd.ss_off, sd.ss_tpr, sd.seg_start, sd.seg_len,
                                    sd.seg_cb, sd.rows, &thr_s, &over_s, &under_s, es, d_vcol, d_vval,
-                                   P->sell1, P->off1, P->tpr1)) return rc2;
+                                   P->sell1, P->off1, P->tpr1, P->fused ? &sd.ss_nch : nullptr)) return rc2;
         P->stage_bytes1 = W * std::max<int>(units, HU) * 16;
     }
     up_vcol.alloc(0); up_vval.alloc(0);   // release the voxel-major CSR copy
@@ -509,15 +605,14 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
     // ---- K2 layout: column tiles of T voxels; per tile, beamlet segments sorted by length
     {
-        int32_t T = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
-        T = (T + 63) / 64 * 64;
-        const int32_t W = P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = header_units_k2(P->iw);
+        const int32_t T = T_plan;
+        const int32_t W = P->fused ? kFW : P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = header_units_k2(P->iw);
         P->W2 = W;
         P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
         P->nstages2 = P->opt.reserved[1] > 0 ? std::max(2, std::min(16, P->opt.reserved[1])) : 8;
         const size_t tile_bytes = ((size_t)T * P->acc_size + 127) & ~(size_t)127;
         P->k2_smem = tile_bytes + (size_t)P->nstages2 * P->stage_bytes2;
-        if (P->k2_smem + 2048 > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
+        if (!P->fused && P->k2_smem + 2048 > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
         const int32_t nt = (int32_t)((V + T - 1) / T);
         P->T = T; P->ntiles = nt;
         DevBuf d_seg;
@@ -541,8 +636,11 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         CU(cudaStreamSynchronize(st));
         d_seg.alloc(0);
 
-        const int32_t cap = P->opt.reserved[7] > 0 ? P->opt.reserved[7] : kChunkCapK2;
-        StreamDesc sd{W, HU, units, cap};
+        const int64_t per_cta2 = nnz / 2048 / std::max(1, P->sm_count);
+        const int32_t cap = P->opt.reserved[7] > 0 ? P->opt.reserved[7]
+                          : P->fused ? (int32_t)std::min<int64_t>(48, std::max<int64_t>(8, per_cta2 / 4)) : kChunkCapK2;
+        StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
+        sd.ragged = P->fused;
         std::vector<StreamDesc::Item> items;
         for (int32_t t = 0; t < nt; ++t) {
             items.clear();
@@ -557,6 +655,31 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const std::vector<int64_t>& ss_cost = sd.ss_cost;
         const std::vector<int32_t>& ss_tile = sd.ss_tile;
         P->nss2 = (int32_t)ss_cost.size(); P->nslices2 = P->nss2 * W; P->units2 = sd.ss_off.back();
+        if (P->fused) {
+            if (sd.too_long) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel: a beamlet segment has more than 32 640 nonzeros (use reserved[8] = 1)");
+            // the queue: dose items (group order), then transposed items (tile order)
+            std::vector<FItem> fi((size_t)P->nss1 + P->nss2);
+            for (int32_t i = 0; i < P->nss1; ++i) {
+                FItem& f = fi[i];
+                std::memset(&f, 0, sizeof(f));
+                for (int w = 0; w < kFW; ++w) f.nch[w] = fused_nch1[(size_t)i * kFW + w];
+                f.tile = -1; f.grp = fused_grp1[i]; f.need = 0; f.tpr = fused_tpr1[i];
+            }
+            for (int32_t i = 0; i < P->nss2; ++i) {
+                FItem& f = fi[(size_t)P->nss1 + i];
+                std::memset(&f, 0, sizeof(f));
+                for (int w = 0; w < kFW; ++w) f.nch[w] = sd.ss_nch[(size_t)i * kFW + w];
+                f.tile = ss_tile[i]; f.grp = ss_tile[i] / fused_grp_tiles;
+                f.need = kFW * fused_grp_items[f.grp]; f.tpr = sd.ss_tpr[i];
+            }
+            if (upload_vec(P->itemsF, fi, st)) return VMAT_E_CUDA;
+            P->nF1 = P->nss1; P->nF = P->nss1 + P->nss2;
+            CU(P->syncF.alloc((size_t)(kFSyncWords + P->ngroupsF) * 4));
+            CU(cudaMemsetAsync(P->syncF.p, 0, P->syncF.bytes, st));
+            if (int rc = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, sd.ss_off, sd.ss_tpr, sd.seg_start, sd.seg_len,
+                                      sd.seg_cb, sd.rows, nullptr, nullptr, nullptr, 0, d_bcol, d_bval,
+                                      P->sell2, P->off2, P->tpr2, &sd.ss_nch)) return rc;
+        } else {
         // Persistent CTAs, static partition: every CTA gets the same number of ring stages.  Within a
         // tile the super-slices run from long rows (up to cap+1 stages each) to short ones (a few
         // stages), so a CTA takes long ones from the front of the tile's range while they fit and
@@ -605,6 +728,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
                                   sd.seg_cb, sd.rows, nullptr, nullptr, nullptr, 0, d_bcol, d_bval,
                                   P->sell2, P->off2, P->tpr2)) return rc;
         if (upload_vec(P->tasks2, tasks, st)) return VMAT_E_CUDA;
+        }
     }
     up_bcol.alloc(0); up_bval.alloc(0); up_brow.alloc(0);
 
@@ -628,7 +752,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(P->gbf.alloc((B + 1) * 8));     CU(cudaMemset(P->gbf.p, 0, (B + 1) * 8));
     CU(P->result.alloc((nb + 2) * 8)); CU(cudaMemset(P->result.p, 0, (nb + 2) * 8));   // f, g[nb], exchange status
     CU(P->counter.alloc(64));          CU(cudaMemset(P->counter.p, 0, 64));
-    CU(P->fblock.alloc((size_t)std::max(1, P->k2_grid) * 8)); CU(cudaMemset(P->fblock.p, 0, (size_t)std::max(1, P->k2_grid) * 8));
+    const size_t nfblock = (size_t)std::max(std::max(1, P->k2_grid), 4 * P->sm_count);
+    CU(P->fblock.alloc(nfblock * 8)); CU(cudaMemset(P->fblock.p, 0, nfblock * 8));
     CU(P->scratch64.alloc(std::max<int64_t>(V, B) * 8));
     {
         std::vector<double> tt(thr, thr + V), oo(over, over + V), uu(under, under + V);
@@ -649,7 +774,14 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
     // K1 launch shape: persistent CTAs of W1 consumer warps + a producer warp; x (and y) staged
     // once per CTA, the rest of the CTA's shared memory is the TMA ring
-    {
+    if (P->fused) {
+        int occ = 0;
+        if (int rc = fused_occupancy(P, &occ)) return rc;
+        // one CTA per SM (the grid barrier needs every CTA resident; k2_tasks = explicit grid size, for tests)
+        P->gridF = P->opt.k2_tasks > 0 ? std::min(P->opt.k2_tasks, P->sm_count * occ) : P->sm_count;
+        P->x_in_smem = true;
+        P->host_path &= 4;               // no zero-copy y / tagged host results on this path
+    } else {
         const size_t xbytes = (((size_t)B * as + 127) & ~(size_t)127) + (((size_t)nb * 8 + 127) & ~(size_t)127);   // x and y
         P->x_in_smem = xbytes + 2 * (size_t)P->stage_bytes1 + 4096 <= (size_t)P->smem_optin;
         const size_t avail = (size_t)P->smem_optin - 4096 - (P->x_in_smem ? xbytes : 0);
@@ -694,7 +826,7 @@ extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layou
         *layout_bytes = b;
     }
     if (algo_bytes) *algo_bytes = 2 * P->nnz * (sv + P->iw) + 28 * P->V + 12 * P->B;    // SURVEY 8(d) with this plan's index width
-    if (launches) *launches = P->x_in_smem ? 3 : 4;
+    if (launches) *launches = P->fused ? 1 : P->x_in_smem ? 3 : 4;
     if (index_bytes) *index_bytes = P->iw;
     return VMAT_OK;
 }
@@ -702,6 +834,48 @@ extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layou
 // ---------------------------------------------------------------------------------
 // evaluation
 // ---------------------------------------------------------------------------------
+// the fused path: one launch of kf_eval (phase 0 or 1: everything up to gbf/result, with the exchange when
+// ranks are attached and phase == 0; phase 2 is the aperture gradient from an externally all-reduced gbf)
+template <typename VT, typename AT>
+static int launch_fused_t(vmat_plan* P, cudaStream_t st, int phase, bool inline_y, cudaEvent_t* ev) {
+    FArgs<AT> a{};
+    a.sell = P->sell1.as<uint4>(); a.sell2 = P->sell2.as<uint4>();
+    a.it_off = P->off1.as<int64_t>(); a.it_off2 = P->off2.as<int64_t>();
+    a.items = P->itemsF.as<FItem>(); a.n1 = P->nF1; a.nitems = P->col_mode ? P->nF1 : P->nF;
+    a.nstages = P->nstagesF; a.stage_bytes = P->stage_bytesF;
+    a.B = (int32_t)P->B; a.nb = P->nb; a.T = P->T; a.ntiles = P->ntiles; a.ngroups = P->ngroupsF; a.V = P->V;
+    a.y = P->col_mode ? P->col_y.as<double>() : P->y.as<double>();
+    a.beam_of = P->beam_of.as<int32_t>();
+    a.w_dose = P->col_mode ? static_cast<const AT*>(P->col_w_ptr) : P->w_dose.as<AT>();
+    a.d = P->d.as<AT>(); a.vg = P->vg.as<AT>(); a.fpart = P->fpart.as<double>(); a.partial = P->partial.as<AT>();
+    a.sync = P->syncF.as<unsigned int>(); a.fblock = P->fblock.as<double>();
+    a.beam_ptr = P->beam_ptr_d.as<int32_t>(); a.w_grad = P->w_grad.as<double>();
+    a.gbf = P->gbf.as<double>(); a.result = P->result.as<double>();
+    a.claim_lead = P->opt.reserved[6] > 0 ? P->opt.reserved[6] : kClaimLeadDefault;
+    a.dose_only = P->col_mode ? 1 : 0;
+    a.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
+    if (inline_y) {
+        a.y_mirror = P->y.as<double>();
+        a.y_inline_n = P->nb;
+        std::memcpy(a.y_inline, P->h_y, (size_t)P->nb * 8);
+    }
+    CommArgs c{};
+    c.nranks = 1;
+    if (P->comm_nranks > 1 && phase == 0 && !P->col_mode) {
+        c.peer_bufs = P->comm_ptrs.as<double*>(); c.rank = P->comm_rank; c.nranks = P->comm_nranks;
+        c.epoch = ++P->comm_epoch; c.timeout_ns = P->comm_timeout_ns;
+        c.error = P->comm_state.as<int32_t>() + 8; c.status = P->result.as<double>() + P->nb + 1;
+    }
+    DISPATCH_IWF(IW, {
+        auto kern = kf_eval<VT, AT, IW>;
+        CU(launch_pdl(kern, P->gridF, kFThreads, P->smemF, st, P->pdl, a, c));
+    });
+    CU(cudaGetLastError());
+    if (P->col_mode) CU(cudaMemsetAsync(P->syncF.p, 0, P->syncF.bytes, st));    // dose-only launches skip the barrier that resets the queue
+    if (ev) { CU(cudaEventRecord(ev[1], st)); CU(cudaEventRecord(ev[2], st)); CU(cudaEventRecord(ev[3], st)); }
+    return 0;
+}
+
 template <typename VT, typename AT>
 static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mode, bool inline_y) {
     cudaEvent_t* ev = nullptr;
@@ -710,6 +884,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         P->tcount++;
         CU(cudaEventRecord(ev[0], st));
     }
+    if (P->fused && phase != 2) return launch_fused_t<VT, AT>(P, st, phase, inline_y, ev);
     if (phase != 2) {
         if (!P->x_in_smem) {
             if (host_mode) CU(cudaMemcpyAsync(P->y.p, P->h_y, P->nb * 8, cudaMemcpyHostToDevice, st));
@@ -962,7 +1137,7 @@ extern "C" int vmat_get_timing(vmat_plan_t* P, double* ms, int32_t* n) {
 
 extern "C" int vmat_trace_eval(vmat_plan_t* P, uint64_t* out, int64_t cap, int32_t* k1_ctas, int32_t* k2_ctas) {
     if (!P || !out || !k1_ctas || !k2_ctas) return fail(VMAT_E_ARG, "null");
-    const size_t n = ((size_t)P->k1_grid + (size_t)P->k2_grid) * kTraceSlots;
+    const size_t n = P->fused ? (size_t)P->gridF * kTraceSlots : ((size_t)P->k1_grid + (size_t)P->k2_grid) * kTraceSlots;
     if (cap < (int64_t)n) return fail(VMAT_E_ARG, "vmat_trace_eval: buffer too small");
     CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());
@@ -975,7 +1150,7 @@ extern "C" int vmat_trace_eval(vmat_plan_t* P, uint64_t* out, int64_t cap, int32
     P->evaluated = true;
     CU(cudaMemcpyAsync(out, P->trace.p, n * 8, cudaMemcpyDeviceToHost, P->stream));
     CU(cudaStreamSynchronize(P->stream));
-    *k1_ctas = P->k1_grid; *k2_ctas = P->k2_grid;
+    *k1_ctas = P->fused ? P->gridF : P->k1_grid; *k2_ctas = P->fused ? 0 : P->k2_grid;
     return VMAT_OK;
 }
 
@@ -985,10 +1160,10 @@ extern "C" int vmat_reduce_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count
     return VMAT_OK;
 }
 
-// comm buffer: recv[2][kMaxRanks][B+1] doubles + flags[kMaxRanks][nb] u64, allocated on first use
+// comm buffer: recv[2][kMaxRanks][B+1] doubles + flags[kMaxRanks][nb+1] u64, allocated on first use
 static int comm_buffer(vmat_plan* P) {
     if (P->comm_buf.p) return 0;
-    const size_t bytes = (2 * (size_t)kMaxRanks * (size_t)(P->B + 1) + (size_t)kMaxRanks * P->nb) * 8;
+    const size_t bytes = (2 * (size_t)kMaxRanks * (size_t)(P->B + 1) + (size_t)kMaxRanks * (P->nb + 1)) * 8;
     CU(P->comm_buf.alloc(bytes));
     CU(cudaMemset(P->comm_buf.p, 0, bytes));
     return 0;

@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
 // the reduction kernel.  Every rank owns a "comm buffer" in its HBM that all peers have mapped
 // (CUDA IPC over NVLink, or plain peer pointers inside one process):
 //     recv[parity 0..1][source rank 0..nranks-1][gb partial (B) | f partial]   doubles
-//     flags[source rank][control point 0..nb-1]                                 u64 epochs
+//     flags[source rank][control point 0..nb-1, then one word for the objective]  u64 epochs
 // CTA i (control point i) reduces this rank's tile partials for its beamlets and STORES them
 // into slot [parity][my rank] of every rank's buffer (remote stores are fire-and-forget, so the
 // NVLink latency is paid once, not once per peer), then publishes the evaluation's epoch in
@@ -692,7 +692,7 @@ __device__ __forceinline__ size_t comm_slot(int parity, int src, int nranks, int
     return ((size_t)parity * nranks + src) * ((size_t)B + 1);
 }
 __device__ __forceinline__ unsigned long long* comm_flags(double* buf, int src, int nranks, int B, int nb) {
-    return reinterpret_cast<unsigned long long*>(buf + 2 * (size_t)nranks * ((size_t)B + 1)) + (size_t)src * nb;
+    return reinterpret_cast<unsigned long long*>(buf + 2 * (size_t)nranks * ((size_t)B + 1)) + (size_t)src * (nb + 1);
 }
 
 // Publish "control point `cp` of this rank is delivered" to every rank (lanes 0..nranks-1 of the
@@ -772,10 +772,19 @@ __global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, co
     }
     const double g = block_sum_256(contrib, sh);
     if (tid == 0) a.result[1 + blockIdx.x] = ok_s ? g : nan("");
-    if (blockIdx.x == 0 && tid == 0) {
-        const double f = ok_s ? comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)a.B) : nan("");
-        a.gbf[a.B] = f;
-        a.result[0] = f;
+    if (blockIdx.x == 0) {
+        // the objective has its own flag word (index nb), like in the fused evaluation kernel, so that ranks
+        // running either kernel can be mixed
+        __syncthreads();
+        if (tid < 32) {
+            const int ok = ok_s ? comm_publish_and_wait(c, tid, a.nb, a.B, a.nb) : 0;
+            if (tid == 0) {
+                if (!ok && ok_s) { atomicExch(c.error, 1); *c.status = 1.0; }
+                const double f = ok ? comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)a.B) : nan("");
+                a.gbf[a.B] = f;
+                a.result[0] = f;
+            }
+        }
     }
 }
 
@@ -848,7 +857,9 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
                               const unsigned char* __restrict__ thr, const unsigned char* __restrict__ over,
                               const unsigned char* __restrict__ under, int32_t es,
                               const int32_t* __restrict__ col, const ST* __restrict__ val,
-                              uint4* __restrict__ sell) {
+                              uint4* __restrict__ sell, const uint8_t* __restrict__ ss_nch) {
+    // ss_nch != nullptr: ragged super-slices (fused kernel) - warp w has ss_nch[ss*W + w] chunks
+    // (non-increasing in w) and stage c holds chunk c of the warps that still have one
     constexpr int KU = chunk_units<VT, IW>(), IU = idx_units(IW);
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -856,7 +867,7 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
     const int64_t ss = gw / W;
     const int w = (int)(gw % W);
     const int64_t off = ss_off[ss];
-    const int nch = (int)((ss_off[ss + 1] - off - (int64_t)W * HU) / ((int64_t)W * KU));
+    const int nch = ss_nch ? (int)ss_nch[ss * W + w] : (int)((ss_off[ss + 1] - off - (int64_t)W * HU) / ((int64_t)W * KU));
     const int64_t slot = gw * 32 + lane;
     unsigned char* hp = reinterpret_cast<unsigned char*>(sell + off + (int64_t)w * HU);
     reinterpret_cast<int32_t*>(hp)[lane] = rows[slot];
@@ -923,8 +934,14 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
         reinterpret_cast<uint32_t*>(hp + (HU - 8) * 16)[lane] = base;
     } else {
     // absolute indices: the row's nonzeros go round-robin (4 at a time) over its lanes
+    int64_t stage_off = 0;               // ragged: start of stage c = KU * sum over warps of min(nch_w, c)
     for (int c = 0; c < nch; ++c) {
-        uint4* chunk = data + ((int64_t)c * W + w) * KU;
+        uint4* chunk = ss_nch ? data + stage_off + (int64_t)w * KU : data + ((int64_t)c * W + w) * KU;
+        if (ss_nch) {
+            int kact = 0;
+            for (int q = 0; q < W; ++q) kact += ss_nch[ss * W + q] > c ? 1 : 0;
+            stage_off += (int64_t)kact * KU;
+        }
         int32_t ix[4];
         VT vv[4];
 #pragma unroll

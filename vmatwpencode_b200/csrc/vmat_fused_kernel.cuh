@@ -1,0 +1,539 @@
+// KF: the whole evaluation in ONE persistent kernel (sm_100a).
+//
+//   x = y * w_dose  ->  d = D x, penalty, voxel gradient  ->  gb = D^T vg  ->  aperture gradient
+//   (calcObjGrad, greedyVMATsampling.py:578-582 = calcDose :243-251 + calcGradientandObjValue
+//   :254-272, plus the beamlet gradient PPsubroutine :646 needs), optionally with the cross-GPU
+//   exchange of the beamlet gradient.
+//
+// One CTA per SM: 16 consumer warps + 1 producer warp, as in the dose kernel K1.  The work of both
+// sparse products is ONE queue of super-slices ("items"): first the dose items (voxel-major stream),
+// then the transposed items (beamlet-major, column-tiled stream).  CTAs claim items from an atomic
+// counter, so there is a single tail at the very end instead of one per kernel, no launch/drain gap
+// between the two products, and a CTA that runs out of dose items simply continues with transposed
+// ones.  What orders the two products is data, not a kernel boundary:
+//   * the voxels are cut into GROUPS of consecutive tiles; the dose stream is sorted by row length
+//     inside each group, and every consumer warp bumps grp_done[group] when its slice of a dose item
+//     has stored d and vg;
+//   * a transposed item needs the vg of one tile; its producer waits until grp_done[group(tile)] has
+//     reached the number of dose slices of that group, then fetches the tile with one TMA bulk copy.
+//     Transposed items come after all dose items in the queue, so the wait is normally already
+//     satisfied when the item is claimed (it bites only on small slabs, where CTAs start on
+//     transposed items right away and prefetch their D stream while the dose items finish).
+// The region of shared memory that holds x during the dose items is reused for two vg tile buffers
+// once the CTA has seen its first transposed item (the queue order guarantees it never gets a dose
+// item again), so the next item's tile is fetched while the current item is still being consumed.
+//
+// Super-slices are RAGGED: the 16 slices of an item keep their own chunk counts nch[w] (non-increasing
+// in w, the rows are sorted by length); stage c holds chunk c of the warps 0..k_c-1 that still have
+// one.  A 16-warp CTA therefore streams no more padding than a 1-warp layout would.
+//
+// When the queue is empty the CTAs meet at a grid barrier (arrive counter + generation word), then
+// CTA i reduces the tile partials of control points i, i+G, ... (fixed order), forms the aperture
+// gradient and - multi-GPU - runs the push exchange of vmat_eval_kernels.cuh for its control points.
+// The objective is summed in two fixed-shape levels (per-CTA shares of the per-slice partials, then
+// CTA 0).  No floating-point atomics; results are bit-reproducible although the item->CTA assignment
+// is dynamic (which CTA computes a row changes, how it is computed does not).
+#pragma once
+#include "vmat_eval_kernels.cuh"
+
+namespace vmat {
+
+constexpr int kFW = 16;                  // consumer warps per CTA
+constexpr int kFThreads = (kFW + 1) * 32;
+constexpr int kFMaxStages = 16;
+constexpr int kFSyncWords = 16;          // sync[0] queue, [1] barrier arrivals, [2] barrier generation, [3] objective shares done; groups follow
+
+struct FItem {                           // one queue item (32 bytes)
+    uint8_t nch[kFW];                    // chunks of warp w, non-increasing in w
+    int32_t tile;                        // transposed item: voxel tile; dose item: -1
+    int32_t grp;                         // dose item: group to signal; transposed item: group to wait for
+    int32_t need;                        // transposed item: value grp_done[grp] must have reached
+    uint8_t tpr, pad[3];
+};
+static_assert(sizeof(FItem) == 32, "FItem layout");
+
+struct FStage {                          // what the producer tells the consumers about a ring slot
+    int32_t item;                        // -1: no more work
+    int32_t tile;                        // -1 for dose items
+    int32_t grp;
+    uint8_t flags, kact, tpr, tbuf;      // kact: warps 0..kact-1 have a chunk in this stage; tbuf: tile buffer and its phase parity (bit 1)
+    uint8_t nch[kFW];
+};
+static_assert(sizeof(FStage) == 32, "FStage layout");
+
+template <typename AT>
+struct FArgs {
+    const uint4* sell;                   // dose stream (voxel-major), items 0 .. n1-1
+    const uint4* sell2;                  // transposed stream (beamlet-major, column-tiled), items n1 .. nitems-1
+    const int64_t* it_off;               // [n1+1] offsets into sell, 16-byte units
+    const int64_t* it_off2;              // [nitems-n1+1] offsets into sell2
+    const FItem* items;                  // [nitems]
+    int32_t n1, nitems;                  // dose items, all items (dose-only launches pass nitems = n1)
+    int32_t nstages, stage_bytes;
+    int32_t B, nb, T, ntiles, ngroups;
+    int64_t V;
+    const double* y;                     // [nb]
+    const int32_t* beam_of;              // [B]
+    const AT* w_dose;                    // [B]
+    AT* d;                               // [V]
+    AT* vg;                              // [V + T]
+    double* fpart;                       // [n1 * 16] objective partial of every dose slice
+    AT* partial;                         // [ntiles][B]
+    unsigned int* sync;                  // [kFSyncWords + ngroups]
+    double* fblock;                      // [gridDim.x]
+    const int32_t* beam_ptr;             // [nb+1]
+    const double* w_grad;                // [B]
+    double* gbf;                         // [B+1]
+    double* result;                      // [nb+2]
+    double* y_mirror;                    // host-buffer path: y is mirrored into the device copy by CTA 0
+    int32_t y_inline_n;
+    int32_t claim_lead;
+    int32_t dose_only;                   // 1: dose items only, no reductions (RMP column build)
+    unsigned long long* trace;           // [gridDim.x * kTraceSlots] or nullptr
+    double y_inline[kInlineY];
+};
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ float ld_cg_f64(const float* p) { return __ldcg(p); }
+
+// sum of src[first], src[first+stride], ... (< n) in that order, loads bypassing L1 (the data was
+// written by other SMs in this same kernel), batched 8 deep
+template <typename T>
+__device__ __forceinline__ double strided_sum_cg(const T* __restrict__ src, int64_t first, int64_t stride, int64_t n) {
+    double s = 0.0;
+    int64_t k = first;
+    for (; k + 7 * stride < n; k += 8 * stride) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + k + u * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (k + u * stride < n) ? __ldcg(src + k + u * stride) : (T)0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (k + u * stride < n) s += (double)v[u];
+    }
+    return s;
+}
+
+// fixed-shape sum over the kFThreads threads of the CTA: warp butterflies, then the 17 warp sums in order
+__device__ __forceinline__ double block_sum_f(double v, double* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFW + 1; ++w) r += sh[w];
+    return r;
+}
+
+template <typename VT, typename AT, int IW>
+__global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FArgs<AT> a, const CommArgs c) {
+    constexpr int W = kFW, KU = chunk_units<VT, IW>(), HU1 = header_units_k1<AT>(IW), HU2 = header_units_k2(IW);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kFMaxStages], empty[kFMaxStages], tile_full[2], tile_empty[2], x_free;
+    __shared__ __align__(16) FStage sinfo[kFMaxStages];
+    __shared__ double red[kFW + 1];
+    __shared__ int ok_s;
+    const int xbytes = (a.B * (int)sizeof(AT) + 127) & ~127;
+    const int ybytes = (a.nb * 8 + 127) & ~127;
+    const int tbytes = (a.T * (int)sizeof(AT) + 127) & ~127;
+    const int ubytes = max(xbytes + ybytes, 2 * tbytes);
+    AT* xs = reinterpret_cast<AT*>(smem_raw);
+    double* ys = reinterpret_cast<double*>(smem_raw + xbytes);
+    unsigned char* ring = smem_raw + ubytes;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nst = a.nstages, SB = a.stage_bytes;
+    const unsigned int G = gridDim.x;
+    unsigned long long* const trace = a.trace ? a.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
+    unsigned int* const grp_done = a.sync + kFSyncWords;
+
+    if (tid == 0) {
+        if (trace) trace[0] = global_timer_ns();
+        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
+        mbar_init(&tile_full[0], 1); mbar_init(&tile_full[1], 1);
+        mbar_init(&tile_empty[0], W); mbar_init(&tile_empty[1], W);
+        mbar_init(&x_free, W);
+        fence_barrier_init();
+    }
+    pdl_launch_dependents();
+    __syncthreads();
+    if (warp < W) {
+        // x_j = y[beam(j)] * w_dose[j] into shared memory (as in K1; the producer streams D meanwhile)
+        constexpr int kPre = 4;
+        const int ngroups4 = a.B >> 2;
+        int4 bo[kPre];
+        AT wd[kPre][4];
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int gidx = tid + k * W * 32;
+            if (gidx < ngroups4) {
+                bo[k] = reinterpret_cast<const int4*>(a.beam_of)[gidx];
+                load4(a.w_dose + 4 * gidx, wd[k]);
+            }
+        }
+        if (a.y_inline_n > 0) { for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y_inline[j]; }
+        else { for (int j = tid; j < a.nb; j += W * 32) ys[j] = a.y[j]; }
+        named_bar_sync(1, W * 32);
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int gidx = tid + k * W * 32;
+            if (gidx < ngroups4) {
+                store4(xs + 4 * gidx, mul_rn((AT)ys[bo[k].x], wd[k][0]), mul_rn((AT)ys[bo[k].y], wd[k][1]),
+                       mul_rn((AT)ys[bo[k].z], wd[k][2]), mul_rn((AT)ys[bo[k].w], wd[k][3]));
+            }
+        }
+        for (int gidx = tid + kPre * W * 32; gidx < ngroups4; gidx += W * 32) {
+            const int4 b4 = reinterpret_cast<const int4*>(a.beam_of)[gidx];
+            AT w4[4];
+            load4(a.w_dose + 4 * gidx, w4);
+            store4(xs + 4 * gidx, mul_rn((AT)ys[b4.x], w4[0]), mul_rn((AT)ys[b4.y], w4[1]),
+                   mul_rn((AT)ys[b4.z], w4[2]), mul_rn((AT)ys[b4.w], w4[3]));
+        }
+        for (int j = 4 * ngroups4 + tid; j < a.B; j += W * 32) xs[j] = mul_rn((AT)ys[a.beam_of[j]], a.w_dose[j]);
+        named_bar_sync(1, W * 32);
+        // d, vg, fpart, partial and the sync words belong to the previous evaluation until it is complete
+        pdl_wait();
+        if (blockIdx.x == 0 && a.y_mirror != nullptr) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
+    }
+    if (trace && tid == 0) trace[1] = global_timer_ns();
+
+    if (warp == W) {
+        // ---------------- producer: one thread streams items into the ring -------------------
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            RingPos pos;
+            const unsigned int ni = (unsigned)a.nitems;
+            const int lead = a.claim_lead;
+            unsigned int cur = blockIdx.x;
+            bool first = true;                 // the first item is assigned statically; nothing written by the previous evaluation has been touched yet
+            int ntile_use = 0;                 // transposed items of this CTA so far
+            // tile fetch in flight for the current transposed item (issued as soon as buffer and group allow)
+            bool tile_pending = false, tile_buf_free = false, tile_grp_ready = false;
+            int tb = 0; uint32_t tp = 0; int tgrp = 0; unsigned int tneed = 0; int ttile = 0;
+            // Every barrier arrival is anonymous, so each consumer warp must arrive exactly once per phase:
+            // once on x_free (it has read x for the last time), once on tile_empty[b] per item that used
+            // buffer b - and it can reach that item's header only after the tile has landed, i.e. after the
+            // phase of the buffer's previous item is complete.  The first use of a buffer waits for x_free.
+            auto poll_tile = [&]() {
+                if (!tile_buf_free) tile_buf_free = ntile_use <= 2 ? mbar_test(&x_free, 0u) : mbar_test(&tile_empty[tb], tp ^ 1u);
+                if (tile_buf_free && !tile_grp_ready) tile_grp_ready = ld_acquire_gpu_u32(grp_done + tgrp) >= tneed;
+                if (tile_buf_free && tile_grp_ready) {
+                    fence_proxy_async_all();           // vg was written through the generic proxy by other SMs
+                    const int64_t base = (int64_t)ttile * a.T;
+                    const int n = (int)min((int64_t)a.T, a.V - base);
+                    const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(AT) + 15) & ~(size_t)15);
+                    mbar_expect_tx(&tile_full[tb], bytes);
+                    tma_bulk_g2s(smem_raw + (size_t)tb * tbytes, a.vg + base, bytes, &tile_full[tb]);
+                    tile_pending = false;
+                }
+            };
+            auto push = [&](const FStage& info, const void* src, uint32_t bytes) {
+                while (!mbar_test(&empty[pos.stage], pos.phase ^ 1u)) { if (tile_pending) poll_tile(); }
+                sinfo[pos.stage] = info;
+                if (bytes) {
+                    mbar_expect_tx(&full[pos.stage], bytes);
+                    tma_bulk_g2s_hint(ring + (size_t)pos.stage * SB, src, bytes, &full[pos.stage], pol);
+                } else {
+                    mbar_arrive(&full[pos.stage]);
+                }
+                pos.advance(nst);
+                if (tile_pending) poll_tile();
+            };
+            FItem it{};
+            const uint4* o0 = nullptr;
+            const unsigned int n1u = (unsigned)a.n1;
+            auto item_base = [&](unsigned int q) -> const uint4* {
+                return q < n1u ? a.sell + a.it_off[q] : a.sell2 + a.it_off2[q - n1u];
+            };
+            if (cur < ni) { it = a.items[cur]; o0 = item_base(cur); }
+            while (cur < ni) {
+                const bool dose = it.tile < 0;
+                const int HU = dose ? HU1 : HU2;
+                const int nch0 = it.nch[0];
+                if (!dose) {
+                    if (first) { pdl_wait(); first = false; }      // grp_done is about to be read
+                    tb = ntile_use & 1; tp = (uint32_t)(ntile_use >> 1) & 1u; ++ntile_use;
+                    tgrp = it.grp; tneed = (unsigned)it.need; ttile = it.tile;
+                    tile_pending = true; tile_buf_free = false; tile_grp_ready = false;
+                }
+                FStage info{};
+                info.item = (int32_t)cur; info.tile = it.tile; info.grp = it.grp;
+                info.kact = W; info.tpr = it.tpr; info.tbuf = (uint8_t)(tb | (tp << 1));
+#pragma unroll
+                for (int w = 0; w < W; ++w) info.nch[w] = it.nch[w];
+                info.flags = (uint8_t)(kStageHeader | (nch0 == 0 ? kStageLast : 0));
+                push(info, o0, (uint32_t)(W * HU * 16));
+                const uint4* data = o0 + W * HU;
+                unsigned int nxt = 0u;
+                FItem nit{};
+                const uint4* n0 = nullptr;
+                bool claimed = false, loaded = false;
+                const int c_claim = max(0, nch0 - lead), c_load = min(c_claim + 4, max(0, nch0 - 1));
+                int kact = W;
+                while (kact > 0 && it.nch[kact - 1] == 0) --kact;
+                int64_t off = 0;
+                info.flags = 0;
+                for (int cc = 0; cc < nch0; ++cc) {
+                    while (kact > 0 && it.nch[kact - 1] <= cc) --kact;
+                    if (!first) {
+                        if (cc == c_claim) { nxt = G + atomicAdd(a.sync, 1u); claimed = true; }
+                        if (cc == c_load && claimed) {
+                            if (nxt < ni) { nit = a.items[nxt]; n0 = item_base(nxt); }
+                            loaded = true;
+                        }
+                    }
+                    info.kact = (uint8_t)kact;
+                    push(info, data + off, (uint32_t)(kact * KU * 16));
+                    off += (int64_t)kact * KU;
+                }
+                while (tile_pending) poll_tile();            // (only when the item had fewer stages than the ring)
+                if (first) { pdl_wait(); first = false; }    // the queue counter was reset by the previous evaluation
+                if (!claimed) nxt = G + atomicAdd(a.sync, 1u);
+                if (!loaded && nxt < ni) { nit = a.items[nxt]; n0 = item_base(nxt); }
+                cur = nxt; it = nit; o0 = n0;
+            }
+            FStage fin{};
+            fin.item = -1;
+            push(fin, nullptr, 0);
+        }
+    } else {
+        // ---------------- consumers: warp w owns slice w of every item -----------------------------
+        RingPos pos;
+        AT acc = (AT)0, t = (AT)0, ov = (AT)0, un = (AT)0;
+        int32_t row = -1;
+        uint32_t cur = 0;
+        int my_nch = 0, cdone = 0, tpr = 1, item = 0, grp = 0, tile = -1, tbuf = 0;
+        bool dose = true, x_released = false;
+        const AT* vt = reinterpret_cast<const AT*>(smem_raw);
+        if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }
+        while (true) {
+            mbar_wait(&full[pos.stage], pos.phase);
+            const FStage* sp = &sinfo[pos.stage];
+            const int s_item = sp->item;
+            if (s_item < 0) break;
+            const int s_flags = sp->flags;
+            bool finished = false;
+            if (s_flags & kStageHeader) {
+                item = s_item; tile = sp->tile; grp = sp->grp; tpr = sp->tpr; my_nch = sp->nch[warp];
+                dose = tile < 0;
+                cdone = 0;
+                acc = (AT)0;
+                if (dose) {
+                    const unsigned char* hp = ring + (size_t)pos.stage * SB + warp * (HU1 * 16);
+                    row = reinterpret_cast<const int32_t*>(hp)[lane];
+                    t  = reinterpret_cast<const AT*>(hp + 128)[lane];
+                    ov = reinterpret_cast<const AT*>(hp + 128 + 32 * sizeof(AT))[lane];
+                    un = reinterpret_cast<const AT*>(hp + 128 + 64 * sizeof(AT))[lane];
+                } else {
+                    const int tb2 = sp->tbuf;
+                    tbuf = tb2 & 1;
+                    if (!x_released) {       // first transposed item: no dose item follows, the x region becomes the tile buffers
+                        x_released = true;
+                        if (trace && tid == 0) trace[3] = global_timer_ns();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&x_free);
+                    }
+                    row = reinterpret_cast<const int32_t*>(ring + (size_t)pos.stage * SB + warp * (HU2 * 16))[lane];
+                    vt = reinterpret_cast<const AT*>(smem_raw + (size_t)tbuf * tbytes);
+                    mbar_wait(&tile_full[tbuf], (uint32_t)(tb2 >> 1));      // every warp, also one without chunks (see the producer)
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[pos.stage]);
+                finished = my_nch == 0;
+            } else if (warp < (int)sp->kact) {
+                const int warp_off = warp * (KU * 16);
+                ChunkRegs<AT> A;
+                chunk_load<VT, AT, IW>(ring + (size_t)pos.stage * SB + warp_off, lane, A, cur);
+                if (cdone + 1 < my_nch) {         // the next stage belongs to this item and has a chunk of this warp too
+                    RingPos nx = pos;
+                    nx.advance(nst);
+                    mbar_wait(&full[nx.stage], nx.phase);
+                    ChunkRegs<AT> Bc;
+                    chunk_load<VT, AT, IW>(ring + (size_t)nx.stage * SB + warp_off, lane, Bc, cur);
+                    AT x0, x1, x2, x3, y0, y1, y2, y3;
+                    if (dose) {
+                        x0 = xs[A.i[0]]; x1 = xs[A.i[1]]; x2 = xs[A.i[2]]; x3 = xs[A.i[3]];
+                        y0 = xs[Bc.i[0]]; y1 = xs[Bc.i[1]]; y2 = xs[Bc.i[2]]; y3 = xs[Bc.i[3]];
+                    } else {
+                        x0 = vt[A.i[0]]; x1 = vt[A.i[1]]; x2 = vt[A.i[2]]; x3 = vt[A.i[3]];
+                        y0 = vt[Bc.i[0]]; y1 = vt[Bc.i[1]]; y2 = vt[Bc.i[2]]; y3 = vt[Bc.i[3]];
+                    }
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&empty[pos.stage]); mbar_arrive(&empty[nx.stage]); }
+                    acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
+                    acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
+                    acc = fma_acc(Bc.v[0], y0, acc); acc = fma_acc(Bc.v[1], y1, acc);
+                    acc = fma_acc(Bc.v[2], y2, acc); acc = fma_acc(Bc.v[3], y3, acc);
+                    pos = nx;
+                    cdone += 2;
+                } else {
+                    AT x0, x1, x2, x3;
+                    if (dose) { x0 = xs[A.i[0]]; x1 = xs[A.i[1]]; x2 = xs[A.i[2]]; x3 = xs[A.i[3]]; }
+                    else      { x0 = vt[A.i[0]]; x1 = vt[A.i[1]]; x2 = vt[A.i[2]]; x3 = vt[A.i[3]]; }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[pos.stage]);
+                    acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
+                    acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
+                    cdone += 1;
+                }
+                finished = cdone == my_nch;
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[pos.stage]);
+            }
+            if (finished) {
+                for (int o = 1; o < tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // tpr lanes of a row
+                if (dose) {
+                    double fterm = 0.0;
+                    if (row >= 0) {
+                        // (d-t)+ and (t-d)+, objective term, vg = 2*(2*o*over - 2*u*under)  (:255-271)
+                        AT o = sub_rn(acc, t);  o = o > (AT)0 ? o : (AT)0;
+                        AT u = sub_rn(t, acc);  u = u > (AT)0 ? u : (AT)0;
+                        const AT fo = mul_rn(mul_rn(o, o), ov);
+                        const AT fu = mul_rn(mul_rn(u, u), un);
+                        fterm = (double)add_rn(fo, fu);
+                        const AT go = mul_rn(mul_rn((AT)2, o), ov);
+                        const AT gu = mul_rn(mul_rn((AT)2, u), un);
+                        a.d[row] = acc;
+                        a.vg[row] = mul_rn((AT)2, sub_rn(go, gu));
+                    }
+                    fterm = warp_sum(fterm);
+                    if (lane == 0) a.fpart[(int64_t)item * W + warp] = fterm;
+                    __syncwarp();
+                    if (lane == 0) red_release_gpu_add(grp_done + grp, 1u);      // this slice's vg is visible
+                } else {
+                    if (row >= 0) a.partial[(int64_t)tile * a.B + row] = acc;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tile_empty[tbuf]);                // done with this tile buffer
+                }
+            }
+            pos.advance(nst);
+        }
+    }
+    if (trace && tid == 0) trace[4] = global_timer_ns();
+    if (a.dose_only) return;
+
+    // ---------------- all transposed partials of all CTAs are written: grid barrier -----------------
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int gen = ld_acquire_gpu_u32(a.sync + 2);
+        __threadfence();
+        if (atomicAdd(a.sync + 1, 1u) == G - 1) {
+            a.sync[0] = 0u;                                   // queue and group counters for the next evaluation
+            a.sync[1] = 0u;
+            for (int g = 0; g < a.ngroups; ++g) grp_done[g] = 0u;
+            __threadfence();
+            red_release_gpu_add(a.sync + 2, 1u);
+        } else {
+            while (ld_acquire_gpu_u32(a.sync + 2) == gen) { }
+        }
+    }
+    __syncthreads();
+    if (trace && tid == 0) trace[5] = global_timer_ns();
+
+    // ---------------- objective: this CTA's fixed share of the per-slice partials --------------------
+    const int nfpart = a.n1 * W;
+    if (warp == W) {
+        const int per = (nfpart + (int)G - 1) / (int)G;
+        const int f0 = blockIdx.x * per, f1 = min(nfpart, f0 + per);
+        double v = 0.0;
+        for (int k = f0 + lane; k < f1; k += 32) v += __ldcg(a.fpart + k);
+        v = warp_sum(v);
+        if (lane == 0) { a.fblock[blockIdx.x] = v; red_release_gpu_add(a.sync + 3, 1u); }
+    }
+    // ---------------- control points blockIdx.x, blockIdx.x + G, ...: tile partials -> gb -> g ------
+    const bool multi = c.nranks > 1;
+    const int parity = (int)(c.epoch & 1ull);
+    const size_t slot = multi ? comm_slot(parity, c.rank, c.nranks, a.B) : 0;
+    for (int cp = blockIdx.x; cp < a.nb; cp += (int)G) {
+        const int lo = a.beam_ptr[cp], hi = a.beam_ptr[cp + 1];
+        double contrib = 0.0;
+        for (int j0 = lo; j0 < hi; j0 += kFThreads / 4) {
+            // 4 threads per beamlet: thread q sums tiles t = q, q+4, ...; combined (q0+q1)+(q2+q3)
+            const int j = j0 + (tid >> 2), q = tid & 3;
+            double s = 0.0;
+            if (j < hi) s = strided_sum_cg(a.partial + j, (int64_t)q * a.B, (int64_t)4 * a.B, (int64_t)a.ntiles * a.B);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (j < hi) {
+                if (multi) { for (int p = q; p < c.nranks; p += 4) st_sys_f64(c.peer_bufs[p] + slot + j, s); }
+                else if (q == 0) { a.gbf[j] = s; contrib += a.w_grad[j] * s; }
+            }
+        }
+        if (multi) {
+            __syncthreads();
+            if (tid < 32) {
+                const int ok = comm_publish_and_wait(c, tid, cp, a.B, a.nb);
+                if (tid == 0) {
+                    ok_s = ok;
+                    if (!ok) { atomicExch(c.error, 1); *c.status = 1.0; }
+                }
+            }
+            __syncthreads();
+            if (ok_s) {
+                const double* mybuf = c.peer_bufs[c.rank];
+                for (int j = lo + tid; j < hi; j += kFThreads) {
+                    const double s = comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)j);
+                    a.gbf[j] = s;
+                    contrib += a.w_grad[j] * s;
+                }
+            }
+        }
+        const double g = block_sum_f(contrib, red);
+        if (tid == 0) a.result[1 + cp] = (!multi || ok_s) ? g : nan("");
+        __syncthreads();
+    }
+    // ---------------- objective, second level (CTA 0): the per-CTA shares in index order --------------
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            while (ld_acquire_gpu_u32(a.sync + 3) < G) { }
+            a.sync[3] = 0u;
+        }
+        __syncthreads();
+        double fv = strided_sum_cg(a.fblock, (int64_t)tid, (int64_t)kFThreads, (int64_t)G);
+        fv = block_sum_f(fv, red);
+        if (!multi) {
+            if (tid == 0) { a.gbf[a.B] = fv; a.result[0] = fv; }
+        } else {
+            if (tid < c.nranks) st_sys_f64(c.peer_bufs[tid] + slot + a.B, fv);
+            __syncthreads();
+            if (tid < 32) {
+                const int ok = comm_publish_and_wait(c, tid, a.nb, a.B, a.nb);     // flag slot nb: the objective
+                if (tid == 0) {
+                    double f = nan("");
+                    if (ok) f = comm_sum_ranks(c.peer_bufs[c.rank], parity, c.nranks, a.B, (size_t)a.B);
+                    else { atomicExch(c.error, 1); *c.status = 1.0; }
+                    a.gbf[a.B] = f;
+                    a.result[0] = f;
+                }
+            }
+        }
+    }
+    if (trace && tid == 0) trace[6] = global_timer_ns();
+}
+
+}  // namespace vmat
