@@ -335,6 +335,18 @@ def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, h
         barrier()
         f_res, g_res = plan.fetch_result()
 
+    trace_us = None
+    if args.trace:          # per-CTA time stamps of one evaluation (every rank runs it: it includes the exchange)
+        barrier()
+        k1t, k2t = plan.trace_eval()
+        q = lambda col: [round(float(v) / 1e3, 2) for v in np.percentile(col[col >= 0], [0, 50, 100])] if (col >= 0).any() else None
+        if info["launches_per_eval"] == 1:
+            names = ["entry", "x_staged", "first_stage", "first_transposed_item", "queue_empty", "barrier_passed", "end"]
+            trace_us = {n: q(plan.trace_raw[:, i]) for i, n in enumerate(names)}
+        else:
+            trace_us = dict(k1_done=q(k1t[:, 3]), k2_entry=q(k2t[:, 0]), k2_done=q(k2t[:, 3]))
+        barrier()
+
     # ---- check (outside every timed region) ---------------------------------------------------
     check = {"f": f_res, "g_norm": float(np.linalg.norm(g_res))}
     if device_case:
@@ -410,6 +422,8 @@ def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, h
                                     "algorithmic_bytes_per_eval": algo,
                                     "layout_bytes_per_eval": info["layout_bytes_per_eval"],
                                     "scope": "rank 0's slab per evaluation" if world > 1 else "whole case"}
+        if trace_us is not None:
+            out["trace_us"] = trace_us
         out["_case"] = (case, y, w_dose, w_grad)
     barrier()
     plan.close()
@@ -437,7 +451,8 @@ def main():
     ap.add_argument("--index-bytes", type=int, default=0, help="4 forces int32 column indices (default: uint16 when they fit)")
     ap.add_argument("--claim-lead", type=int, default=0, help="dose kernel: stages before a super-slice's end at which the next is claimed (tuning; 0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--fused", type=int, default=0, help="0 = fused evaluation kernel when it fits, 1 = the three kernels, 2 = fused or fail")
+    ap.add_argument("--fused", type=int, default=0, help="0 / 1 = the three kernels K1/K2/K3 (default), 2 = the single fused evaluation kernel")
+    ap.add_argument("--trace", action="store_true", help="add per-CTA time stamps of one evaluation (diagnostics)")
     ap.add_argument("--largest", default="cfg4", help="workload of the `largest_case` block ('none' skips it)")
     ap.add_argument("--largest-steps", type=int, default=200)
     args = ap.parse_args()
@@ -484,7 +499,7 @@ def main():
             "plan": head["plan"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
             "clocks": clocks, "check": head["check"],
         }
-        for k in ("roofline", "kernels_ms", "roofline_eval"):
+        for k in ("roofline", "kernels_ms", "roofline_eval", "trace_us"):
             if k in head:
                 line[k] = head[k]
         if largest is not None:

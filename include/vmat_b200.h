@@ -54,10 +54,11 @@ typedef struct vmat_options {
                                    4 y inside the launch parameters (default), 8 none (copy nodes)
                                [5] 4 = int32 column indices, 1 = byte deltas (default: uint16 whenever they fit)
                                [6] stages before a super-slice's end at which the dose kernel claims the next
-                               [8] evaluation kernels: 0 = one fused persistent kernel (dose, transposed product,
-                                   reductions and exchange in a single launch) whenever its shared-memory budget
-                                   works out, 1 = the three kernels K1/K2/K3, 2 = fused or fail;
-                                   with the fused kernel k2_tasks is the grid size (default: one CTA per SM) */
+                               [8] evaluation kernels: 0 or 1 = the three kernels K1/K2/K3 chained by programmatic
+                                   dependent launch (default), 2 = one fused persistent kernel (dose, transposed
+                                   product, reductions and exchange in a single launch; fails if x does not fit in
+                                   shared memory); with the fused kernel k2_tasks is the grid size (default: one
+                                   CTA per SM) */
 } vmat_options_t;
 
 /* Library / build identification. */
@@ -139,13 +140,15 @@ int vmat_reduce_buffer(vmat_plan_t* plan, void** dev_ptr, int64_t* count);
  * Multi-GPU exchange without NCCL: every rank exports the CUDA IPC handle of its comm buffer
  * (vmat_comm_handle, 64 bytes), the caller gathers the handles of all ranks (any transport) and
  * hands them to vmat_comm_attach (at most 16 ranks).  From then on vmat_eval_async(phase 0) /
- * vmat_eval run the reduction kernel fused with a push all-reduce over peer memory (NVLink): the CTA
- * of control point i stores its partial beamlet gradient into every rank's buffer, publishes an
- * epoch flag, waits for the peers' flags of the same control point in its own memory and adds the
- * ranks in rank order - identical bits on every rank; phases 1/2 are not needed.  All ranks must
- * attach before any of them evaluates, and must evaluate in lock step.  A peer that does not deliver
- * within the time-out (default 20 s, vmat_comm_set_timeout) makes the evaluation return VMAT_E_CUDA
- * with NaN results; the peers then fail the same way in their next evaluation.
+ * vmat_eval run the reductions fused with a push all-reduce over peer memory (NVLink): the CTA of
+ * control point i stores its partial beamlet gradient into every rank's buffer, each value carrying
+ * the evaluation's epoch (two 8-byte words {32 bits of the value | epoch}), and the thread that needs
+ * a value polls its own buffer until every rank's entry carries the epoch, then adds the ranks in rank
+ * order - identical bits on every rank, no fence and no separate flag on the path; phases 1/2 are not
+ * needed.  All ranks must attach before any of them evaluates, and must evaluate in lock step.  A peer
+ * that does not deliver within the time-out (default 20 s, vmat_comm_set_timeout) makes the evaluation
+ * return VMAT_E_CUDA with NaN results; the peers then fail the same way in their next evaluation, and
+ * the ranks have to attach again before they can continue.
  * This replaces the reference's only parallelism, the process pool of greedyVMATsampling.py:836-841.
  *
  * vmat_comm_attach_local is the same for plans that live in ONE process (plans[q] = rank q's plan,

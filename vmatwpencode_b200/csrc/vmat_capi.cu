@@ -65,7 +65,7 @@ struct vmat_plan {
     int64_t units2 = 0;
     // fused single-kernel evaluation (vmat_fused_kernel.cuh): both streams ragged, W = 16, one item queue
     bool fused = false;
-    DevBuf itemsF, syncF;
+    DevBuf itemsF, syncF, offF2;           // offF2[q]: stream offset of the q-th transposed item of the queue
     int32_t nF1 = 0, nF = 0, nstagesF = 0, stage_bytesF = 0, ngroupsF = 0, gridF = 0;
     size_t smemF = 0;
     // state
@@ -225,6 +225,7 @@ struct StreamDesc {
     int32_t W, HU, units, cap;
     bool ragged = false;                          // fused kernel: every slice keeps its own chunk count
     bool too_long = false;                        // ragged: a row needs more than 255 chunks per lane
+    bool record_nch = false;                      // fused kernel with uniform stages: ss_nch = the item's chunk count for every warp
     std::vector<uint8_t> ss_nch;                  // [nss * W] (ragged only)
     std::vector<int64_t> ss_off{0}, seg_start;
     std::vector<uint8_t> ss_tpr;
@@ -276,6 +277,7 @@ struct StreamDesc {
                 }
                 ss_off.push_back(ss_off.back() + (int64_t)W * HU + chunks * (int64_t)units);
             } else {
+                if (record_nch) { if (nch > 255) too_long = true; for (int w = 0; w < W; ++w) ss_nch.push_back((uint8_t)nch); }
                 ss_off.push_back(ss_off.back() + (int64_t)W * HU + nch * (int64_t)W * units);
             }
         }
@@ -441,8 +443,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     }
 
     // ---- one fused kernel or the three-kernel path --------------------------------------------------
-    // reserved[8]: 0 = the fused kernel whenever its shared-memory budget works out (x + y or two vg tiles
-    // next to at least 6 ring stages of 16 warps), 1 = the three kernels K1/K2/K3, 2 = fused or fail
+    // reserved[8] & 3: 0 / 1 = the three kernels K1/K2/K3 chained by programmatic dependent launch (default:
+    // measured faster on every configuration), 2 = the single fused kernel (needs x + y or
+    // two vg tiles next to at least 6 ring stages of 16 warps in shared memory); bit 2: uniform stages (experiment)
     int32_t T_plan = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
     T_plan = (T_plan + 63) / 64 * 64;
     {
@@ -456,9 +459,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         int nst = (int)std::min<size_t>(kFMaxStages, room / SB);
         if (P->opt.reserved[0] > 0) nst = std::min(nst, std::max(2, P->opt.reserved[0]));
         const bool can = P->iw != 1 && nst >= (P->opt.reserved[0] > 0 ? 2 : 6);
-        const int mode = P->opt.reserved[8];
+        const int mode = P->opt.reserved[8] & 3;
         if (mode == 2 && !can) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel does not fit this plan (beamlet vector too large for shared memory, or byte-delta indices)");
-        P->fused = can && mode != 1;
+        P->fused = can && mode == 2;
         if (P->fused) {
             P->W1 = kFW;
             P->nstagesF = nst; P->stage_bytesF = (int32_t)SB;
@@ -498,6 +501,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     std::vector<uint8_t> fused_nch1, fused_tpr1;          // fused plans: per dose item chunk counts, lanes per row,
     std::vector<int32_t> fused_grp1, fused_grp_items;     // group, and the number of dose items per group
     int32_t fused_grp_tiles = 1;
+    const bool fused_uniform = (P->opt.reserved[8] & 4) != 0;     // experiment: uniform (padded) stages in the fused layout
     std::vector<int32_t> vpads;            // per voxel row (byte-delta layout only)
     CU(csr_flag.alloc(4)); CU(cudaMemsetAsync(csr_flag.p, 0, 4, st));
     auto check_csr = [&](int64_t nrows, int64_t ncols, int sorted, const int64_t* d_rowptr, const int32_t* d_col,
@@ -552,7 +556,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2]
                           : P->fused ? (int32_t)std::min<int64_t>(kChunkCapK1, std::max<int64_t>(12, per_cta / 2)) : kChunkCapK1;
         StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
-        sd.ragged = P->fused;
+        sd.ragged = P->fused && !fused_uniform;
+        sd.record_nch = P->fused;
         std::vector<StreamDesc::Item> items(V);
         for (int64_t pos = 0; pos < V; ++pos) {
             const int32_t v = order[pos];
@@ -589,7 +594,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         if (rc) return VMAT_E_CUDA;
         if (int rc2 = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, sd.ss_off, sd.ss_tpr, sd.seg_start, sd.seg_len,
                                    sd.seg_cb, sd.rows, &thr_s, &over_s, &under_s, es, d_vcol, d_vval,
-                                   P->sell1, P->off1, P->tpr1, P->fused ? &sd.ss_nch : nullptr)) return rc2;
+                                   P->sell1, P->off1, P->tpr1, sd.ragged ? &sd.ss_nch : nullptr)) return rc2;
         P->stage_bytes1 = W * std::max<int>(units, HU) * 16;
     }
     up_vcol.alloc(0); up_vval.alloc(0);   // release the voxel-major CSR copy
@@ -640,7 +645,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const int32_t cap = P->opt.reserved[7] > 0 ? P->opt.reserved[7]
                           : P->fused ? (int32_t)std::min<int64_t>(48, std::max<int64_t>(8, per_cta2 / 4)) : kChunkCapK2;
         StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
-        sd.ragged = P->fused;
+        sd.ragged = P->fused && !fused_uniform;
+        sd.record_nch = P->fused;
         std::vector<StreamDesc::Item> items;
         for (int32_t t = 0; t < nt; ++t) {
             items.clear();
@@ -665,20 +671,36 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
                 for (int w = 0; w < kFW; ++w) f.nch[w] = fused_nch1[(size_t)i * kFW + w];
                 f.tile = -1; f.grp = fused_grp1[i]; f.need = 0; f.tpr = fused_tpr1[i];
             }
-            for (int32_t i = 0; i < P->nss2; ++i) {
-                FItem& f = fi[(size_t)P->nss1 + i];
+            // Transposed items in three passes over the tiles - long, medium, short (by stage count) - so that the
+            // queue ends with small items and the tail of the kernel is a short item, not a long one.  Every
+            // item fetches its own tile, so the order is free; tile order inside a pass keeps the items whose
+            // group finishes last at the end of each pass.
+            std::vector<int32_t> perm;
+            perm.reserve(P->nss2);
+            for (int pass = 0; pass < 3; ++pass)
+                for (int32_t i = 0; i < P->nss2; ++i) {
+                    const int64_t stages = ss_cost[i];
+                    const int cls = stages > cap / 2 ? 0 : stages > std::max(2, cap / 6) ? 1 : 2;
+                    if (cls == pass) perm.push_back(i);
+                }
+            std::vector<int64_t> off2q(P->nss2 + 1, 0);
+            for (int32_t q = 0; q < P->nss2; ++q) {
+                const int32_t i = perm[q];
+                FItem& f = fi[(size_t)P->nss1 + q];
                 std::memset(&f, 0, sizeof(f));
                 for (int w = 0; w < kFW; ++w) f.nch[w] = sd.ss_nch[(size_t)i * kFW + w];
                 f.tile = ss_tile[i]; f.grp = ss_tile[i] / fused_grp_tiles;
                 f.need = kFW * fused_grp_items[f.grp]; f.tpr = sd.ss_tpr[i];
+                off2q[q] = sd.ss_off[i];
             }
+            if (upload_vec(P->offF2, off2q, st)) return VMAT_E_CUDA;
             if (upload_vec(P->itemsF, fi, st)) return VMAT_E_CUDA;
             P->nF1 = P->nss1; P->nF = P->nss1 + P->nss2;
             CU(P->syncF.alloc((size_t)(kFSyncWords + P->ngroupsF) * 4));
             CU(cudaMemsetAsync(P->syncF.p, 0, P->syncF.bytes, st));
             if (int rc = build_stream(P, P->opt.store_dtype, src_dtype, W, HU, sd.ss_off, sd.ss_tpr, sd.seg_start, sd.seg_len,
                                       sd.seg_cb, sd.rows, nullptr, nullptr, nullptr, 0, d_bcol, d_bval,
-                                      P->sell2, P->off2, P->tpr2, &sd.ss_nch)) return rc;
+                                      P->sell2, P->off2, P->tpr2, sd.ragged ? &sd.ss_nch : nullptr)) return rc;
         } else {
         // Persistent CTAs, static partition: every CTA gets the same number of ring stages.  Within a
         // tile the super-slices run from long rows (up to cap+1 stages each) to short ones (a few
@@ -840,7 +862,7 @@ template <typename VT, typename AT>
 static int launch_fused_t(vmat_plan* P, cudaStream_t st, int phase, bool inline_y, cudaEvent_t* ev) {
     FArgs<AT> a{};
     a.sell = P->sell1.as<uint4>(); a.sell2 = P->sell2.as<uint4>();
-    a.it_off = P->off1.as<int64_t>(); a.it_off2 = P->off2.as<int64_t>();
+    a.it_off = P->off1.as<int64_t>(); a.it_off2 = P->offF2.as<int64_t>();
     a.items = P->itemsF.as<FItem>(); a.n1 = P->nF1; a.nitems = P->col_mode ? P->nF1 : P->nF;
     a.nstages = P->nstagesF; a.stage_bytes = P->stage_bytesF;
     a.B = (int32_t)P->B; a.nb = P->nb; a.T = P->T; a.ntiles = P->ntiles; a.ngroups = P->ngroupsF; a.V = P->V;
@@ -1137,7 +1159,7 @@ extern "C" int vmat_get_timing(vmat_plan_t* P, double* ms, int32_t* n) {
 
 extern "C" int vmat_trace_eval(vmat_plan_t* P, uint64_t* out, int64_t cap, int32_t* k1_ctas, int32_t* k2_ctas) {
     if (!P || !out || !k1_ctas || !k2_ctas) return fail(VMAT_E_ARG, "null");
-    const size_t n = P->fused ? (size_t)P->gridF * kTraceSlots : ((size_t)P->k1_grid + (size_t)P->k2_grid) * kTraceSlots;
+    const size_t n = P->fused ? (size_t)P->gridF * (kTraceSlots + kFTraceItems * 8) : ((size_t)P->k1_grid + (size_t)P->k2_grid) * kTraceSlots;
     if (cap < (int64_t)n) return fail(VMAT_E_ARG, "vmat_trace_eval: buffer too small");
     CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());
@@ -1160,10 +1182,10 @@ extern "C" int vmat_reduce_buffer(vmat_plan_t* P, void** dev_ptr, int64_t* count
     return VMAT_OK;
 }
 
-// comm buffer: recv[2][kMaxRanks][B+1] doubles + flags[kMaxRanks][nb+1] u64, allocated on first use
+// comm buffer: recv[2 parities][kMaxRanks][B+1] entries of 16 bytes (value + epoch tags), allocated on first use
 static int comm_buffer(vmat_plan* P) {
     if (P->comm_buf.p) return 0;
-    const size_t bytes = (2 * (size_t)kMaxRanks * (size_t)(P->B + 1) + (size_t)kMaxRanks * (P->nb + 1)) * 8;
+    const size_t bytes = 2 * (size_t)kMaxRanks * (size_t)(P->B + 1) * 16;
     CU(P->comm_buf.alloc(bytes));
     CU(cudaMemset(P->comm_buf.p, 0, bytes));
     return 0;

@@ -644,103 +644,98 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
 
 // ---------------------------------------------------------------------------------
 // K3 fused with the cross-GPU exchange (multi-GPU, one rank per GPU): a push all-reduce inside
-// the reduction kernel.  Every rank owns a "comm buffer" in its HBM that all peers have mapped
-// (CUDA IPC over NVLink, or plain peer pointers inside one process):
-//     recv[parity 0..1][source rank 0..nranks-1][gb partial (B) | f partial]   doubles
-//     flags[source rank][control point 0..nb-1, then one word for the objective]  u64 epochs
-// CTA i (control point i) reduces this rank's tile partials for its beamlets and STORES them
-// into slot [parity][my rank] of every rank's buffer (remote stores are fire-and-forget, so the
-// NVLink latency is paid once, not once per peer), then publishes the evaluation's epoch in
-// flags[my rank][i] of every rank (system-scope release).  It then polls only its OWN flags -
-// local memory - until every rank has delivered control point i, and adds the nranks partials
-// from its own buffer in rank order: identical bits on every rank, no NCCL launch, no
-// rank-wide "last CTA" step (CTA i depends on the peers' CTA i only).  Two parities make a slot
-// safe to overwrite in the next evaluation: a rank can only be one evaluation ahead of a peer,
-// because finishing evaluation e needs every peer's push of e, which the peer issues after its
-// own reduction kernel of e-1 has completed (stream order).
+// the reduction kernel, with the flag carried by the data (the "LL" idea of NCCL's low-latency
+// protocol).  Every rank owns a "comm buffer" in its HBM that all peers have mapped (CUDA IPC over
+// NVLink, or plain peer pointers inside one process):
+//     recv[parity 0..1][source rank 0..nranks-1][gb partial (B) | f partial]   16 bytes per value
+// A value travels as two 8-byte words {low 32 bits | epoch << 32, high 32 bits | epoch << 32}
+// written with one 16-byte store (each 8-byte half is atomic).  CTA i (control point i) reduces this
+// rank's tile partials for its beamlets and stores them into slot [parity][my rank] of EVERY rank's
+// buffer - fire-and-forget remote stores, no fence, no separate flag.  The thread that needs value
+// j then polls its OWN buffer (local memory) until both words of every rank's entry carry this
+// evaluation's epoch, and adds the ranks in rank order: identical bits on every rank, one NVLink
+// one-way latency, no NCCL launch, no rank-wide step (a CTA depends on the peers' CTA of the same
+// control point only).  Two parities make a slot safe to overwrite in the next evaluation: a rank
+// can only be one evaluation ahead of a peer, because finishing evaluation e needs every peer's
+// values of e, which the peer stores after its own reduction of e-1 has completed (stream order).
+// Epochs are counted by the host (1, 2, ...: the same on all ranks; 0 is the cleared buffer).
 // ---------------------------------------------------------------------------------
 constexpr int kMaxRanks = 16;
 
 struct CommArgs {
     double* const* peer_bufs;     // [nranks] device pointers to every rank's comm buffer (own included)
     int32_t rank, nranks;
-    unsigned long long epoch;     // this evaluation's epoch (1, 2, ...: counted by the host, same on all ranks)
+    unsigned long long epoch;     // this evaluation's epoch
     unsigned long long timeout_ns;
     int32_t* error;               // set when a peer did not deliver within the time-out
     double* status;               // result[nb+1]: set to 1.0 by a CTA that timed out
 };
 
-__device__ __forceinline__ double ld_sys_f64(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
+// entry (parity, source rank, j) of a comm buffer, in 16-byte units
+__device__ __forceinline__ size_t comm_entry(int parity, int src, int nranks, int B, size_t j) {
+    return ((size_t)parity * nranks + src) * ((size_t)B + 1) + j;
 }
-__device__ __forceinline__ void st_sys_f64(double* p, double v) {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+__device__ __forceinline__ void ll_store(double* buf, size_t entry, double v, uint32_t ep) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v), tag = (unsigned long long)ep << 32;
+    const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};"
+                 :: "l"(reinterpret_cast<ulonglong2*>(buf) + entry), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ ulonglong2 ll_load_raw(const double* buf, size_t entry) {
+    ulonglong2 w;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(w.x), "=l"(w.y) : "l"(reinterpret_cast<const ulonglong2*>(buf) + entry) : "memory");
+    return w;
 }
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-// comm buffer geometry (doubles): data slot of (parity, source rank), then the flag words
-__device__ __forceinline__ size_t comm_slot(int parity, int src, int nranks, int B) {
-    return ((size_t)parity * nranks + src) * ((size_t)B + 1);
-}
-__device__ __forceinline__ unsigned long long* comm_flags(double* buf, int src, int nranks, int B, int nb) {
-    return reinterpret_cast<unsigned long long*>(buf + 2 * (size_t)nranks * ((size_t)B + 1)) + (size_t)src * (nb + 1);
-}
-
-// Publish "control point `cp` of this rank is delivered" to every rank (lanes 0..nranks-1 of the
-// calling warp; the data stores of the whole CTA must be ordered before by a CTA barrier), then wait
-// until every rank's delivery of `cp` has landed here.  Returns 0 on time-out (warp-uniform).
-__device__ __forceinline__ int comm_publish_and_wait(const CommArgs& c, int lane, int cp, int B, int nb) {
-    int ok = 1;
-    if (lane < c.nranks) {
-        __threadfence_system();
-        st_release_sys_u64(comm_flags(c.peer_bufs[lane], c.rank, c.nranks, B, nb) + cp, c.epoch);
-        const unsigned long long* mine = comm_flags(c.peer_bufs[c.rank], lane, c.nranks, B, nb) + cp;
-        const unsigned long long t0 = global_timer_ns();
-        unsigned int spins = 0;
-        while (ld_acquire_sys_u64(mine) < c.epoch) {
-            if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > c.timeout_ns) { ok = 0; break; }
-        }
-    }
-    return __all_sync(0xffffffffu, ok);
-}
-
-// sum over the ranks, in rank order, of entry j of the (parity, rank) slots of this rank's own buffer
-__device__ __forceinline__ double comm_sum_ranks(const double* mybuf, int parity, int nranks, int B, size_t j) {
-    double v[kMaxRanks];
+// Sum over the ranks, in rank order, of entry j of this rank's own buffer; waits for entries that have not
+// arrived yet.  Returns false on time-out.  (Loads of all ranks are issued together; late ones are retried.)
+__device__ __forceinline__ bool comm_sum_ranks(const CommArgs& c, int B, size_t j, double& out) {
+    const double* mybuf = c.peer_bufs[c.rank];
+    const int parity = (int)(c.epoch & 1ull);
+    const uint32_t ep = (uint32_t)c.epoch;
+    ulonglong2 w[kMaxRanks];
+    uint32_t missing = 0;
 #pragma unroll
     for (int q = 0; q < kMaxRanks; ++q)
-        if (q < nranks) v[q] = ld_sys_f64(mybuf + comm_slot(parity, q, nranks, B) + j);
+        if (q < c.nranks) w[q] = ll_load_raw(mybuf, comm_entry(parity, q, c.nranks, B, j));
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+        if (q < c.nranks && ((uint32_t)(w[q].x >> 32) != ep || (uint32_t)(w[q].y >> 32) != ep)) missing |= 1u << q;
+    if (missing) {
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
+        while (missing) {
+#pragma unroll
+            for (int q = 0; q < kMaxRanks; ++q)
+                if ((missing >> q) & 1u) {
+                    w[q] = ll_load_raw(mybuf, comm_entry(parity, q, c.nranks, B, j));
+                    if ((uint32_t)(w[q].x >> 32) == ep && (uint32_t)(w[q].y >> 32) == ep) missing &= ~(1u << q);
+                }
+            if (missing && (++spins & 0xffu) == 0 && global_timer_ns() - t0 > c.timeout_ns) return false;
+        }
+    }
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < kMaxRanks; ++q)
-        if (q < nranks) s += v[q];
-    return s;
+        if (q < c.nranks) s += __longlong_as_double((long long)((w[q].x & 0xffffffffull) | (w[q].y << 32)));
+    out = s;
+    return true;
 }
 
 template <typename AT>
 __global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, const CommArgs c) {
     __shared__ double sh[256];
-    __shared__ int ok_s;
     const int tid = threadIdx.x;
     pdl_launch_dependents();
     const int lo = a.beam_ptr[blockIdx.x], hi = a.beam_ptr[blockIdx.x + 1];
     pdl_wait();
     const int parity = (int)(c.epoch & 1ull);
-    const size_t slot = comm_slot(parity, c.rank, c.nranks, a.B);
-    // ---- A: this rank's partial for my beamlets (and the objective), pushed to every rank
+    const uint32_t ep = (uint32_t)c.epoch;
+    // ---- A: this rank's partial for my beamlets (and the objective), stored into every rank's buffer
     if (blockIdx.x == 0) {
         double fv = strided_sum(a.fblock, tid, 256, a.nfblock);
         fv = block_sum_256(fv, sh);
-        if (tid < c.nranks) st_sys_f64(c.peer_bufs[tid] + slot + a.B, fv);
+        if (tid < c.nranks) ll_store(c.peer_bufs[tid], comm_entry(parity, c.rank, c.nranks, a.B, (size_t)a.B), fv, ep);
     }
     for (int j0 = lo; j0 < hi; j0 += 64) {
         const int j = j0 + (tid >> 2), q = tid & 3;
@@ -748,43 +743,25 @@ __global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, co
         if (j < hi) s = strided_sum(a.partial + j, (int64_t)q * a.B, (int64_t)4 * a.B, (int64_t)a.ntiles * a.B);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);       // all four lanes hold the sum: lane q serves ranks q, q+4, ...
-        if (j < hi) for (int p = q; p < c.nranks; p += 4) st_sys_f64(c.peer_bufs[p] + slot + j, s);
+        if (j < hi) for (int p = q; p < c.nranks; p += 4) ll_store(c.peer_bufs[p], comm_entry(parity, c.rank, c.nranks, a.B, (size_t)j), s, ep);
     }
-    __syncthreads();
-    // ---- B: publish, then wait for every rank's delivery of this control point (own memory only)
-    if (tid < 32) {
-        const int ok = comm_publish_and_wait(c, tid, blockIdx.x, a.B, a.nb);
-        if (tid == 0) {
-            ok_s = ok;
-            if (!ok) { atomicExch(c.error, 1); *c.status = 1.0; }
-        }
-    }
-    __syncthreads();
-    // ---- C: add the ranks' partials in rank order
-    const double* mybuf = c.peer_bufs[c.rank];
+    // ---- B/C: add the ranks' partials in rank order as they arrive in this rank's own buffer
     double contrib = 0.0;
-    if (ok_s) {
-        for (int j = lo + tid; j < hi; j += 256) {
-            const double s = comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)j);
-            a.gbf[j] = s;
-            contrib += a.w_grad[j] * s;
-        }
+    int ok = 1;
+    for (int j = lo + tid; j < hi; j += 256) {
+        double s = 0.0;
+        if (!comm_sum_ranks(c, a.B, (size_t)j, s)) { ok = 0; break; }
+        a.gbf[j] = s;
+        contrib += a.w_grad[j] * s;
     }
+    double f = 0.0;
+    if (blockIdx.x == 0 && tid == 0 && ok) ok = comm_sum_ranks(c, a.B, (size_t)a.B, f) ? 1 : 0;
+    ok = __syncthreads_and(ok);
     const double g = block_sum_256(contrib, sh);
-    if (tid == 0) a.result[1 + blockIdx.x] = ok_s ? g : nan("");
-    if (blockIdx.x == 0) {
-        // the objective has its own flag word (index nb), like in the fused evaluation kernel, so that ranks
-        // running either kernel can be mixed
-        __syncthreads();
-        if (tid < 32) {
-            const int ok = ok_s ? comm_publish_and_wait(c, tid, a.nb, a.B, a.nb) : 0;
-            if (tid == 0) {
-                if (!ok && ok_s) { atomicExch(c.error, 1); *c.status = 1.0; }
-                const double f = ok ? comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)a.B) : nan("");
-                a.gbf[a.B] = f;
-                a.result[0] = f;
-            }
-        }
+    if (tid == 0) {
+        a.result[1 + blockIdx.x] = ok ? g : nan("");
+        if (blockIdx.x == 0) { a.gbf[a.B] = ok ? f : nan(""); a.result[0] = ok ? f : nan(""); }
+        if (!ok) { atomicExch(c.error, 1); *c.status = 1.0; }
     }
 }
 

@@ -39,11 +39,13 @@
 namespace vmat {
 
 constexpr int kFW = 16;                  // consumer warps per CTA
-constexpr int kFThreads = (kFW + 1) * 32;
+constexpr int kFWarps = kFW + 2;         // + producer warp + signal warp
+constexpr int kFThreads = kFWarps * 32;
 constexpr int kFMaxStages = 16;
+constexpr int kFTraceItems = 32;         // items per CTA covered by the per-item diagnostics (vmat_trace_eval)
 constexpr int kFSyncWords = 16;          // sync[0] queue, [1] barrier arrivals, [2] barrier generation, [3] objective shares done; groups follow
 
-struct FItem {                           // one queue item (32 bytes)
+struct __align__(16) FItem {             // one queue item (32 bytes)
     uint8_t nch[kFW];                    // chunks of warp w, non-increasing in w
     int32_t tile;                        // transposed item: voxel tile; dose item: -1
     int32_t grp;                         // dose item: group to signal; transposed item: group to wait for
@@ -52,7 +54,7 @@ struct FItem {                           // one queue item (32 bytes)
 };
 static_assert(sizeof(FItem) == 32, "FItem layout");
 
-struct FStage {                          // what the producer tells the consumers about a ring slot
+struct __align__(16) FStage {            // what the producer tells the consumers about a ring slot
     int32_t item;                        // -1: no more work
     int32_t tile;                        // -1 for dose items
     int32_t grp;
@@ -103,10 +105,26 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// one bounded hardware wait (the thread sleeps until the phase completes or a time limit expires)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned int atom_add_release_gpu(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -138,7 +156,7 @@ __device__ __forceinline__ double strided_sum_cg(const T* __restrict__ src, int6
     return s;
 }
 
-// fixed-shape sum over the kFThreads threads of the CTA: warp butterflies, then the 17 warp sums in order
+// fixed-shape sum over the kFThreads threads of the CTA: warp butterflies, then the 18 warp sums in order
 __device__ __forceinline__ double block_sum_f(double v, double* sh) {
     v = warp_sum(v);
     __syncthreads();
@@ -146,7 +164,7 @@ __device__ __forceinline__ double block_sum_f(double v, double* sh) {
     __syncthreads();
     double r = 0.0;
 #pragma unroll
-    for (int w = 0; w < kFW + 1; ++w) r += sh[w];
+    for (int w = 0; w < kFWarps; ++w) r += sh[w];
     return r;
 }
 
@@ -156,8 +174,10 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kFMaxStages], empty[kFMaxStages], tile_full[2], tile_empty[2], x_free;
     __shared__ __align__(16) FStage sinfo[kFMaxStages];
-    __shared__ double red[kFW + 1];
-    __shared__ int ok_s;
+    __shared__ double red[kFWarps];
+    // dose-slice announcements (see the signal warp): one barrier per CTA-local dose item, modulo 16
+    __shared__ __align__(8) uint64_t sbar[16];
+    __shared__ int scmd[16];
     const int xbytes = (a.B * (int)sizeof(AT) + 127) & ~127;
     const int ybytes = (a.nb * 8 + 127) & ~127;
     const int tbytes = (a.T * (int)sizeof(AT) + 127) & ~127;
@@ -169,6 +189,10 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
     const int nst = a.nstages, SB = a.stage_bytes;
     const unsigned int G = gridDim.x;
     unsigned long long* const trace = a.trace ? a.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
+    // diagnostics: per CTA, 8 stamps for each of its first kFTraceItems items (after the per-CTA block):
+    // producer [0] item known, [1] header pushed, [2] all stages pushed, [3] next item claimed;
+    // consumer warp 0 [4] header seen, [5] header done (tile there), [6] last chunk done, [7] epilogue done
+    unsigned long long* const itrace = a.trace ? a.trace + (size_t)gridDim.x * kTraceSlots + (size_t)blockIdx.x * kFTraceItems * 8 : nullptr;
     unsigned int* const grp_done = a.sync + kFSyncWords;
 
     if (tid == 0) {
@@ -177,6 +201,7 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
         mbar_init(&tile_full[0], 1); mbar_init(&tile_full[1], 1);
         mbar_init(&tile_empty[0], W); mbar_init(&tile_empty[1], W);
         mbar_init(&x_free, W);
+        for (int k = 0; k < 16; ++k) mbar_init(&sbar[k], W);
         fence_barrier_init();
     }
     pdl_launch_dependents();
@@ -222,25 +247,39 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
     if (trace && tid == 0) trace[1] = global_timer_ns();
 
     if (warp == W) {
-        // ---------------- producer: one thread streams items into the ring -------------------
-        if (lane == 0) {
+        // ---------------- producer warp: streams items into the ring ---------------------------------
+        // All lanes walk the item loop together; the stages of an item are pushed in batches of NB, one
+        // lane per stage, so the per-stage bookkeeping (active warps, stream offset, ring slot) is done
+        // once per batch in SIMD instead of once per stage by a single thread - a one-thread producer
+        // needed ~0.5 us per stage and starved the consumers (measured: 102 us per evaluation on config 2
+        // against 65 us for the three kernels, the consumers waiting on `full` a third of the time).  A lane
+        // issues its copy as soon as its own slot is free; slots free in ring order, so lanes finish in
+        // order and a batch never holds back a copy that could have been issued.  Lane 0 takes the LAST
+        // stage of a batch: it waits the longest and is the one that polls a pending tile fetch meanwhile.
+        {
             const uint64_t pol = l2_evict_first_policy();
-            RingPos pos;
+            const int NB = min(8, nst);
+            const unsigned int unst = (unsigned)nst;
+            unsigned int abs_pos = 0;          // ring stages pushed so far (header and data stages)
             const unsigned int ni = (unsigned)a.nitems;
             const int lead = a.claim_lead;
             unsigned int cur = blockIdx.x;
             bool first = true;                 // the first item is assigned statically; nothing written by the previous evaluation has been touched yet
             int ntile_use = 0;                 // transposed items of this CTA so far
-            // tile fetch in flight for the current transposed item (issued as soon as buffer and group allow)
+            // tile fetch in flight for the current transposed item (lane 0 issues it as soon as buffer and group allow)
             bool tile_pending = false, tile_buf_free = false, tile_grp_ready = false;
             int tb = 0; uint32_t tp = 0; int tgrp = 0; unsigned int tneed = 0; int ttile = 0;
+            unsigned long long ready_mask = 0ull;       // groups whose dose items were seen complete
             // Every barrier arrival is anonymous, so each consumer warp must arrive exactly once per phase:
             // once on x_free (it has read x for the last time), once on tile_empty[b] per item that used
             // buffer b - and it can reach that item's header only after the tile has landed, i.e. after the
             // phase of the buffer's previous item is complete.  The first use of a buffer waits for x_free.
             auto poll_tile = [&]() {
                 if (!tile_buf_free) tile_buf_free = ntile_use <= 2 ? mbar_test(&x_free, 0u) : mbar_test(&tile_empty[tb], tp ^ 1u);
-                if (tile_buf_free && !tile_grp_ready) tile_grp_ready = ld_acquire_gpu_u32(grp_done + tgrp) >= tneed;
+                if (tile_buf_free && !tile_grp_ready) {
+                    if (tgrp < 64 && ((ready_mask >> tgrp) & 1ull)) tile_grp_ready = true;       // seen complete before
+                    else if (ld_acquire_gpu_u32(grp_done + tgrp) >= tneed) { tile_grp_ready = true; if (tgrp < 64) ready_mask |= 1ull << tgrp; }
+                }
                 if (tile_buf_free && tile_grp_ready) {
                     fence_proxy_async_all();           // vg was written through the generic proxy by other SMs
                     const int64_t base = (int64_t)ttile * a.T;
@@ -251,74 +290,126 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                     tile_pending = false;
                 }
             };
-            auto push = [&](const FStage& info, const void* src, uint32_t bytes) {
-                while (!mbar_test(&empty[pos.stage], pos.phase ^ 1u)) { if (tile_pending) poll_tile(); }
-                sinfo[pos.stage] = info;
-                if (bytes) {
-                    mbar_expect_tx(&full[pos.stage], bytes);
-                    tma_bulk_g2s_hint(ring + (size_t)pos.stage * SB, src, bytes, &full[pos.stage], pol);
-                } else {
-                    mbar_arrive(&full[pos.stage]);
+            // push ring stage number `at` (slot at % nst, lap at / nst): wait for the slot, describe it, start the copy
+            auto push_at = [&](unsigned int at, const uint4 w0, const uint4 w1, const void* src, uint32_t bytes, bool poller) {
+                const unsigned int lap = at / unst, slot = at - lap * unst;
+                for (;;) {
+                    // try_wait sleeps in hardware and returns now and then, which is when a pending tile is polled
+                    if (mbar_try_wait(&empty[slot], (lap & 1u) ^ 1u)) {
+                        reinterpret_cast<uint4*>(&sinfo[slot])[0] = w0;
+                        reinterpret_cast<uint4*>(&sinfo[slot])[1] = w1;
+                        if (bytes) {
+                            mbar_expect_tx(&full[slot], bytes);
+                            tma_bulk_g2s_hint(ring + (size_t)slot * SB, src, bytes, &full[slot], pol);
+                        } else {
+                            mbar_arrive(&full[slot]);
+                        }
+                        break;
+                    }
+                    if (poller && tile_pending) poll_tile();
                 }
-                pos.advance(nst);
-                if (tile_pending) poll_tile();
             };
-            FItem it{};
+            // an item's metadata as two 16-byte loads: {nch[16]} and {tile, grp, need, tpr}
+            uint4 nchw = make_uint4(0u, 0u, 0u, 0u);
+            int4 meta = make_int4(-1, 0, 0, 1);
             const uint4* o0 = nullptr;
             const unsigned int n1u = (unsigned)a.n1;
             auto item_base = [&](unsigned int q) -> const uint4* {
                 return q < n1u ? a.sell + a.it_off[q] : a.sell2 + a.it_off2[q - n1u];
             };
-            if (cur < ni) { it = a.items[cur]; o0 = item_base(cur); }
+            auto load_item = [&](unsigned int q, uint4& n, int4& m) {
+                const uint4* ip = reinterpret_cast<const uint4*>(a.items + q);
+                n = __ldg(ip);
+                const uint4 v1 = __ldg(ip + 1);
+                m = make_int4((int)v1.x, (int)v1.y, (int)v1.z, (int)(v1.w & 0xffu));
+            };
+            if (cur < ni) { load_item(cur, nchw, meta); o0 = item_base(cur); }
+            int pk = 0;                        // items of this CTA so far (diagnostics)
             while (cur < ni) {
-                const bool dose = it.tile < 0;
+                const int it_tile = meta.x, it_grp = meta.y, it_need = meta.z, it_tpr = meta.w;
+                unsigned long long* const its = (itrace && pk < kFTraceItems && lane == 0) ? itrace + pk * 8 : nullptr;
+                ++pk;
+                if (its) its[0] = global_timer_ns();
+                const bool dose = it_tile < 0;
                 const int HU = dose ? HU1 : HU2;
-                const int nch0 = it.nch[0];
+                const int nch0 = (int)(nchw.x & 0xffu);
                 if (!dose) {
                     if (first) { pdl_wait(); first = false; }      // grp_done is about to be read
                     tb = ntile_use & 1; tp = (uint32_t)(ntile_use >> 1) & 1u; ++ntile_use;
-                    tgrp = it.grp; tneed = (unsigned)it.need; ttile = it.tile;
+                    tgrp = it_grp; tneed = (unsigned)it_need; ttile = it_tile;
                     tile_pending = true; tile_buf_free = false; tile_grp_ready = false;
                 }
-                FStage info{};
-                info.item = (int32_t)cur; info.tile = it.tile; info.grp = it.grp;
-                info.kact = W; info.tpr = it.tpr; info.tbuf = (uint8_t)(tb | (tp << 1));
-#pragma unroll
-                for (int w = 0; w < W; ++w) info.nch[w] = it.nch[w];
-                info.flags = (uint8_t)(kStageHeader | (nch0 == 0 ? kStageLast : 0));
-                push(info, o0, (uint32_t)(W * HU * 16));
+                // FStage as two 16-byte words: {item, tile, grp, flags | kact << 8 | tpr << 16 | tbuf << 24}, {nch[16]}
+                const uint32_t tail = ((uint32_t)it_tpr << 16) | ((uint32_t)(tb | (tp << 1)) << 24);
+                if (lane == 0) {
+                    push_at(abs_pos, make_uint4(cur, (uint32_t)it_tile, (uint32_t)it_grp,
+                                                (uint32_t)(kStageHeader | (nch0 == 0 ? kStageLast : 0)) | ((uint32_t)W << 8) | tail),
+                            nchw, o0, (uint32_t)(W * HU * 16), true);
+                    if (tile_pending) poll_tile();
+                    if (its) its[1] = global_timer_ns();
+                }
+                __syncwarp();
                 const uint4* data = o0 + W * HU;
                 unsigned int nxt = 0u;
-                FItem nit{};
+                uint4 nnch = make_uint4(0u, 0u, 0u, 0u);
+                int4 nmeta = make_int4(-1, 0, 0, 1);
                 const uint4* n0 = nullptr;
-                bool claimed = false, loaded = false;
-                const int c_claim = max(0, nch0 - lead), c_load = min(c_claim + 4, max(0, nch0 - 1));
-                int kact = W;
-                while (kact > 0 && it.nch[kact - 1] == 0) --kact;
-                int64_t off = 0;
-                info.flags = 0;
-                for (int cc = 0; cc < nch0; ++cc) {
-                    while (kact > 0 && it.nch[kact - 1] <= cc) --kact;
-                    if (!first) {
-                        if (cc == c_claim) { nxt = G + atomicAdd(a.sync, 1u); claimed = true; }
-                        if (cc == c_load && claimed) {
-                            if (nxt < ni) { nit = a.items[nxt]; n0 = item_base(nxt); }
-                            loaded = true;
-                        }
+                bool claimed = false;
+                const int c_claim = max(0, nch0 - lead);
+                for (int c0 = 0; c0 < nch0; c0 += NB) {
+                    if (!first && !claimed && c0 + NB > c_claim) {      // claim the next item while the last stages go out
+                        if (lane == 0) nxt = G + atomicAdd(a.sync, 1u);
+                        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+                        claimed = true;
+                        if (nxt < ni) { load_item(nxt, nnch, nmeta); n0 = item_base(nxt); }
                     }
-                    info.kact = (uint8_t)kact;
-                    push(info, data + off, (uint32_t)(kact * KU * 16));
-                    off += (int64_t)kact * KU;
+                    const int nact = min(NB, nch0 - c0);
+                    if (lane < nact) {
+                        const int cc = c0 + (lane == 0 ? nact - 1 : lane - 1);
+                        // warps with a chunk in stage cc, and where the stage starts: KU * sum_w min(nch_w, cc)
+                        const uint32_t crep = (uint32_t)cc * 0x01010101u;
+                        const int kact = (__popc(__vcmpgtu4(nchw.x, crep)) + __popc(__vcmpgtu4(nchw.y, crep)) +
+                                          __popc(__vcmpgtu4(nchw.z, crep)) + __popc(__vcmpgtu4(nchw.w, crep))) >> 3;
+                        const uint32_t before = __dp4a(__vminu4(nchw.x, crep), 0x01010101u, 0u) + __dp4a(__vminu4(nchw.y, crep), 0x01010101u, 0u) +
+                                                __dp4a(__vminu4(nchw.z, crep), 0x01010101u, 0u) + __dp4a(__vminu4(nchw.w, crep), 0x01010101u, 0u);
+                        push_at(abs_pos + 1u + (unsigned)cc,
+                                make_uint4(cur, (uint32_t)it_tile, (uint32_t)it_grp, ((uint32_t)kact << 8) | tail), nchw,
+                                data + (int64_t)before * KU, (uint32_t)(kact * KU * 16), lane == 0);
+                    }
+                    __syncwarp();
+                    if (lane == 0 && tile_pending) poll_tile();
                 }
-                while (tile_pending) poll_tile();            // (only when the item had fewer stages than the ring)
+                if (lane == 0) { while (tile_pending) poll_tile(); }      // (only when the item had fewer stages than the ring)
+                __syncwarp();
+                if (its) its[2] = global_timer_ns();
+                abs_pos += 1u + (unsigned)nch0;
                 if (first) { pdl_wait(); first = false; }    // the queue counter was reset by the previous evaluation
-                if (!claimed) nxt = G + atomicAdd(a.sync, 1u);
-                if (!loaded && nxt < ni) { nit = a.items[nxt]; n0 = item_base(nxt); }
-                cur = nxt; it = nit; o0 = n0;
+                if (!claimed) {
+                    if (lane == 0) nxt = G + atomicAdd(a.sync, 1u);
+                    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+                    if (nxt < ni) { load_item(nxt, nnch, nmeta); n0 = item_base(nxt); }
+                }
+                cur = nxt; nchw = nnch; meta = nmeta; o0 = n0;
+                if (its) its[3] = global_timer_ns() | (unsigned long long)(o0 != nullptr);     // (uses the loaded values)
             }
-            FStage fin{};
-            fin.item = -1;
-            push(fin, nullptr, 0);
+            if (lane == 0) push_at(abs_pos, make_uint4(0xffffffffu, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), nullptr, 0, false);
+        }
+    } else if (warp == W + 1) {
+        // ---------------- signal warp: announces finished dose items to the other CTAs ----------------------
+        // Barrier k (mod 16) completes when all 16 consumer warps have stored d / vg of this CTA's k-th dose
+        // item (they cannot be 16 items apart: the ring has at most 16 slots and every item has a header
+        // stage).  The barrier orders their stores before this thread at CTA scope; its gpu-scope fence then
+        // orders them before the counter update for everybody (cumulativity), so a producer that sees
+        // grp_done[g] complete may fetch the group's vg.
+        if (lane == 0) {
+            pdl_wait();
+            for (int k = 0;; ++k) {
+                mbar_wait(&sbar[k & 15], (uint32_t)(k >> 4) & 1u);
+                const int g = scmd[k & 15];
+                if (g < 0) break;
+                __threadfence();
+                atomicAdd(grp_done + g, (unsigned)W);
+            }
         }
     } else {
         // ---------------- consumers: warp w owns slice w of every item -----------------------------
@@ -328,17 +419,28 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
         uint32_t cur = 0;
         int my_nch = 0, cdone = 0, tpr = 1, item = 0, grp = 0, tile = -1, tbuf = 0;
         bool dose = true, x_released = false;
+        // A finished dose slice is announced to the signal warp through a CTA-local barrier (cheap); the
+        // gpu-scope release fence in front of the grp_done update costs about 1 us under load (measured), so
+        // it is taken by the signal warp, off the consumers' path.  dk counts this CTA's dose items.
+        int dk = 0;
+        bool dose_over = false;
+        int ck = -1;                           // items seen so far (diagnostics)
+        unsigned long long* its = nullptr;
         const AT* vt = reinterpret_cast<const AT*>(smem_raw);
         if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }
         while (true) {
             mbar_wait(&full[pos.stage], pos.phase);
             const FStage* sp = &sinfo[pos.stage];
-            const int s_item = sp->item;
+            const uint4 sw = *reinterpret_cast<const uint4*>(sp);
+            const int s_item = (int)sw.x;
             if (s_item < 0) break;
-            const int s_flags = sp->flags;
+            const int s_flags = (int)(sw.w & 0xffu), s_kact = (int)((sw.w >> 8) & 0xffu);
             bool finished = false;
             if (s_flags & kStageHeader) {
-                item = s_item; tile = sp->tile; grp = sp->grp; tpr = sp->tpr; my_nch = sp->nch[warp];
+                ++ck;
+                its = (itrace && ck < kFTraceItems && tid == 0) ? itrace + ck * 8 : nullptr;
+                if (its) its[4] = global_timer_ns();
+                item = s_item; tile = (int)sw.y; grp = (int)sw.z; tpr = (int)((sw.w >> 16) & 0xffu); my_nch = sp->nch[warp];
                 dose = tile < 0;
                 cdone = 0;
                 acc = (AT)0;
@@ -349,10 +451,14 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                     ov = reinterpret_cast<const AT*>(hp + 128 + 32 * sizeof(AT))[lane];
                     un = reinterpret_cast<const AT*>(hp + 128 + 64 * sizeof(AT))[lane];
                 } else {
-                    const int tb2 = sp->tbuf;
+                    const int tb2 = (int)(sw.w >> 24);
                     tbuf = tb2 & 1;
                     if (!x_released) {       // first transposed item: no dose item follows, the x region becomes the tile buffers
                         x_released = true;
+                        if (tid == 0) scmd[dk & 15] = -1;              // no more dose items: the signal warp can go
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sbar[dk & 15]);
+                        dose_over = true;
                         if (trace && tid == 0) trace[3] = global_timer_ns();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&x_free);
@@ -363,8 +469,9 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[pos.stage]);
+                if (its) its[5] = global_timer_ns();
                 finished = my_nch == 0;
-            } else if (warp < (int)sp->kact) {
+            } else if (warp < s_kact) {
                 const int warp_off = warp * (KU * 16);
                 ChunkRegs<AT> A;
                 chunk_load<VT, AT, IW>(ring + (size_t)pos.stage * SB + warp_off, lane, A, cur);
@@ -406,6 +513,7 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                 if (lane == 0) mbar_arrive(&empty[pos.stage]);
             }
             if (finished) {
+                if (its) its[6] = global_timer_ns();
                 for (int o = 1; o < tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // tpr lanes of a row
                 if (dose) {
                     double fterm = 0.0;
@@ -423,16 +531,25 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                     }
                     fterm = warp_sum(fterm);
                     if (lane == 0) a.fpart[(int64_t)item * W + warp] = fterm;
+                    if (tid == 0) scmd[dk & 15] = grp;
                     __syncwarp();
-                    if (lane == 0) red_release_gpu_add(grp_done + grp, 1u);      // this slice's vg is visible
+                    if (lane == 0) mbar_arrive(&sbar[dk & 15]);                   // d, vg of this slice are stored
+                    ++dk;
                 } else {
                     if (row >= 0) a.partial[(int64_t)tile * a.B + row] = acc;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tile_empty[tbuf]);                // done with this tile buffer
                 }
+                if (its) its[7] = global_timer_ns();
             }
             pos.advance(nst);
         }
+        if (!dose_over) {
+            if (tid == 0) scmd[dk & 15] = -1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sbar[dk & 15]);
+        }
+        __threadfence();      // this warp's partial / fpart stores, while the other warps are still working
     }
     if (trace && tid == 0) trace[4] = global_timer_ns();
     if (a.dose_only) return;
@@ -440,17 +557,10 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
     // ---------------- all transposed partials of all CTAs are written: grid barrier -----------------
     __syncthreads();
     if (tid == 0) {
-        const unsigned int gen = ld_acquire_gpu_u32(a.sync + 2);
-        __threadfence();
-        if (atomicAdd(a.sync + 1, 1u) == G - 1) {
-            a.sync[0] = 0u;                                   // queue and group counters for the next evaluation
-            a.sync[1] = 0u;
-            for (int g = 0; g < a.ngroups; ++g) grp_done[g] = 0u;
-            __threadfence();
-            red_release_gpu_add(a.sync + 2, 1u);
-        } else {
-            while (ld_acquire_gpu_u32(a.sync + 2) == gen) { }
-        }
+        // sync[1] counts arrivals of all launches (never reset): this launch's arrivals take it from k*G to (k+1)*G
+        const unsigned int old = atom_add_release_gpu(a.sync + 1, 1u);
+        const unsigned int target = (old / G + 1u) * G;
+        while ((int)(ld_acquire_gpu_u32(a.sync + 1) - target) < 0) { }
     }
     __syncthreads();
     if (trace && tid == 0) trace[5] = global_timer_ns();
@@ -466,72 +576,76 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
         if (lane == 0) { a.fblock[blockIdx.x] = v; red_release_gpu_add(a.sync + 3, 1u); }
     }
     // ---------------- control points blockIdx.x, blockIdx.x + G, ...: tile partials -> gb -> g ------
+    // (the objective's second level is done by CTA nb % G, one with the fewest control points)
     const bool multi = c.nranks > 1;
     const int parity = (int)(c.epoch & 1ull);
-    const size_t slot = multi ? comm_slot(parity, c.rank, c.nranks, a.B) : 0;
-    for (int cp = blockIdx.x; cp < a.nb; cp += (int)G) {
-        const int lo = a.beam_ptr[cp], hi = a.beam_ptr[cp + 1];
-        double contrib = 0.0;
-        for (int j0 = lo; j0 < hi; j0 += kFThreads / 4) {
-            // 4 threads per beamlet: thread q sums tiles t = q, q+4, ...; combined (q0+q1)+(q2+q3)
-            const int j = j0 + (tid >> 2), q = tid & 3;
-            double s = 0.0;
-            if (j < hi) s = strided_sum_cg(a.partial + j, (int64_t)q * a.B, (int64_t)4 * a.B, (int64_t)a.ntiles * a.B);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (j < hi) {
-                if (multi) { for (int p = q; p < c.nranks; p += 4) st_sys_f64(c.peer_bufs[p] + slot + j, s); }
-                else if (q == 0) { a.gbf[j] = s; contrib += a.w_grad[j] * s; }
-            }
-        }
-        if (multi) {
-            __syncthreads();
-            if (tid < 32) {
-                const int ok = comm_publish_and_wait(c, tid, cp, a.B, a.nb);
-                if (tid == 0) {
-                    ok_s = ok;
-                    if (!ok) { atomicExch(c.error, 1); *c.status = 1.0; }
-                }
-            }
-            __syncthreads();
-            if (ok_s) {
-                const double* mybuf = c.peer_bufs[c.rank];
-                for (int j = lo + tid; j < hi; j += kFThreads) {
-                    const double s = comm_sum_ranks(mybuf, parity, c.nranks, a.B, (size_t)j);
-                    a.gbf[j] = s;
-                    contrib += a.w_grad[j] * s;
-                }
-            }
-        }
-        const double g = block_sum_f(contrib, red);
-        if (tid == 0) a.result[1 + cp] = (!multi || ok_s) ? g : nan("");
-        __syncthreads();
-    }
-    // ---------------- objective, second level (CTA 0): the per-CTA shares in index order --------------
-    if (blockIdx.x == 0) {
+    const uint32_t ep = (uint32_t)c.epoch;
+    const bool fcta = (int)blockIdx.x == a.nb % (int)G;
+    double fv = 0.0;
+    if (fcta) {     // the per-CTA shares in index order
         if (tid == 0) {
             while (ld_acquire_gpu_u32(a.sync + 3) < G) { }
             a.sync[3] = 0u;
+            a.sync[0] = 0u;                                   // queue and group counters for the next evaluation:
+            for (int g = 0; g < a.ngroups; ++g) grp_done[g] = 0u;     // everybody is past the barrier, nobody reads them any more
         }
         __syncthreads();
-        double fv = strided_sum_cg(a.fblock, (int64_t)tid, (int64_t)kFThreads, (int64_t)G);
+        fv = strided_sum_cg(a.fblock, (int64_t)tid, (int64_t)kFThreads, (int64_t)G);
         fv = block_sum_f(fv, red);
-        if (!multi) {
-            if (tid == 0) { a.gbf[a.B] = fv; a.result[0] = fv; }
-        } else {
-            if (tid < c.nranks) st_sys_f64(c.peer_bufs[tid] + slot + a.B, fv);
-            __syncthreads();
-            if (tid < 32) {
-                const int ok = comm_publish_and_wait(c, tid, a.nb, a.B, a.nb);     // flag slot nb: the objective
-                if (tid == 0) {
-                    double f = nan("");
-                    if (ok) f = comm_sum_ranks(c.peer_bufs[c.rank], parity, c.nranks, a.B, (size_t)a.B);
-                    else { atomicExch(c.error, 1); *c.status = 1.0; }
-                    a.gbf[a.B] = f;
-                    a.result[0] = f;
-                }
+        __syncthreads();
+        if (multi) { if (tid < c.nranks) ll_store(c.peer_bufs[tid], comm_entry(parity, c.rank, c.nranks, a.B, (size_t)a.B), fv, ep); }
+        else if (tid == 0) { a.gbf[a.B] = fv; a.result[0] = fv; }
+    }
+    // A: this rank's sums over the tiles; single GPU: that is gb; multi-GPU: stored into every rank's buffer
+    for (int cp = blockIdx.x; cp < a.nb; cp += (int)G) {
+        const int lo = a.beam_ptr[cp], hi = a.beam_ptr[cp + 1];
+        double contrib = 0.0;
+        for (int j0 = lo; j0 < hi; j0 += kFThreads / 8) {
+            // 8 threads per beamlet: thread q sums tiles t = q, q+8, ...; combined ((q0+q1)+(q2+q3))+((q4+q5)+(q6+q7))
+            const int j = j0 + (tid >> 3), q = tid & 7;
+            double s = 0.0;
+            if (j < hi) s = strided_sum_cg(a.partial + j, (int64_t)q * a.B, (int64_t)8 * a.B, (int64_t)a.ntiles * a.B);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (j < hi) {
+                if (multi) { for (int p = q; p < c.nranks; p += 8) ll_store(c.peer_bufs[p], comm_entry(parity, c.rank, c.nranks, a.B, (size_t)j), s, ep); }
+                else if (q == 0) { a.gbf[j] = s; contrib += a.w_grad[j] * s; }
             }
         }
+        if (!multi) {
+            const double g = block_sum_f(contrib, red);
+            if (tid == 0) a.result[1 + cp] = g;
+            __syncthreads();
+        }
+    }
+    if (multi) {
+        // B/C: all of this CTA's values are on their way; add the ranks' parts in rank order as they arrive in
+        // this rank's own buffer (identical bits on every rank)
+        int ok = 1;
+        for (int cp = blockIdx.x; cp < a.nb; cp += (int)G) {
+            const int lo = a.beam_ptr[cp], hi = a.beam_ptr[cp + 1];
+            double contrib = 0.0;
+            for (int j = lo + tid; j < hi && ok; j += kFThreads) {
+                double s = 0.0;
+                if (!comm_sum_ranks(c, a.B, (size_t)j, s)) { ok = 0; break; }
+                a.gbf[j] = s;
+                contrib += a.w_grad[j] * s;
+            }
+            ok = __syncthreads_and(ok);
+            const double g = block_sum_f(contrib, red);
+            if (tid == 0) a.result[1 + cp] = ok ? g : nan("");
+            __syncthreads();
+        }
+        if (fcta) {
+            if (tid == 0) {
+                double f = 0.0;
+                if (ok && !comm_sum_ranks(c, a.B, (size_t)a.B, f)) ok = 0;
+                a.gbf[a.B] = ok ? f : nan("");
+                a.result[0] = ok ? f : nan("");
+            }
+        }
+        if (tid == 0 && !ok) { atomicExch(c.error, 1); *c.status = 1.0; }
     }
     if (trace && tid == 0) trace[6] = global_timer_ns();
 }

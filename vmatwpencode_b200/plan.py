@@ -63,7 +63,7 @@ class DosePlan:
         opt.reserved[6] = claim_lead           # dose kernel: stages before a super-slice's end at which the next is claimed (0 = default)
         opt.reserved[7] = k2_chunk_cap         # chunk cap of the transposed layout (chunk_cap is the dose layout's)
         opt.reserved[5] = index_bytes          # 4 forces int32 column indices, 1 byte deltas; 0 = uint16 whenever they fit
-        opt.reserved[8] = fused                # 0 = one fused evaluation kernel when it fits, 1 = the three kernels, 2 = fused or fail
+        opt.reserved[8] = fused                # 0 / 1 = the three kernels K1/K2/K3 (default), 2 = the single fused evaluation kernel
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         over = np.ascontiguousarray(over, dtype=np.float64)
@@ -177,12 +177,18 @@ class DosePlan:
     def trace_eval(self):
         """One evaluation with per-CTA time stamps: (k1[ctas, 5], k2[ctas, 5]) in ns relative to the
         earliest stamp; columns = entry, inputs ready, first stage landed, consumers done, producer done."""
-        buf = np.zeros(8 * 4096, dtype=np.uint64)
+        buf = np.zeros(8 * 4096 * 40, dtype=np.uint64)
         n1, n2 = C.c_int32(), C.c_int32()
         check(self._lib.vmat_trace_eval(self._h, _ptr(buf), buf.size, C.byref(n1), C.byref(n2)), "vmat_trace_eval")
-        t = buf[:8 * (n1.value + n2.value)].reshape(-1, 8)[:, :5].astype(np.int64)
-        t0 = t[t > 0].min()
-        t = np.where(t > 0, t - t0, -1)
+        self.trace_items = None
+        if n2.value == 0:       # fused kernel: per-item stamps of every CTA follow the per-CTA block
+            it = buf[8 * n1.value: 8 * n1.value + n1.value * 32 * 8].reshape(n1.value, 32, 8).astype(np.int64)
+            self.trace_items = it
+        full = buf[:8 * (n1.value + n2.value)].reshape(-1, 8).astype(np.int64)
+        t0 = full[full > 0].min()
+        full = np.where(full > 0, full - t0, -1)
+        self.trace_raw = full            # all 8 slots (the fused kernel uses 7: see tools/fused_probe.py)
+        t = full[:, :5]
         return t[:n1.value], t[n1.value:]
 
     def reduce_buffer(self):
