@@ -47,7 +47,7 @@ class ClockSampler:
                ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, index=0):
-        self.index, self.sm, self.bits, self.marks = index, [], 0, []
+        self.index, self.sm, self.bits, self.label = index, {}, {}, "headline"
         self.stop_flag = threading.Event()
         self.loaded = threading.Event()          # set while a timed region is running
         self.nv = self.h = self.t = None
@@ -70,8 +70,9 @@ class ClockSampler:
         while not self.stop_flag.is_set():
             if self.loaded.is_set():
                 try:
-                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    lab = self.label
+                    self.sm.setdefault(lab, []).append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.bits[lab] = self.bits.get(lab, 0) | int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     pass
                 time.sleep(0.0002)
@@ -79,13 +80,18 @@ class ClockSampler:
                 time.sleep(0.0005)
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+
+    def summary(self, label):
+        """Clocks seen while the timed regions of workload `label` ran."""
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
-        self.stop_flag.set()
-        self.t.join(timeout=2)
-        reasons = [n for n, b in self.REASONS if self.bits & b]
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
-                "reasons": reasons, "samples": len(self.sm), "how": "NVML, sampled only while timed regions run"}
+        sm, bits = self.sm.get(label, []), self.bits.get(label, 0)
+        reasons = [n for n, b in self.REASONS if bits & b]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                "samples": len(sm), "how": "NVML, sampled in-process only while this workload's timed regions run"}
 
 
 DEVICE_WORKLOADS = ("cfg3", "cfg4")      # too large to build through scipy on the host
@@ -255,6 +261,7 @@ def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, h
     from vmatwpencode_b200.plan import DosePlan
     from vmatwpencode_b200.dist import ShardedEvaluator, slab_of, slab_of_device
     device_case = name in DEVICE_WORKLOADS
+    sampler.label = "headline" if headline else name
     case, y, w_dose, w_grad = workload(name, args.scale, device=f"cuda:{local}")
     if device_case:
         D, thr, over, under = slab_of_device(case, rank, world)
@@ -487,7 +494,8 @@ def main():
     if args.largest != "none" and args.largest != args.workload and args.scale == 1.0:
         largest = run_case(args, args.largest, max(1, args.largest_steps), W, rank, local, world, dist, torch, sampler,
                            opts, headline=False)
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.stop()
+    clocks = sampler.summary("headline") if rank == 0 else None
 
     if rank == 0:
         case, y, w_dose, w_grad = head.pop("_case")
@@ -505,6 +513,7 @@ def main():
         if largest is not None:
             largest.pop("_case")
             largest["scaling"] = "strong"
+            largest["clocks"] = sampler.summary(args.largest)
             line["largest_case"] = largest
         if world == 1 and not args.no_cpu and args.workload not in DEVICE_WORKLOADS:
             rate, cores, n, scipy_rate, _ = cpu_port_rate(case, y, w_dose, w_grad)

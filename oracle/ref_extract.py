@@ -32,6 +32,11 @@ _HOT = ["region", "apertureList", "vmat_class", "calcObjGrad", "fvalidbeamlets",
 WANTED = {
     "greedyVMATsampling": _HOT,
     "greedyVMATsamplingLaptop": _HOT,
+    # the two earlier generations: same function names, plain-list candidate sets
+    "greedyVMAT": ["region", "vmat_class", "calcObjGrad", "fvalidbeamlets", "PPsubroutine", "parallelizationPricingProblem",
+                   "PricingProblem", "solveRMC", "updateOpenAperture"],
+    "greedyVMATshort": ["region", "vmat_class", "calcObjGrad", "PPsubroutine", "PricingProblem", "solveRMC",
+                        "updateOpenAperture"],
     "kmedoids": ["distancemin", "listdiff", "insertnewelement", "givemewholelist"],
 }
 
@@ -123,6 +128,78 @@ def reference_namespace(case, module: str = "greedyVMATsampling") -> dict:
     ns["M"] = case.M
     ns["penalizationweights"] = [None] * case.nb      # Laptop variant: Kelly measure per control point
     return ns
+
+
+def variant_namespace(case, module: str, gastep=None) -> dict:
+    """Namespace with the functions of greedyVMAT.py / greedyVMATshort.py bound to `case`: these generations
+    read the module globals ``Dlist`` (not data.Dlist), ``quadHelper*``, ``gastep``, ``N``, ``M`` and keep
+    data.notinC / data.caligraphicC as plain lists (Appendix A step 3)."""
+    ns = extract(module)
+    data = ns["vmat_class"]()
+    data.numvoxels = case.V
+    data.numbeams = case.nb
+    data.xinter = np.array(case.xinter)
+    data.yinter = np.array(case.yinter)
+    data.xdirection = [np.array(a) for a in case.xdirection]
+    data.ydirection = [np.array(a) for a in case.ydirection]
+    data.llist = [[-1] * case.M for _ in range(case.nb)]
+    data.rlist = [[case.N + 1] * case.M for _ in range(case.nb)]
+    data.openApertureMaps = [[] for _ in range(case.nb)]
+    data.diagmakers = [[] for _ in range(case.nb)]
+    data.currentIntensities = np.zeros(case.nb)
+    data.notinC = list(range(case.nb))
+    data.caligraphicC = []
+    ns["data"] = data
+    ns["Dlist"] = case.Dlist()
+    ns["DlistT"] = [d.transpose() for d in ns["Dlist"]]          # greedyVMAT.py:124 (greedyVMATshort.py transposes in place)
+    ns["quadHelperThresh"] = np.array(case.thr)
+    ns["quadHelperOver"] = np.array(case.over)
+    ns["quadHelperUnder"] = np.array(case.under)
+    ns["N"], ns["M"] = case.N, case.M
+    ns["gastep"] = gastep if gastep is not None else (case.angles[1] - case.angles[0] if case.nb > 1 else 1)
+    return ns
+
+
+def variant_colgen(ns, case, module: str, C, max_iter=None, C2=1.0, C3=1.0, b=0.5):
+    """The colGen loops of greedyVMATshort.py:746-814 / greedyVMAT.py:779-836 (WholeCircle=False) driven over the
+    reference's own PricingProblem / updateOpenAperture / solveRMC, without plots and file output."""
+    import warnings
+    data = ns["data"]
+    short = module == "greedyVMATshort"
+    vmax, speedlim = (2.0, 3.0) if short else (2.0 * 1000, 3.0)
+    data.llist = [[-1] * case.M for _ in range(case.nb)]
+    data.rlist = [[case.N + 1] * case.M for _ in range(case.nb)]
+    with quiet():
+        data.calcDose()
+    data.caligraphicC = []
+    data.notinC = list(range(case.nb))
+    pstar = -float("inf")
+    history = []
+    while pstar < 0 and (short or len(data.notinC) > 0):
+        data.calcDose()
+        data.calcGradientandObjValue()
+        with quiet():
+            if short:
+                pstar, lm, rm, best = ns["PricingProblem"](C, C2, C3, b, 60, 60, vmax, speedlim, case.N, case.M)
+            else:
+                pstar, lm, rm, best = ns["PricingProblem"](C, C2, C3, b, vmax, speedlim, case.N, case.M)
+        if pstar >= 0:
+            break
+        data.caligraphicC.append(best)
+        data.caligraphicC.sort()
+        data.notinC.remove(best)
+        data.notinC.sort()
+        data.llist[best], data.rlist[best] = lm, rm
+        with quiet():
+            data.openApertureMaps[best], data.diagmakers[best] = ns["updateOpenAperture"](best)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = ns["solveRMC"]()
+        history.append(dict(idx=int(best), l=[int(v) for v in lm], r=[int(v) for v in rm], pstar=float(pstar),
+                            x=np.array(res.x, dtype=float), fun=float(res.fun), nit=int(res.nit)))
+        if max_iter is not None and len(history) >= max_iter:
+            break
+    return history
 
 
 def ref_pricing_problem(ns, C, C2, C3, b, vmax, speedlim, N, M, bw):

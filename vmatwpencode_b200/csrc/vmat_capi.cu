@@ -551,10 +551,12 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             for (int64_t v = 0; v < V; ++v) order[cnt[maxlen - slots[v]]++] = (int32_t)v;
         }
         const int32_t W = P->W1, HU = 8 + 3 * (32 * es / 16) + header_base_units(P->iw);
-        // fused kernel: 16-warp stages per CTA if the work were spread evenly; small slabs get finer items
+        // 16-warp stages per CTA if the work were spread evenly: small slabs (a case sharded over several GPUs)
+        // get shorter super-slices, so that the longest one is not most of the kernel (config 2 on 8 GPUs:
+        // 73 super-slices of up to 49 stages for 148 CTAs, the dose kernel's CTAs finished between 2 and 12.5 us)
         const int64_t per_cta = nnz / 2048 / std::max(1, P->sm_count);
         const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2]
-                          : P->fused ? (int32_t)std::min<int64_t>(kChunkCapK1, std::max<int64_t>(12, per_cta / 2)) : kChunkCapK1;
+                          : (int32_t)std::min<int64_t>(kChunkCapK1, std::max<int64_t>(12, per_cta / 2));
         StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
         sd.ragged = P->fused && !fused_uniform;
         sd.record_nch = P->fused;
@@ -643,7 +645,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
 
         const int64_t per_cta2 = nnz / 2048 / std::max(1, P->sm_count);
         const int32_t cap = P->opt.reserved[7] > 0 ? P->opt.reserved[7]
-                          : P->fused ? (int32_t)std::min<int64_t>(48, std::max<int64_t>(8, per_cta2 / 4)) : kChunkCapK2;
+                          : (int32_t)std::min<int64_t>(P->fused ? 48 : kChunkCapK2, std::max<int64_t>(8, per_cta2 / 4));
         StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
         sd.ragged = P->fused && !fused_uniform;
         sd.record_nch = P->fused;
@@ -1204,13 +1206,16 @@ extern "C" int vmat_comm_handle(vmat_plan_t* P, void* handle_out) {
 
 // common tail of the two attach entry points: `ptrs[q]` = rank q's comm buffer as seen from this device
 static int comm_finish_attach(vmat_plan* P, int32_t rank, int32_t nranks, const std::vector<double*>& ptrs) {
-    // every CTA of the reduction kernel waits for its peers' CTA of the same index, so all of them
-    // must be able to be resident at once
-    int occ = 0;
-    if (P->acc_size == 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_reduce_exchange<double>, 256, 0));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_reduce_exchange<float>, 256, 0));
-    if ((int64_t)P->nb > (int64_t)occ * P->sm_count)
-        return fail(VMAT_E_UNSUPPORTED, "vmat_comm_attach: more control points than reduction CTAs that can be resident at once");
+    // Every CTA of the reduction kernel first stores its part into the peers' buffers and then waits for the
+    // peers' CTA of the same index, so it is enough that CTAs start in the same order on every rank; with all
+    // of them resident at once not even that is needed, which is what is required here.
+    if (!P->fused) {
+        int occ = 0;
+        if (P->acc_size == 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_reduce_exchange<double>, 256, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_reduce_exchange<float>, 256, 0));
+        if ((int64_t)P->nb > (int64_t)occ * P->sm_count)
+            return fail(VMAT_E_UNSUPPORTED, "vmat_comm_attach: more control points than reduction CTAs that can be resident at once");
+    }
     if (upload_vec(P->comm_ptrs, ptrs, P->stream)) return VMAT_E_CUDA;
     CU(cudaMemset(P->comm_buf.p, 0, P->comm_buf.bytes));
     CU(cudaMemset(P->comm_state.p, 0, 64));

@@ -688,42 +688,45 @@ __device__ __forceinline__ ulonglong2 ll_load_raw(const double* buf, size_t entr
     return w;
 }
 // Sum over the ranks, in rank order, of entry j of this rank's own buffer; waits for entries that have not
-// arrived yet.  Returns false on time-out.  (Loads of all ranks are issued together; late ones are retried.)
+// arrived yet.  Returns false on time-out.  (Eight ranks at a time: their loads are issued together, late
+// ones are retried.)
 __device__ __forceinline__ bool comm_sum_ranks(const CommArgs& c, int B, size_t j, double& out) {
     const double* mybuf = c.peer_bufs[c.rank];
     const int parity = (int)(c.epoch & 1ull);
     const uint32_t ep = (uint32_t)c.epoch;
-    ulonglong2 w[kMaxRanks];
-    uint32_t missing = 0;
-#pragma unroll
-    for (int q = 0; q < kMaxRanks; ++q)
-        if (q < c.nranks) w[q] = ll_load_raw(mybuf, comm_entry(parity, q, c.nranks, B, j));
-#pragma unroll
-    for (int q = 0; q < kMaxRanks; ++q)
-        if (q < c.nranks && ((uint32_t)(w[q].x >> 32) != ep || (uint32_t)(w[q].y >> 32) != ep)) missing |= 1u << q;
-    if (missing) {
-        const unsigned long long t0 = global_timer_ns();
-        unsigned int spins = 0;
-        while (missing) {
-#pragma unroll
-            for (int q = 0; q < kMaxRanks; ++q)
-                if ((missing >> q) & 1u) {
-                    w[q] = ll_load_raw(mybuf, comm_entry(parity, q, c.nranks, B, j));
-                    if ((uint32_t)(w[q].x >> 32) == ep && (uint32_t)(w[q].y >> 32) == ep) missing &= ~(1u << q);
-                }
-            if (missing && (++spins & 0xffu) == 0 && global_timer_ns() - t0 > c.timeout_ns) return false;
-        }
-    }
     double s = 0.0;
+    for (int q0 = 0; q0 < c.nranks; q0 += 8) {
+        ulonglong2 w[8];
+        uint32_t missing = 0;
 #pragma unroll
-    for (int q = 0; q < kMaxRanks; ++q)
-        if (q < c.nranks) s += __longlong_as_double((long long)((w[q].x & 0xffffffffull) | (w[q].y << 32)));
+        for (int q = 0; q < 8; ++q)
+            if (q0 + q < c.nranks) w[q] = ll_load_raw(mybuf, comm_entry(parity, q0 + q, c.nranks, B, j));
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q0 + q < c.nranks && ((uint32_t)(w[q].x >> 32) != ep || (uint32_t)(w[q].y >> 32) != ep)) missing |= 1u << q;
+        if (missing) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
+            while (missing) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if ((missing >> q) & 1u) {
+                        w[q] = ll_load_raw(mybuf, comm_entry(parity, q0 + q, c.nranks, B, j));
+                        if ((uint32_t)(w[q].x >> 32) == ep && (uint32_t)(w[q].y >> 32) == ep) missing &= ~(1u << q);
+                    }
+                if (missing && (++spins & 0xffu) == 0 && global_timer_ns() - t0 > c.timeout_ns) return false;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q0 + q < c.nranks) s += __longlong_as_double((long long)((w[q].x & 0xffffffffull) | (w[q].y << 32)));
+    }
     out = s;
     return true;
 }
 
 template <typename AT>
-__global__ void __launch_bounds__(256) k3_reduce_exchange(const K3Args<AT> a, const CommArgs c) {
+__global__ void __launch_bounds__(256, 4) k3_reduce_exchange(const K3Args<AT> a, const CommArgs c) {
     __shared__ double sh[256];
     const int tid = threadIdx.x;
     pdl_launch_dependents();
