@@ -189,12 +189,34 @@ typedef struct vmat_price_row {     /* one leaf row of one candidate (host-built
 
 typedef struct vmat_price_params {
     double C, C2, C3, b;
-    int32_t M, N;
+    int32_t M, N;                   /* network rows (= row descriptors per candidate), beamlets per leaf row */
+    int32_t variant;                /* which generation of the reference's network (VMAT_PRICE_*), 0 = canonical */
+    int32_t reserved[5];
 } vmat_price_params_t;
+
+/* The generations of PPsubroutine.  The row descriptors are built by the caller with the
+ * generation's own range expressions; the kernel wires the network accordingly:
+ *   SAMPLING  greedyVMATsampling.py:618-789 (canonical): M rows; empty r range -> midpoint (r_mid, n_r_mid);
+ *             tie-break and DoseSide terms; result = M leaf pairs.
+ *   CLASSIC   greedyVMAT.py:469-636: rows 0..M-2; empty r range -> r from its start up to r_mid (the row's first l);
+ *             relaxation window = previous row shifted by one node, predecessor recorded one node later, the sink
+ *             also scans the row's last node, untouched weights 0.0; result = one pair per visited row plus the
+ *             sink's (0, 0), as the reference returns it.
+ *   SHORT     greedyVMATshort.py:456-616: row 0 and rows 2..M-1 (with the beamlets of row m-1); no fallback
+ *             (n_r_mid = 0); shifted window, no tie-break; dose terms read beamGrad by raw position (row 0, vb_mask =
+ *             all ones, grad_offset = vb_min = 0) or from grad_offset + 1 over r - l - 1 entries (other rows). */
+enum { VMAT_PRICE_SAMPLING = 0, VMAT_PRICE_CLASSIC = 1, VMAT_PRICE_SHORT = 2 };
 
 int vmat_price(vmat_plan_t* plan, int32_t ncand, const int32_t* cand_beam,
                const vmat_price_params_t* params, const vmat_price_row_t* rows /* ncand*M */,
                double* p /* ncand */, int32_t* l /* ncand*M */, int32_t* r /* ncand*M */);
+/* Any generation: l and r hold params->M + 1 entries per candidate, len[c] says how many are used (the earlier
+ * generations return paths of varying length).  p[c] is NaN where the reference would leave p unassigned (no
+ * path into the sink at or below its initial weight: it raises UnboundLocalError there). */
+int vmat_price_ex(vmat_plan_t* plan, int32_t ncand, const int32_t* cand_beam,
+                  const vmat_price_params_t* params, const vmat_price_row_t* rows /* ncand*M */,
+                  double* p /* ncand */, int32_t* l /* ncand*(M+1) */, int32_t* r /* ncand*(M+1) */,
+                  int32_t* len /* ncand */);
 
 /*
  * k-medoid insertion costs (kmedoids.py:32-60): for every candidate point c, the sum over

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("VMAT_B200_LIB") or os.path.join(_HERE, "libvmat_b200.
 
 VMAT_F32, VMAT_BF16, VMAT_F64 = 0, 1, 2
 VMAT_HOST, VMAT_DEVICE = 0, 1
+VMAT_PRICE_SAMPLING, VMAT_PRICE_CLASSIC, VMAT_PRICE_SHORT = 0, 1, 2
 DTYPE_CODES = {"f32": VMAT_F32, "bf16": VMAT_BF16, "f64": VMAT_F64}
 
 
@@ -36,7 +37,7 @@ class PriceRow(C.Structure):
 
 class PriceParams(C.Structure):
     _fields_ = [("C", C.c_double), ("C2", C.c_double), ("C3", C.c_double), ("b", C.c_double),
-                ("M", C.c_int32), ("N", C.c_int32)]
+                ("M", C.c_int32), ("N", C.c_int32), ("variant", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 # every symbol include/vmat_b200.h declares: name -> (restype, argtypes)
@@ -75,6 +76,7 @@ SIGNATURES = {
     "vmat_dose_max": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "vmat_dvh_histogram": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P]),
     "vmat_price": (C.c_int, [_P, C.c_int32, _P, C.POINTER(PriceParams), C.POINTER(PriceRow), _P, _P, _P]),
+    "vmat_price_ex": (C.c_int, [_P, C.c_int32, _P, C.POINTER(PriceParams), C.POINTER(PriceRow), _P, _P, _P, _P]),
     "vmat_kmedoid_costs": (C.c_int, [C.c_int, C.c_int64, C.c_int32, _P, _P, _P]),
     "vmat_kmedoid_costs_shard": (C.c_int, [C.c_int, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
 }

@@ -92,7 +92,7 @@ struct vmat_plan {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     // pricing scratch
-    DevBuf price_rows, price_cand, price_p, price_l, price_r, price_dad;
+    DevBuf price_rows, price_cand, price_p, price_l, price_r, price_dad, price_len, price_gstart;
     size_t price_cap_cand = 0, price_cap_rows = 0, price_cap_dad = 0;
     // natural-order penalty tables and the RMP column cache (vmat_rmp_begin)
     DevBuf thr_n, over_n, under_n, colA, colG, col_y, col_w, rmp_yk, rmp_beams, rmp_fpart, rmp_gpart;
@@ -1329,15 +1329,16 @@ extern "C" int vmat_get_beamlet_grad(vmat_plan_t* P, double* out) {
 // ---------------------------------------------------------------------------------
 // pricing
 // ---------------------------------------------------------------------------------
-extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_beam,
-                          const vmat_price_params_t* prm, const vmat_price_row_t* rows,
-                          double* p, int32_t* l, int32_t* r) {
+static int price_impl(vmat_plan_t* P, int32_t ncand, const int32_t* cand_beam,
+                      const vmat_price_params_t* prm, const vmat_price_row_t* rows,
+                      double* p, int32_t* l, int32_t* r, int32_t* len, int32_t out_stride) {
     if (!P || ncand < 0 || (ncand > 0 && (!cand_beam || !prm || !rows || !p || !l || !r)))
         return fail(VMAT_E_ARG, "vmat_price: null argument");
     if (ncand == 0) return VMAT_OK;
     if (!P->evaluated) return fail(VMAT_E_STATE, "vmat_price: no evaluation has produced a beamlet gradient yet");
-    const int32_t M = prm->M, N = prm->N;
+    const int32_t M = prm->M, N = prm->N, variant = prm->variant;
     if (M <= 0 || N <= 0 || N > 62) return fail(VMAT_E_UNSUPPORTED, "vmat_price: need 1 <= N <= 62, M >= 1");
+    if (variant < VMAT_PRICE_SAMPLING || variant > VMAT_PRICE_SHORT) return fail(VMAT_E_ARG, "vmat_price: unknown variant");
     for (int32_t c = 0; c < ncand; ++c)
         if (cand_beam[c] < 0 || cand_beam[c] >= P->nb) return fail(VMAT_E_ARG, "vmat_price: bad candidate");
     CU(cudaSetDevice(P->device));
@@ -1348,26 +1349,32 @@ extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_bea
         const vmat_price_row_t& R = rows[k];
         if (R.n_l < 1 || R.n_l > N + 1 || !(R.l_first >= -1.0) || !(R.l_first + (double)(R.n_l - 1) <= (double)N))
             return fail(VMAT_E_ARG, "vmat_price: a row has no left-leaf positions or leaves the grid (need 1 <= n_l <= N+1, -1 <= l <= N)");
-        if (R.n_r_mid < 1 || R.n_r_mid > 2 || !(R.r_hi <= (double)N) || R.vb_min < 0 || R.vb_min >= 64)
+        if (R.n_r_mid < 0 || R.n_r_mid > 2 || (variant == VMAT_PRICE_SAMPLING && R.n_r_mid < 1) || !(R.r_hi <= (double)N) ||
+            R.vb_min < 0 || R.vb_min >= 64)
             return fail(VMAT_E_ARG, "vmat_price: bad row descriptor (need n_r_mid in {1,2}, r_hi <= N, 0 <= vb_min < 64)");
-        if (R.vb_mask) {      // beamGrad entries the dose term may touch: [grad_offset - vb_min + lowest, ... + highest existing y]
-            const int32_t beam = cand_beam[k / M], nbl = P->beam_ptr[beam + 1] - P->beam_ptr[beam];
+        const int32_t beam = cand_beam[k / M], nbl = P->beam_ptr[beam + 1] - P->beam_ptr[beam];
+        if (variant != VMAT_PRICE_SHORT && R.vb_mask) {      // beamGrad entries the dose term may touch: [grad_offset - vb_min + lowest, ... + highest existing y]
             const int ylo = __builtin_ctzll(R.vb_mask), yhi = 63 - __builtin_clzll(R.vb_mask);
             if ((int64_t)R.grad_offset - R.vb_min + ylo < 0 || (int64_t)R.grad_offset - R.vb_min + yhi >= nbl)
                 return fail(VMAT_E_ARG, "vmat_price: a row's beamlet gradient window leaves its control point");
         }
+        if (variant == VMAT_PRICE_SHORT && (R.grad_offset < 0 || R.grad_offset > nbl))      // (reads past the end are clipped, like a Python slice)
+            return fail(VMAT_E_ARG, "vmat_price: a row's beamlet gradient offset leaves its control point");
         int64_t total = 0;
         for (int32_t q = 0; q < R.n_l; ++q) {
             const double lval = R.l_first + (double)q;
             const double r0 = std::ceil(std::fmax(lval + 1.0, R.r_lo)), r1 = std::floor(R.r_hi);
-            total += (r1 >= r0) ? (int64_t)(r1 - r0) + 1 : R.n_r_mid;
+            if (r1 >= r0) total += (int64_t)(r1 - r0) + 1;
+            else if (variant == VMAT_PRICE_SAMPLING) total += R.n_r_mid;
+            else if (variant == VMAT_PRICE_CLASSIC) total += std::max<int64_t>(0, (int64_t)(R.r_mid + 1.0 - r0));
         }
-        if (total < 1 || total > kmax) return fail(VMAT_E_ARG, "vmat_price: a row's node count exceeds the network size for this N");
+        if (total < 1 || total > kmax) return fail(VMAT_E_ARG, "vmat_price: a row has no nodes, or more than the network size for this N");
     }
     if ((size_t)ncand > P->price_cap_cand || nrow > P->price_cap_rows || nrow * kmax > P->price_cap_dad) {
         CU(P->price_cand.alloc(ncand * 4)); CU(P->price_p.alloc(ncand * 8));
         CU(P->price_rows.alloc(nrow * sizeof(vmat_price_row_t)));
-        CU(P->price_l.alloc(nrow * 4)); CU(P->price_r.alloc(nrow * 4));
+        CU(P->price_l.alloc((nrow + ncand) * 4)); CU(P->price_r.alloc((nrow + ncand) * 4));
+        CU(P->price_len.alloc(ncand * 4)); CU(P->price_gstart.alloc((nrow + ncand) * 4));
         CU(P->price_dad.alloc(nrow * kmax * sizeof(int32_t) * 3));
         P->price_cap_cand = ncand; P->price_cap_rows = nrow; P->price_cap_dad = nrow * kmax;
     }
@@ -1377,18 +1384,36 @@ extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_bea
     PriceArgs a{};
     a.gb = P->gbf.as<double>(); a.beam_ptr = P->beam_ptr_d.as<int32_t>(); a.cand = P->price_cand.as<int32_t>();
     a.rows = P->price_rows.as<vmat_price_row_t>(); a.C = prm->C; a.C2 = prm->C2; a.C3 = prm->C3; a.b = prm->b;
-    a.M = M; a.N = N; a.kmax = kmax; a.p = P->price_p.as<double>(); a.l = P->price_l.as<int32_t>();
-    a.r = P->price_r.as<int32_t>(); a.scratch = P->price_dad.as<int32_t>();
+    a.M = M; a.N = N; a.kmax = kmax; a.variant = variant; a.out_stride = out_stride;
+    a.p = P->price_p.as<double>(); a.l = P->price_l.as<int32_t>();
+    a.r = P->price_r.as<int32_t>(); a.len = P->price_len.as<int32_t>(); a.scratch = P->price_dad.as<int32_t>();
+    a.gstart = P->price_gstart.as<int32_t>();
     const size_t smem = price_smem_bytes(kmax);
     if (smem > (size_t)P->smem_optin) return fail(VMAT_E_UNSUPPORTED, "vmat_price: N too large for shared memory");
     CU(cudaFuncSetAttribute(k5_price_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k5_price_dp<<<ncand, kPriceThreads, smem, st>>>(a);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(p, P->price_p.p, ncand * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(l, P->price_l.p, nrow * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(r, P->price_r.p, nrow * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(l, P->price_l.p, (size_t)ncand * out_stride * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(r, P->price_r.p, (size_t)ncand * out_stride * 4, cudaMemcpyDeviceToHost, st));
+    if (len) CU(cudaMemcpyAsync(len, P->price_len.p, ncand * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return VMAT_OK;
+}
+
+extern "C" int vmat_price(vmat_plan_t* P, int32_t ncand, const int32_t* cand_beam,
+                          const vmat_price_params_t* prm, const vmat_price_row_t* rows,
+                          double* p, int32_t* l, int32_t* r) {
+    if (prm && prm->variant != VMAT_PRICE_SAMPLING)
+        return fail(VMAT_E_ARG, "vmat_price: the earlier generations return paths of varying length: use vmat_price_ex");
+    return price_impl(P, ncand, cand_beam, prm, rows, p, l, r, nullptr, prm ? prm->M : 0);
+}
+
+extern "C" int vmat_price_ex(vmat_plan_t* P, int32_t ncand, const int32_t* cand_beam,
+                             const vmat_price_params_t* prm, const vmat_price_row_t* rows,
+                             double* p, int32_t* l, int32_t* r, int32_t* len) {
+    if (!len) return fail(VMAT_E_ARG, "vmat_price_ex: null argument");
+    return price_impl(P, ncand, cand_beam, prm, rows, p, l, r, len, prm ? prm->M + 1 : 0);
 }
 
 // ---------------------------------------------------------------------------------

@@ -295,6 +295,24 @@ class DosePlan:
         return p, l, r
 
 
+def _price_ex(self, cands, params, rows):
+    """Batched PPsubroutine of any generation (params.variant): -> (p, [l...], [r...]) with one leaf list per
+    candidate, as long as the reference returns it."""
+    n = len(cands)
+    cand = np.ascontiguousarray(cands, dtype=np.int32)
+    p = np.empty(n)
+    stride = params.M + 1
+    l = np.empty((n, stride), dtype=np.int32)
+    r = np.empty((n, stride), dtype=np.int32)
+    ln = np.empty(n, dtype=np.int32)
+    check(self._lib.vmat_price_ex(self._h, n, _ptr(cand), C.byref(params), rows, _ptr(p), _ptr(l), _ptr(r), _ptr(ln)),
+          "vmat_price_ex")
+    return p, [l[k, :ln[k]].tolist() for k in range(n)], [r[k, :ln[k]].tolist() for k in range(n)]
+
+
+DosePlan.price_ex = _price_ex
+
+
 def kmedoid_costs(points, curmin, device: int = 0, candidates=None) -> np.ndarray:
     """cost[c] = sum_j min(curmin[j], dist(c, j))  (kmedoids.py:32-60) on the GPU.  With
     `candidates` (n_cand x dim) the sum runs over `points` (e.g. one rank's shard) only."""
