@@ -104,6 +104,53 @@ def colgen_fixture(name, case, C, kappasize, max_iter, elimination=False, module
     print(name, "iterations", len(hist), "sequence", [h["idx"] for h in hist])
 
 
+def variant_fixture(name, module, case, C, max_iter, gastep):
+    """A greedy run of one of the EARLIER generations (greedyVMATshort.py / greedyVMAT.py) by the reference's own
+    functions, plus its per-candidate pricing results in the state the run ends in."""
+    ns = R.variant_namespace(case, module, gastep=gastep)
+    hist = R.variant_colgen(ns, case, module, C=C, max_iter=max_iter)
+    data = ns["data"]
+    out = case_to_arrays(case)
+    out["C"] = np.float64(C)
+    out["max_iter"] = np.int64(max_iter)
+    out["gastep"] = np.int64(gastep)
+    out["idx"] = np.asarray([h["idx"] for h in hist], dtype=np.int64)
+    out["l_flat"] = np.asarray([v for h in hist for v in h["l"]], dtype=np.int64)
+    out["r_flat"] = np.asarray([v for h in hist for v in h["r"]], dtype=np.int64)
+    out["l_len"] = np.asarray([len(h["l"]) for h in hist], dtype=np.int64)
+    out["pstar"] = np.asarray([h["pstar"] for h in hist])
+    out["x"] = np.asarray([h["x"] for h in hist])
+    out["fun"] = np.asarray([h["fun"] for h in hist])
+    # pricing of every remaining candidate in the final state (the evaluation of that state first)
+    data.calcDose()
+    data.calcGradientandObjValue()
+    ps, ls, rs, idxs = [], [], [], []
+    short = module == "greedyVMATshort"
+    for k, i in enumerate(list(data.notinC)):
+        with R.quiet():
+            if short:
+                p, l, r = ns["PPsubroutine"](C, 1.0, 1.0, 0.5, 60, 60, 2.0, 3.0, [], [], case.N, case.M, i)
+            else:
+                p, l, r, _ = ns["parallelizationPricingProblem"](k, C, 1.0, 1.0, 0.5, 2.0 * 1000, 3.0, case.N, case.M)
+        ps.append(float(p)); ls.append([int(v) for v in l]); rs.append([int(v) for v in r]); idxs.append(int(i))
+    out["final_idx"] = np.asarray(idxs, dtype=np.int64)
+    out["final_p"] = np.asarray(ps)
+    out["final_l_flat"] = np.asarray([v for l in ls for v in l], dtype=np.int64)
+    out["final_r_flat"] = np.asarray([v for r in rs for v in r], dtype=np.int64)
+    out["final_len"] = np.asarray([len(l) for l in ls], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "iterations", len(hist), "sequence", [h["idx"] for h in hist], "remaining", idxs)
+
+
+def variant_fixtures():
+    """BASELINE.json configs[0] names greedyVMATshort.py; greedyVMAT.py is the generation in between."""
+    variant_fixture("variant_short_A", "greedyVMATshort", make_case(V=1500, nb=6, M=5, N=6, density=0.05, seed=11, gastep=60), 0.5, 4, 60)
+    variant_fixture("variant_short_B", "greedyVMATshort", make_case(V=2500, nb=8, M=6, N=8, density=0.03, seed=12, gastep=10, ragged=True), 0.5, 5, 10)
+    variant_fixture("variant_classic_A", "greedyVMAT", make_case(V=1500, nb=6, M=5, N=6, density=0.05, seed=11, gastep=60), 0.01, 4, 60)
+    variant_fixture("variant_classic_B", "greedyVMAT", make_case(V=2500, nb=8, M=6, N=8, density=0.03, seed=12, gastep=10, ragged=True), 0.5, 5, 10)
+    variant_fixture("variant_classic_C", "greedyVMAT", make_case(V=2500, nb=8, M=6, N=8, density=0.03, seed=13, gastep=2), 0.05, 5, 2)
+
+
 def colgen_files_fixture(name, seed, C, kappasize, max_iter):
     """Files -> the reference's own loader -> the reference's own greedy loop, on a synthetic
     CORT-format data set the tests regenerate from `seed` (oracle/cort_fixture.py)."""
@@ -254,6 +301,7 @@ def main():
     colgen_files_fixture("colgen_files", seed=3, C=0.01, kappasize=3, max_iter=6)
     kmedoids_fixture()
     kmedoids_perm_fixture()
+    variant_fixtures()
 
 
 if __name__ == "__main__":

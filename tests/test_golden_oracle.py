@@ -148,3 +148,43 @@ def test_dvh_matches_reference_printresults():
     b, m = O.dvh_matrix(z["dose"], z["full_mask"].astype(float), int(z["numstructs"]))
     assert np.array_equal(b, z["bin_center"]) and np.array_equal(m, z["dvh_matrix"])
     assert np.all(m[5] == 0)          # the empty structure keeps a zero row
+
+
+# ---- the two earlier generations (greedyVMATshort.py, greedyVMAT.py): oracle/vmat_oracle_variants.py ----------
+def _variant_history(z):
+    off = np.concatenate([[0], np.cumsum(z["l_len"])])
+    return [(int(z["idx"][k]), list(z["l_flat"][off[k]:off[k + 1]]), list(z["r_flat"][off[k]:off[k + 1]]),
+             float(z["pstar"][k]), z["x"][k], float(z["fun"][k])) for k in range(len(z["idx"]))]
+
+
+@pytest.mark.parametrize("name", ["variant_short_A", "variant_short_B", "variant_classic_A", "variant_classic_B",
+                                  "variant_classic_C"])
+def test_variant_oracle_reproduces_reference_runs_bitwise(name):
+    """Greedy runs of greedyVMATshort.py / greedyVMAT.py recorded from the reference's own functions
+    (oracle/make_golden.py: variant_fixture): same control points, leaf vectors (including the trailing sink
+    entry and the paths the shifted window produces), prices, intensities and objective values, bit for bit."""
+    from oracle import vmat_oracle_variants as V
+    z, case = load_golden(name)
+    var = V.SHORT if "short" in name else V.CLASSIC
+    st = V.VariantState(case)
+    got = V.col_gen(st, var, C=float(z["C"]), gastep=int(z["gastep"]), max_iter=int(z["max_iter"]))
+    want = _variant_history(z)
+    assert len(got) == len(want)
+    for h, (idx, l, r, p, x, fun) in zip(got, want):
+        assert h["idx"] == idx and h["l"] == l and h["r"] == r
+        assert h["pstar"] == p and h["fun"] == fun and np.array_equal(h["x"], x)
+    # per-candidate prices of the final state
+    V.calc_obj_grad(st, st.currentIntensities)
+    off = np.concatenate([[0], np.cumsum(z["final_len"])])
+    gastep = int(z["gastep"])
+    for k, i in enumerate(z["final_idx"]):
+        predec, succ = V.neighbours(st, var, int(i), gastep)
+        if var.rows == "short":
+            am = ap = 60
+        else:
+            ap = (succ - int(i)) * gastep if not isinstance(succ, list) else np.inf
+            am = (int(i) - predec) * gastep if not isinstance(predec, list) else np.inf
+        p, l, r = V.pp_subroutine(st, var, float(z["C"]), 1.0, 1.0, 0.5, am, ap, var.vmax, var.speedlim, predec, succ,
+                                  case.N, case.M, int(i))
+        assert p == z["final_p"][k]
+        assert l == list(z["final_l_flat"][off[k]:off[k + 1]]) and r == list(z["final_r_flat"][off[k]:off[k + 1]])

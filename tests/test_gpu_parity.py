@@ -740,3 +740,118 @@ def test_greedy_loop_same_with_and_without_column_cache():
         finally:
             vl.use_column_cache = False
     assert seqs[0] == seqs[1] == [(int(i), tuple(l), tuple(r)) for i, l, r in zip(z["idx"], z["l"], z["r"])]
+
+
+# ---- the two earlier generations of the driver functions (vmatwpencode_b200/variants.py) ------------------------
+def _variant_api(name):
+    from vmatwpencode_b200 import variants
+    return variants.short if "short" in name else variants.classic
+
+
+@pytest.mark.parametrize("name", ["variant_short_A", "variant_short_B", "variant_classic_A", "variant_classic_B",
+                                  "variant_classic_C"])
+def test_variant_greedy_runs_against_reference_fixture(name):
+    """greedyVMATshort.py / greedyVMAT.py semantics on the GPU path against runs recorded from the reference's own
+    functions: control points, leaf vectors (bit-exact, including the trailing sink entry and the odd paths of
+    the shifted relaxation window), prices, intensities, objective."""
+    z, case = load_golden(name)
+    g = _variant_api(name)
+    g.gastep = int(z["gastep"])
+    data = vl.bind(case, store="f32", acc="f64")
+    g.colGen(float(z["C"]), max_iter=int(z["max_iter"]))
+    off = np.concatenate([[0], np.cumsum(z["l_len"])])
+    assert [h["idx"] for h in data.history] == list(z["idx"])
+    for k, h in enumerate(data.history):
+        assert h["l"] == list(z["l_flat"][off[k]:off[k + 1]]) and h["r"] == list(z["r_flat"][off[k]:off[k + 1]])
+        assert abs(h["pstar"] - z["pstar"][k]) <= 1e-9 * abs(z["pstar"][k])
+        assert abs(h["fun"] - z["fun"][k]) <= 1e-9 * abs(z["fun"][k])
+        assert np.abs(h["x"] - z["x"][k]).max() <= 1e-6 * max(1.0, np.abs(z["x"][k]).max())
+    # every remaining candidate priced in the final state, one by one (PPsubroutine) and batched (PricingProblem)
+    data.calcDose()
+    data.calcGradientandObjValue()
+    offf = np.concatenate([[0], np.cumsum(z["final_len"])])
+    C = float(z["C"])
+    for k, i in enumerate(z["final_idx"]):
+        predec, succ = g._neighbours(int(i))
+        if g.name == "short":
+            am = ap = 60
+        else:
+            ap = (succ - int(i)) * g.gastep if type(succ) is not list else np.inf
+            am = (int(i) - predec) * g.gastep if type(predec) is not list else np.inf
+        p, l, r = g.PPsubroutine(C, 1.0, 1.0, 0.5, am, ap, g.vmax, g.speedlim, predec, succ, case.N, case.M, int(i))
+        assert abs(p - z["final_p"][k]) <= 1e-9 * max(abs(z["final_p"][k]), 1e-300)
+        assert [int(v) for v in l] == list(z["final_l_flat"][offf[k]:offf[k + 1]])
+        assert [int(v) for v in r] == list(z["final_r_flat"][offf[k]:offf[k + 1]])
+    data.plan.close()
+
+
+@pytest.mark.parametrize("gen", ["short", "classic"])
+def test_variant_pricing_random_states_vs_oracle(gen):
+    """Per-candidate pricing of both earlier generations in random selected states (random leaf vectors of the
+    neighbours, loose and tight leaf speeds) against oracle/vmat_oracle_variants.py; an exception of the oracle
+    (the reference's NameError / UnboundLocalError / ValueError paths) must be raised by the product as well."""
+    from oracle import vmat_oracle_variants as V
+    from vmatwpencode_b200 import variants
+    g = getattr(variants, gen)
+    var = V.VARIANTS[gen]
+    rng = np.random.default_rng(91)
+    for trial in range(6):
+        case = make_case(V=3000, nb=10, M=5 + trial % 3, N=6 + trial % 4, density=0.03, seed=300 + trial,
+                         gastep=[10, 2, 1][trial % 3], ragged=bool(trial & 1))
+        gastep = case.angles[1] - case.angles[0]
+        g.gastep = gastep
+        st = V.VariantState(case)
+        data = vl.bind(case, store="f32", acc="f64")
+        sel = sorted(rng.choice(case.nb, size=4, replace=False).tolist())
+        st.caligraphicC, st.notinC = list(sel), [i for i in range(case.nb) if i not in sel]
+        data.caligraphicC, data.notinC = list(sel), list(st.notinC)
+        for i in sel:
+            l = rng.integers(-1, case.N - 2, size=case.M)
+            r = l + rng.integers(1, 4, size=case.M)
+            st.llist[i] = data.llist[i] = [int(v) for v in l]
+            st.rlist[i] = data.rlist[i] = [int(min(v, case.N)) for v in r]
+            st.openApertureMaps[i], st.diagmakers[i] = V.update_open_aperture(st, i)
+            data.openApertureMaps[i], data.diagmakers[i] = g.updateOpenAperture(i)
+            assert np.array_equal(st.openApertureMaps[i], data.openApertureMaps[i])
+            assert np.array_equal(st.diagmakers[i], data.diagmakers[i])
+            data.strengths[i] = [1.0] * len(data.openApertureMaps[i])
+        y = np.zeros(case.nb)
+        y[sel] = rng.random(4) * 2
+        f0, g0 = V.calc_obj_grad(st, y.copy())
+        f1, g1 = g.calcObjGrad(y.copy())
+        assert abs(f1 - f0) <= 1e-11 * abs(f0) and relerr(g1, g0) <= 1e-11
+        for vmax in (var.vmax, 0.05):
+            for i in st.notinC:
+                predec, succ = V.neighbours(st, var, i, gastep)
+                if gen == "short":
+                    am = ap = 60
+                else:
+                    ap = (succ - i) * gastep if not isinstance(succ, list) else np.inf
+                    am = (i - predec) * gastep if not isinstance(predec, list) else np.inf
+                args = (0.3, 1.0, 1.0, 0.5, am, ap, vmax, var.speedlim, predec, succ, case.N, case.M, i)
+                try:
+                    want = V.pp_subroutine(st, var, *args)
+                except (NameError, UnboundLocalError, ValueError) as e:
+                    with pytest.raises(type(e)):
+                        g.PPsubroutine(*args)
+                    continue
+                p, l, r = g.PPsubroutine(*args)
+                assert [int(v) for v in l] == want[1] and [int(v) for v in r] == want[2], (trial, i, vmax)
+                assert abs(p - want[0]) <= 1e-9 * max(abs(want[0]), 1e-300)
+        data.plan.close()
+
+
+def test_greedy_loop_config1_short_semantics_vs_oracle():
+    """BASELINE.json configs[0] as it names it: greedyVMATshort.py on the 20k-voxel x 2016-beamlet x 36-control-
+    point phantom - the first-generation greedy loop to completion, same aperture sequence as the oracle."""
+    from oracle import vmat_oracle_variants as V
+    from vmatwpencode_b200 import variants
+    case = make_config("cfg1")
+    want = V.col_gen(V.VariantState(case), V.SHORT, C=1, max_iter=12)
+    data = vl.bind(case, store="f32", acc="f64")
+    variants.short.colGen(1, max_iter=12)
+    assert len(want) > 0 and [h["idx"] for h in data.history] == [w["idx"] for w in want]
+    for h, w in zip(data.history, want):
+        assert h["l"] == w["l"] and h["r"] == w["r"]
+        assert abs(h["fun"] - w["fun"]) <= 1e-8 * abs(w["fun"])
+    data.plan.close()

@@ -60,3 +60,33 @@ def test_kmedoids_functions():
         d = ns["distancemin"]([2, 9, 4], range(0, 17))
     assert O.km_givemewholelist([2, 9], list(range(17))) == a
     assert O.km_distancemin([2, 9, 4], list(range(17))) == d
+
+
+@pytest.mark.parametrize("module,var", [("greedyVMATshort", "short"), ("greedyVMAT", "classic")])
+def test_variant_oracle_against_live_reference(module, var):
+    """oracle/vmat_oracle_variants.py against the functions of greedyVMATshort.py / greedyVMAT.py executed here:
+    whole greedy runs, bit for bit (also with a tight gantry step for the classic generation, where neighbouring
+    apertures bound the leaf ranges)."""
+    import warnings
+    from oracle import vmat_oracle_variants as V
+    for kw, C in ((dict(V=1200, nb=5, M=4, N=6, density=0.05, seed=31, gastep=60), 0.5),
+                  (dict(V=2000, nb=7, M=6, N=7, density=0.04, seed=32, gastep=2, ragged=True), 0.05)):
+        case = make_case(**kw)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns = R.variant_namespace(case, module, gastep=kw["gastep"])
+            try:
+                ref = R.variant_colgen(ns, case, module, C=C, max_iter=5)
+            except UnboundLocalError as e:       # no path into the sink at or below its initial 0.0: p is never assigned there
+                ref = type(e)
+        try:
+            got = V.col_gen(V.VariantState(case), V.VARIANTS[var], C=C, gastep=kw["gastep"], max_iter=5)
+        except UnboundLocalError as e:
+            got = type(e)
+        if isinstance(ref, type) or isinstance(got, type):
+            assert ref is got
+            continue
+        assert len(ref) == len(got) and len(ref) > 0
+        for a, b in zip(ref, got):
+            assert a["idx"] == b["idx"] and a["l"] == b["l"] and a["r"] == b["r"]
+            assert a["pstar"] == b["pstar"] and a["fun"] == b["fun"] and np.array_equal(a["x"], b["x"])

@@ -196,12 +196,13 @@ class vmat_class:
         return self._gb
 
     def _sync_apertures(self):
-        sel = set(self.caligraphicC.loc)
+        selected = getattr(self.caligraphicC, "loc", self.caligraphicC)      # the earlier generations keep a plain list
+        sel = set(selected)
         for i in list(self._uploaded):
             if i not in sel:
                 self.plan.set_aperture(i, None, None)
                 del self._uploaded[i]
-        for i in self.caligraphicC.loc:
+        for i in selected:
             # what was uploaded is remembered by object (holding the references, so an address cannot
             # be recycled for new arrays): colGen assigns fresh objects whenever an aperture changes
             key = (self.openApertureMaps[i], self.diagmakers[i], self.strengths[i])
