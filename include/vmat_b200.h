@@ -191,7 +191,8 @@ typedef struct vmat_price_params {
     double C, C2, C3, b;
     int32_t M, N;                   /* network rows (= row descriptors per candidate), beamlets per leaf row */
     int32_t variant;                /* which generation of the reference's network (VMAT_PRICE_*), 0 = canonical */
-    int32_t reserved[5];
+    int32_t reserved[5];            /* [0] = 1 (CLASSIC only): the sink scans the last node only - what the reference's
+                                       sink loop covers when the rows after the last described one had no nodes */
 } vmat_price_params_t;
 
 /* The generations of PPsubroutine.  The row descriptors are built by the caller with the

@@ -806,10 +806,14 @@ def test_variant_pricing_random_states_vs_oracle(gen):
         st.caligraphicC, st.notinC = list(sel), [i for i in range(case.nb) if i not in sel]
         data.caligraphicC, data.notinC = list(sel), list(st.notinC)
         for i in sel:
-            l = rng.integers(-1, case.N - 2, size=case.M)
-            r = l + rng.integers(1, 4, size=case.M)
-            st.llist[i] = data.llist[i] = [int(v) for v in l]
-            st.rlist[i] = data.rlist[i] = [int(min(v, case.N)) for v in r]
+            ll, rr = [], []
+            for m in range(case.M):              # leaves inside the row's beamlets (outside, the reference's index arithmetic
+                vb = O.valid_beamlets(st, m, i)  # leaves the control point's vector and raises IndexError)
+                l = int(rng.integers(vb.min() - 1, vb.max()))
+                ll.append(l)
+                rr.append(int(min(l + rng.integers(1, 4), vb.max() + 1)))
+            st.llist[i] = data.llist[i] = ll
+            st.rlist[i] = data.rlist[i] = rr
             st.openApertureMaps[i], st.diagmakers[i] = V.update_open_aperture(st, i)
             data.openApertureMaps[i], data.diagmakers[i] = g.updateOpenAperture(i)
             assert np.array_equal(st.openApertureMaps[i], data.openApertureMaps[i])

@@ -1385,6 +1385,7 @@ static int price_impl(vmat_plan_t* P, int32_t ncand, const int32_t* cand_beam,
     a.gb = P->gbf.as<double>(); a.beam_ptr = P->beam_ptr_d.as<int32_t>(); a.cand = P->price_cand.as<int32_t>();
     a.rows = P->price_rows.as<vmat_price_row_t>(); a.C = prm->C; a.C2 = prm->C2; a.C3 = prm->C3; a.b = prm->b;
     a.M = M; a.N = N; a.kmax = kmax; a.variant = variant; a.out_stride = out_stride;
+    a.sink_last_only = (variant == VMAT_PRICE_CLASSIC && prm->reserved[0] == 1) ? 1 : 0;
     a.p = P->price_p.as<double>(); a.l = P->price_l.as<int32_t>();
     a.r = P->price_r.as<int32_t>(); a.len = P->price_len.as<int32_t>(); a.scratch = P->price_dad.as<int32_t>();
     a.gstart = P->price_gstart.as<int32_t>();

@@ -38,6 +38,7 @@ struct PriceArgs {
     int32_t M, N, kmax;             // M: network rows (descriptors per candidate)
     int32_t variant;                // VMAT_PRICE_SAMPLING / _CLASSIC / _SHORT
     int32_t out_stride;             // entries per candidate in l / r
+    int32_t sink_last_only;         // classic, after trailing rows without nodes: the sink scans the last node only
     double* p;                      // [ncand]
     int32_t* l;                     // [ncand*out_stride]
     int32_t* r;                     // [ncand*out_stride]
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kPriceThreads) k5_price_dp(const PriceArgs a) 
     const int nwin = nlast + sink_ext;
     double best = INFINITY;
     int bestk = -1;
-    for (int k = tid; k < nwin; k += blockDim.x) {
+    for (int k = (a.sink_last_only ? nwin - 1 : 0) + tid; k < nwin; k += blockDim.x) {
         const int e = k - shift;
         const double tot = __dadd_rn(S.w_prev[e], __dmul_rn(C, __dmul_rn(C2, (double)(S.r_prev[e] - S.l_prev[e]))));
         if (bestk < 0 || tot <= best) { best = tot; bestk = k; }

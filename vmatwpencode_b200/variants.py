@@ -116,6 +116,19 @@ class _Generation:
                 leftmost = cnt - 1 if k == 0 else leftmost + cnt
         return len(plan)
 
+    @staticmethod
+    def _node_counts(arr, classic):
+        """Nodes of every described row (the kernel's enumeration, on the host)."""
+        out = np.zeros(len(arr), dtype=np.int64)
+        for k, o in enumerate(arr):
+            tot = 0
+            r1 = math.floor(o["r_hi"])
+            for q in range(int(o["n_l"])):
+                r0 = math.ceil(max(o["l_first"] + q + 1.0, o["r_lo"]))
+                tot += (r1 - r0 + 1) if r1 >= r0 else (max(0, int(o["r_mid"] + 1.0 - r0)) if classic else 0)
+            out[k] = tot
+        return out
+
     def _price(self, cands, C, C2, C3, b, vmax, speedlim, Nn, Mm):
         d = vl.data
         if d._fg is None:
@@ -127,10 +140,35 @@ class _Generation:
         for k, (idx, predec, succ, am, ap) in enumerate(cands):
             self._fill_rows(rows, k * nrows, am, ap, vmax, speedlim, predec, succ, Nn, Mm, idx)
         arr = np.frombuffer(rows, dtype=_ROW)
-        if (arr["n_l"] < 1).any():
-            raise ValueError("attempt to get argmin of an empty sequence")      # a row without nodes: what numpy raises there
-        prm = PriceParams(C=float(C), C2=float(C2), C3=float(C3), b=float(b), M=nrows, N=Nn, variant=self.code)
-        p, l, r = d.plan.price_ex([c[0] for c in cands], prm, rows)
+        classic = self.name == "classic"
+        counts = self._node_counts(arr, classic).reshape(len(cands), nrows)
+        # Rows without nodes (leaf speeds so tight that no position is reachable).  The reference then either runs
+        # np.argmin over an empty window in the next row that has nodes (ValueError), or - when no later row has
+        # nodes - reaches its sink loop, which covers nothing (short: p stays unassigned) or only the last node
+        # of the last row that had any (classic).
+        used = np.full(len(cands), nrows)
+        for k in range(len(cands)):
+            empty = np.flatnonzero(counts[k] == 0)
+            if empty.size:
+                first = int(empty[0])
+                if (counts[k, first:] > 0).any() or first == 0:
+                    raise ValueError("attempt to get argmin of an empty sequence")
+                if not classic:
+                    raise UnboundLocalError("local variable 'p' referenced before assignment")
+                used[k] = first
+        p = np.empty(len(cands))
+        l, r = [None] * len(cands), [None] * len(cands)
+        for m_used in sorted(set(used.tolist())):             # normally one group: every row has nodes
+            grp = [k for k in range(len(cands)) if used[k] == m_used]
+            sub = (PriceRow * (len(grp) * m_used))()
+            sub_arr = np.frombuffer(sub, dtype=_ROW)
+            for q, k in enumerate(grp):
+                sub_arr[q * m_used:(q + 1) * m_used] = arr[k * nrows:k * nrows + m_used]
+            prm = PriceParams(C=float(C), C2=float(C2), C3=float(C3), b=float(b), M=m_used, N=Nn, variant=self.code)
+            prm.reserved[0] = 1 if m_used < nrows else 0
+            pp, ll, rr = d.plan.price_ex([cands[k][0] for k in grp], prm, sub)
+            for q, k in enumerate(grp):
+                p[k], l[k], r[k] = pp[q], ll[q], rr[q]
         if np.isnan(p).any():
             raise UnboundLocalError("local variable 'p' referenced before assignment")
         return p, l, r
