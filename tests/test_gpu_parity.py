@@ -859,3 +859,24 @@ def test_greedy_loop_config1_short_semantics_vs_oracle():
         assert h["l"] == w["l"] and h["r"] == w["r"]
         assert abs(h["fun"] - w["fun"]) <= 1e-8 * abs(w["fun"])
     data.plan.close()
+
+
+def test_lean_rmp_loop_equals_scipy_minimize():
+    """solveRMC through the lean loop over scipy's compiled L-BFGS-B routine and through scipy.optimize.minimize:
+    same iterates, bit for bit, and the same greedy sequences."""
+    case = make_case(V=20_000, nb=24, M=6, N=8, density=0.01, seed=88, gastep=10)
+    runs = {}
+    for fast in (True, False):
+        vl.fast_rmp = fast
+        try:
+            data = vl.bind(case, store="f32", acc="f64")
+            vl.colGen(0.01, False, 8, max_iter=8)
+            runs[fast] = [(h["idx"], h["l"], h["r"], h["fun"], h["nit"], h["nfev"], h["x"].tobytes()) for h in data.history]
+            last = (data.objectiveValue, np.asarray(data.aperturegradient).ravel().copy(), np.array(data.currentIntensities))
+            runs[(fast, "state")] = last
+            data.plan.close()
+        finally:
+            vl.fast_rmp = True
+    assert len(runs[True]) > 0 and runs[True] == runs[False]
+    a, b = runs[(True, "state")], runs[(False, "state")]
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])

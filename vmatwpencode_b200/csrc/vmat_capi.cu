@@ -70,6 +70,9 @@ struct vmat_plan {
     size_t smemF = 0;
     // state
     DevBuf y, beam_of, beam_ptr_d, w_dose, w_grad, xg, d, vg, fpart, fblock, partial, gbf, result, counter, scratch64;
+    void* h_w = nullptr;         // pinned staging for vmat_set_aperture: [max_beamlets f64 | max_beamlets f64]
+    int32_t max_beamlets = 0;
+    bool weights_in_flight = false;    // vmat_set_aperture's copies may still be running on the plan's stream
     double* h_y = nullptr;       // pinned + mapped: K1 reads it directly on the host-buffer path
     double* h_res = nullptr;     // pinned + mapped: K3 writes results here ...
     unsigned long long* h_tags = nullptr;   // ... each followed by a completion tag the host polls
@@ -117,6 +120,7 @@ struct vmat_plan {
         if (graph) cudaGraphDestroy(graph);
         for (auto e : tev) cudaEventDestroy(e);
         if (comm_ipc) for (void* q : comm_peers) if (q) cudaIpcCloseMemHandle(q);
+        if (h_w) cudaFreeHost(h_w);
         if (h_y) cudaFreeHost(h_y);
         if (h_res) cudaFreeHost(h_res);
         if (h_tags) cudaFreeHost(h_tags);
@@ -788,6 +792,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         if (rc) return VMAT_E_CUDA;
     }
     CU(P->comm_state.alloc(64));         CU(cudaMemset(P->comm_state.p, 0, 64));
+    for (int32_t i = 0; i < nb; ++i) P->max_beamlets = std::max(P->max_beamlets, beam_ptr[i + 1] - beam_ptr[i]);
+    CU(cudaHostAlloc(&P->h_w, (size_t)std::max(1, P->max_beamlets) * 16, cudaHostAllocDefault));
     CU(cudaHostAlloc(&P->h_y, nb * 8, cudaHostAllocMapped));
     CU(cudaHostAlloc(&P->h_res, (nb + 2) * 8, cudaHostAllocMapped));
     CU(cudaHostAlloc(&P->h_tags, (nb + 1) * 8, cudaHostAllocMapped));
@@ -1014,22 +1020,26 @@ extern "C" int vmat_set_aperture(vmat_plan_t* P, int32_t beam, const double* w_d
     if (P->ap_epoch.empty()) P->ap_epoch.assign(P->nb, 0);
     P->ap_epoch[beam]++;                 // cached RMP columns of this control point are stale now
     const size_t as = P->acc_size;
+    // One synchronisation, in front: earlier evaluations have read the old weights and the pinned staging buffer
+    // is free again.  The weights are converted into the staging buffer (so the caller's arrays may go away) and
+    // copied with stream-ordered asynchronous copies: later launches on the plan's stream see the new weights.
     CU(cudaStreamSynchronize(P->stream));
+    char* stage = static_cast<char*>(P->h_w);
     if (w_dose) {
-        if (as == 4) {
-            std::vector<float> tmp(n);
-            for (int k = 0; k < n; ++k) tmp[k] = (float)w_dose[k];
-            CU(cudaMemcpyAsync(P->w_dose.as<char>() + (size_t)lo * 4, tmp.data(), (size_t)n * 4, cudaMemcpyHostToDevice, P->stream));
-            CU(cudaStreamSynchronize(P->stream));        // tmp goes out of scope
-        } else {
-            CU(cudaMemcpyAsync(P->w_dose.as<char>() + (size_t)lo * 8, w_dose, (size_t)n * 8, cudaMemcpyHostToDevice, P->stream));
-        }
+        if (as == 4) { float* t = reinterpret_cast<float*>(stage); for (int k = 0; k < n; ++k) t[k] = (float)w_dose[k]; }
+        else std::memcpy(stage, w_dose, (size_t)n * 8);
+        CU(cudaMemcpyAsync(P->w_dose.as<char>() + (size_t)lo * as, stage, (size_t)n * as, cudaMemcpyHostToDevice, P->stream));
     } else {
         CU(cudaMemsetAsync(P->w_dose.as<char>() + (size_t)lo * as, 0, (size_t)n * as, P->stream));
     }
-    if (w_grad) CU(cudaMemcpyAsync(P->w_grad.as<double>() + lo, w_grad, (size_t)n * 8, cudaMemcpyHostToDevice, P->stream));
-    else CU(cudaMemsetAsync(P->w_grad.as<double>() + lo, 0, (size_t)n * 8, P->stream));
-    CU(cudaStreamSynchronize(P->stream));      // the caller's buffers may go away; later launches see the new weights
+    if (w_grad) {
+        char* sg = stage + (size_t)P->max_beamlets * 8;
+        std::memcpy(sg, w_grad, (size_t)n * 8);
+        CU(cudaMemcpyAsync(P->w_grad.as<double>() + lo, sg, (size_t)n * 8, cudaMemcpyHostToDevice, P->stream));
+    } else {
+        CU(cudaMemsetAsync(P->w_grad.as<double>() + lo, 0, (size_t)n * 8, P->stream));
+    }
+    P->weights_in_flight = true;
     return VMAT_OK;
 }
 
@@ -1106,6 +1116,10 @@ extern "C" int vmat_eval_async(vmat_plan_t* P, void* stream, int phase) {
     if (!P || phase < 0 || phase > 2) return fail(VMAT_E_ARG, "vmat_eval_async: bad argument");
     CU(cudaSetDevice(P->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : P->stream;
+    if (P->weights_in_flight) {          // a caller's stream is not ordered behind the weight copies on the plan's stream
+        if (st != P->stream) CU(cudaStreamSynchronize(P->stream));
+        P->weights_in_flight = false;
+    }
     P->evaluated = true;
     return launch_eval(P, st, phase);
 }

@@ -51,15 +51,16 @@ def listdiff(a, b):
     return [aa for aa in a if aa not in b]
 
 
-def _sharded_costs(P, cur, device, group):
+def _sharded_costs(P, cur, device, group, cand=None):
     """Every rank sums over its shard of the points j; the per-rank costs are all-reduced (the voxel
-    use of BASELINE.json's north star: the point set is too large for one distance pass)."""
+    use of BASELINE.json's north star: the point set is too large for one distance pass).  `cand`:
+    candidate coordinates (default: every point)."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = P.shape[0]
     j0, j1 = n * rank // world, n * (rank + 1) // world
-    part = kmedoid_costs(P[j0:j1], cur[j0:j1], device, candidates=P)
+    part = kmedoid_costs(P[j0:j1], cur[j0:j1], device, candidates=P if cand is None else cand)
     t = torch.from_numpy(part)
     if dist.get_backend(group) == "nccl":
         t = t.to(f"cuda:{device}")
@@ -88,6 +89,18 @@ def insertnewelement(kappa, ba, device: int = 0, _state=None, group=None):
     With a torch.distributed `group` the distance pass is sharded over the points."""
     P = _points(ba) if _state is None else _state["P"]
     cur = _nearest(P, kappa) if _state is None else _state["cur"]
+    cidx = None if _state is None else _state.get("cand")
+    if cidx is not None:        # candidates restricted to a subset of the points (sample_voxels(candidates=...))
+        Pc = _state["Pc"]
+        cost = kmedoid_costs(P, cur, device, candidates=Pc) if group is None else _sharded_costs(P, cur, device, group, Pc)
+        cost = np.where(_state["cand_taken"], np.inf, cost)
+        k = int(np.argmin(cost))
+        _state["cand_taken"][k] = True
+        best = int(cidx[k])
+        kappa.append(best)
+        diff = P - P[best]
+        _state["cur"] = np.minimum(cur, np.sqrt((diff * diff).sum(axis=1)))
+        return kappa
     cost = kmedoid_costs(P, cur, device) if group is None else _sharded_costs(P, cur, device, group)
     order = _candidate_order(kappa, ba, P.shape[0]) if _state is None else _state["order"]
     if order is None:
@@ -106,20 +119,29 @@ def insertnewelement(kappa, ba, device: int = 0, _state=None, group=None):
     return kappa
 
 
-def givemewholelist(kappa, ba, device: int = 0, group=None, limit=None):
+def givemewholelist(kappa, ba, device: int = 0, group=None, limit=None, candidates=None):
     """Order all points by greedy k-medoid insertion (kmedoids.py:62-68); `limit` stops after that
-    many medoids (voxel subsampling wants the first k, not the whole ordering)."""
+    many medoids (voxel subsampling wants the first k, not the whole ordering).  `candidates` (point
+    indices, an extension for large voxel sets): only these points may become medoids; the cost of a
+    candidate is still summed over ALL points."""
     kappa = list(kappa)
     P = _points(ba)
     state = {"P": P, "cur": _nearest(P, kappa), "order": _candidate_order(kappa, ba, P.shape[0])}
+    if candidates is not None:
+        cidx = np.asarray(candidates, dtype=np.int64)
+        state.update(cand=cidx, Pc=np.ascontiguousarray(P[cidx]), cand_taken=np.isin(cidx, kappa))
+        limit = min(limit if limit is not None else len(cidx), len(kappa) + int((~state["cand_taken"]).sum()))
     stop = P.shape[0] if limit is None else min(limit, P.shape[0])
     while len(kappa) < stop:
         kappa = insertnewelement(kappa, ba, device, state, group)
     return kappa
 
 
-def sample_voxels(coords, k: int, start: int = 0, device: int = 0, group=None):
+def sample_voxels(coords, k: int, start: int = 0, device: int = 0, group=None, candidates=None):
     """The first k medoids of the greedy insertion over voxel coordinates (n, 3), starting from voxel
     `start`: a spatially even voxel subsample.  With a torch.distributed `group` every rank prices the
-    candidates against its share of the voxels and the costs are all-reduced."""
-    return givemewholelist([int(start)], np.asarray(coords, dtype=np.float64), device=device, group=group, limit=k)
+    candidates against its share of the voxels and the costs are all-reduced.  `candidates`: indices of the
+    voxels that may be picked (default all; with a million voxels an insertion step over all candidates is
+    10^12 distances)."""
+    return givemewholelist([int(start)], np.asarray(coords, dtype=np.float64), device=device, group=group, limit=k,
+                           candidates=candidates)

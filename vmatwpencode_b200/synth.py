@@ -142,6 +142,37 @@ def subsample_case(case: "Case", rows) -> "Case":
                 struct_id=sid[rows].copy(), val_dtype=case.val_dtype, meta=dict(case.meta, subsampled_from=case.V))
 
 
+def subsample_device_case(dcase: "DeviceCase", rows, rich_structures: bool = False) -> "Case":
+    """subsample_case for a device-generated case: the rows of D are gathered on the GPU and brought to
+    the host as a scipy matrix; beamlet geometry is the full M x N rectangle per control point the device
+    generator uses."""
+    rows = np.sort(np.asarray(rows, dtype=np.int64))
+    c = dcase.csr
+    dev = c["vval"].device
+    r = torch.as_tensor(rows, device=dev)
+    lo, hi = c["vrowptr"][r], c["vrowptr"][r + 1]
+    n = hi - lo
+    pos = torch.arange(int(n.sum().item()), device=dev) - torch.repeat_interleave(torch.cumsum(n, 0) - n, n) + \
+        torch.repeat_interleave(lo, n)
+    indptr = np.concatenate([[0], np.cumsum(n.cpu().numpy())])
+    D = sp.csr_matrix((c["vval"][pos].double().cpu().numpy(), c["vcol"][pos].cpu().numpy(), indptr),
+                      shape=(len(rows), dcase.B))
+    sid, _ = structures(dcase.V, dcase.M, device=dev, rich=rich_structures)     # same device as the case: same memberships
+    sid = sid.cpu().numpy()
+    full = np.bincount(sid, minlength=256).astype(np.float64)
+    kept = np.bincount(sid[rows], minlength=256).astype(np.float64)
+    scale = np.divide(full, kept, out=np.ones(256), where=kept > 0)[sid[rows]]
+    M, N = dcase.M, dcase.N
+    xinter = np.arange(M, dtype=np.float64) * 0.5 - 0.25 * (M - 1)
+    yinter = np.arange(N, dtype=np.float64) * 0.5 - 0.25 * (N - 1)
+    xd = [np.repeat(xinter, N) for _ in range(dcase.nb)]
+    yd = [np.tile(yinter, M) for _ in range(dcase.nb)]
+    return Case(V=len(rows), nb=dcase.nb, M=M, N=N, beam_ptr=dcase.beam_ptr, angles=list(dcase.angles),
+                xinter=xinter, yinter=yinter, xdirection=xd, ydirection=yd, D=D,
+                thr=dcase.thr[rows].copy(), over=dcase.over[rows] * scale, under=dcase.under[rows] * scale,
+                struct_id=sid[rows].copy(), val_dtype="f32", meta=dict(dcase.meta, subsampled_from=dcase.V))
+
+
 def structures(V: int, M: int, device="cpu", rich: bool = False):
     """struct_id[V] plus the per-structure (threshold, over, under) table.
 
