@@ -32,16 +32,19 @@ def main():
     out = dict(workload=f"{args.workload}: {case.V} voxels x {case.B} beamlets, {case.nb} control points",
                iters=args.iters, C=args.C, kappasize=args.kappa, host_cores=os.cpu_count())
     seqs = {}
-    for name, flag in (("gpu_column_cache", True), ("gpu_sparse_only", False)):
+    for name, flag, lean in (("gpu_column_cache", True, False), ("gpu_sparse_minimize", False, False), ("gpu_sparse_only", False, True)):
         vl.use_column_cache = flag
+        vl.fast_rmp = lean             # gpu_sparse_only: the default path (lean loop over scipy's compiled L-BFGS-B routine)
         data = vl.bind(case, store="f32", acc="f64")
         t0 = time.perf_counter()
         vl.colGen(args.C, False, args.kappa, max_iter=args.iters)
         out[name + "_s"] = round(time.perf_counter() - t0, 4)
         out[name + "_evals"] = sum(h["nfev"] + 2 for h in data.history)
+        out[name + "_rmp_s"] = round(sum(h.get("rmp_s", 0.0) for h in data.history), 4)
         seqs[name] = [(h["idx"], tuple(h["l"]), tuple(h["r"])) for h in data.history]
         data.plan.close()
     vl.use_column_cache = False
+    vl.fast_rmp = True
     if args.profile:
         import cProfile
         import pstats

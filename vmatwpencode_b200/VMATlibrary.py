@@ -791,6 +791,7 @@ def colGen(C, WholeCircle, initialApertures, max_iter=None):
         data.history.append(dict(idx=int(bestApertureIndex), l=[int(v) for v in lm], r=[int(v) for v in rm],
                                  pstar=float(pstar), x=np.array(rmpres.x, dtype=float), fun=float(rmpres.fun),
                                  nit=int(rmpres.nit), nfev=int(rmpres.nfev), removed=list(removed),
+                                 rmp_s=float(getattr(data, "rmp_seconds", 0.0)),
                                  kelly=float(kelly_measure(lm, rm))))
         if len(data.listIndexofAperturesRemovedEachStep) > 1:
             # the same aperture keeps entering and leaving: stop (:1020-1031)
