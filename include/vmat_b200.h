@@ -44,21 +44,22 @@ typedef struct vmat_options {
     int32_t k2_tasks;       /* CTAs of the transposed kernel (0 = SM count x resident CTAs per SM) */
     int32_t use_graph;      /* 1: capture the evaluation as a CUDA graph (used by vmat_eval when y
                                cannot travel in the launch parameters)                          */
-    int32_t reserved[9];    /* tuning, 0 = default everywhere:
-                               [0] ring stages of the dose kernel      [1] ring stages of the transposed kernel
-                               [2] chunk cap of the dose layout        [7] chunk cap of the transposed layout
-                                   (chunks of 4 nonzeros per lane and super-slice; longer rows get more lanes)
-                               [3] 1 = no programmatic dependent launch
-                               [4] host-buffer path of vmat_eval, bits: 1 y read from mapped host memory,
-                                   2 results + completion tags written to mapped host memory,
-                                   4 y inside the launch parameters (default), 8 none (copy nodes)
-                               [5] 4 = int32 column indices, 1 = byte deltas (default: uint16 whenever they fit)
-                               [6] stages before a super-slice's end at which the dose kernel claims the next
-                               [8] evaluation kernels: 0 or 1 = the three kernels K1/K2/K3 chained by programmatic
-                                   dependent launch (default), 2 = one fused persistent kernel (dose, transposed
-                                   product, reductions and exchange in a single launch; fails if x does not fit in
-                                   shared memory); with the fused kernel k2_tasks is the grid size (default: one
-                                   CTA per SM) */
+    /* tuning, 0 = default everywhere */
+    int32_t k1_stages;      /* ring stages of the dose kernel (and of the fused kernel)                              */
+    int32_t k2_stages;      /* ring stages of the transposed kernel                                                  */
+    int32_t chunk_cap;      /* chunk cap of the dose layout: chunks of 4 nonzeros per lane and super-slice; longer
+                               rows get more lanes (default: 48, less on small slabs)                                */
+    int32_t no_pdl;         /* 1 = no programmatic dependent launch between the evaluation kernels                   */
+    int32_t host_path;      /* host-buffer path of vmat_eval, bits: 1 y read from mapped host memory, 2 results +
+                               completion tags written to mapped host memory, 4 y inside the launch parameters
+                               (default), 8 none (copy nodes)                                                        */
+    int32_t index_bytes;    /* 4 = int32 column indices, 1 = byte deltas (default: uint16 whenever they fit)         */
+    int32_t claim_lead;     /* stages before a super-slice's end at which the dose kernel claims the next            */
+    int32_t k2_chunk_cap;   /* chunk cap of the transposed layout (default: 24, less on small slabs)                 */
+    int32_t eval_kernels;   /* 0 or 1 = the three kernels K1/K2/K3 chained by programmatic dependent launch
+                               (default), 2 = one fused persistent kernel (dose, transposed product, reductions and
+                               exchange in a single launch; fails if x does not fit in shared memory); with the
+                               fused kernel k2_tasks is the grid size (default: one CTA per SM)                      */
 } vmat_options_t;
 
 /* Library / build identification. */

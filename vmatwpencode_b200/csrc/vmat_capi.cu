@@ -419,12 +419,12 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     if (P->opt.acc_dtype != VMAT_F32 && P->opt.acc_dtype != VMAT_F64) return fail(VMAT_E_ARG, "bad acc_dtype");
     if (P->opt.store_dtype < 0 || P->opt.store_dtype > 2) return fail(VMAT_E_ARG, "bad store_dtype");
     P->acc_size = P->opt.acc_dtype == VMAT_F64 ? 8 : 4;
-    P->pdl = P->opt.reserved[3] == 0;     // reserved[3] = 1 disables programmatic dependent launch
-    // reserved[4]: host-buffer path bits - 1 = K1 reads y from mapped host memory, 2 = K3 publishes
+    P->pdl = P->opt.no_pdl == 0;     // no_pdl = 1 disables programmatic dependent launch
+    // host_path: host-buffer path bits - 1 = K1 reads y from mapped host memory, 2 = K3 publishes
     // results + completion tags to mapped host memory, 4 = y travels in the launch parameters (plain
     // launches, no graph; default - measured on config 2: 86 us per call against 90-95 us for the
     // graph replays with a copy node in front, tools/latency.py)
-    P->host_path = P->opt.reserved[4] > 0 ? (P->opt.reserved[4] & 7) : 4;     // 8 = none of the bits
+    P->host_path = P->opt.host_path > 0 ? (P->opt.host_path & 7) : 4;     // 8 = none of the bits
     P->beam_ptr.assign(beam_ptr, beam_ptr + nb + 1);
     CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -433,8 +433,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     {   // index width: uint16 when every stored index fits (x index < B; K2 indices are tile-local, < T)
         const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
         const bool fits16 = B <= 65536 && ((T0 + 63) / 64 * 64) <= 65536;
-        // reserved[5]: 4 forces int32 indices, 1 selects byte deltas (any B: a lane's start index is a u32 in the header)
-        P->iw = P->opt.reserved[5] == 1 ? 1 : (P->opt.reserved[5] == 4 || !fits16) ? 4 : 2;
+        // index_bytes: 4 forces int32 indices, 1 selects byte deltas (any B: a lane's start index is a u32 in the header)
+        P->iw = P->opt.index_bytes == 1 ? 1 : (P->opt.index_bytes == 4 || !fits16) ? 4 : 2;
     }
     {   // dose-kernel CTA shape
         const size_t as0 = P->acc_size;
@@ -447,7 +447,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     }
 
     // ---- one fused kernel or the three-kernel path --------------------------------------------------
-    // reserved[8] & 3: 0 / 1 = the three kernels K1/K2/K3 chained by programmatic dependent launch (default:
+    // eval_kernels & 3: 0 / 1 = the three kernels K1/K2/K3 chained by programmatic dependent launch (default:
     // measured faster on every configuration), 2 = the single fused kernel (needs x + y or
     // two vg tiles next to at least 6 ring stages of 16 warps in shared memory); bit 2: uniform stages (experiment)
     int32_t T_plan = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
@@ -461,9 +461,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const size_t SB = (size_t)kFW * std::max<int>(store_units(P->opt.store_dtype, P->iw), std::max(hu1, hu2)) * 16;
         const size_t room = (size_t)P->smem_optin > U + 2048 ? (size_t)P->smem_optin - U - 2048 : 0;
         int nst = (int)std::min<size_t>(kFMaxStages, room / SB);
-        if (P->opt.reserved[0] > 0) nst = std::min(nst, std::max(2, P->opt.reserved[0]));
-        const bool can = P->iw != 1 && nst >= (P->opt.reserved[0] > 0 ? 2 : 6);
-        const int mode = P->opt.reserved[8] & 3;
+        if (P->opt.k1_stages > 0) nst = std::min(nst, std::max(2, P->opt.k1_stages));
+        const bool can = P->iw != 1 && nst >= (P->opt.k1_stages > 0 ? 2 : 6);
+        const int mode = P->opt.eval_kernels & 3;
         if (mode == 2 && !can) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel does not fit this plan (beamlet vector too large for shared memory, or byte-delta indices)");
         P->fused = can && mode == 2;
         if (P->fused) {
@@ -505,7 +505,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     std::vector<uint8_t> fused_nch1, fused_tpr1;          // fused plans: per dose item chunk counts, lanes per row,
     std::vector<int32_t> fused_grp1, fused_grp_items;     // group, and the number of dose items per group
     int32_t fused_grp_tiles = 1;
-    const bool fused_uniform = (P->opt.reserved[8] & 4) != 0;     // experiment: uniform (padded) stages in the fused layout
+    const bool fused_uniform = (P->opt.eval_kernels & 4) != 0;     // experiment: uniform (padded) stages in the fused layout
     std::vector<int32_t> vpads;            // per voxel row (byte-delta layout only)
     CU(csr_flag.alloc(4)); CU(cudaMemsetAsync(csr_flag.p, 0, 4, st));
     auto check_csr = [&](int64_t nrows, int64_t ncols, int sorted, const int64_t* d_rowptr, const int32_t* d_col,
@@ -559,7 +559,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         // get shorter super-slices, so that the longest one is not most of the kernel (config 2 on 8 GPUs:
         // 73 super-slices of up to 49 stages for 148 CTAs, the dose kernel's CTAs finished between 2 and 12.5 us)
         const int64_t per_cta = nnz / 2048 / std::max(1, P->sm_count);
-        const int32_t cap = P->opt.reserved[2] > 0 ? P->opt.reserved[2]
+        const int32_t cap = P->opt.chunk_cap > 0 ? P->opt.chunk_cap
                           : (int32_t)std::min<int64_t>(kChunkCapK1, std::max<int64_t>(12, per_cta / 2));
         StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
         sd.ragged = P->fused && !fused_uniform;
@@ -586,7 +586,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
                 fused_grp_items.push_back((int32_t)(sd.ss_tpr.size() - before));
             }
             fused_nch1 = sd.ss_nch; fused_tpr1 = sd.ss_tpr; fused_grp1 = sd.ss_tile;
-            if (sd.too_long) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel: a voxel row has more than 32 640 nonzeros (use reserved[8] = 1)");
+            if (sd.too_long) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel: a voxel row has more than 32 640 nonzeros (use eval_kernels = 1)");
         }
         const int32_t nss = (int32_t)sd.ss_tpr.size();
         P->nslices1 = nss * W; P->nss1 = nss; P->W1 = W; P->units1 = sd.ss_off.back();
@@ -620,7 +620,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const int32_t W = P->fused ? kFW : P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = header_units_k2(P->iw);
         P->W2 = W;
         P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
-        P->nstages2 = P->opt.reserved[1] > 0 ? std::max(2, std::min(16, P->opt.reserved[1])) : 8;
+        P->nstages2 = P->opt.k2_stages > 0 ? std::max(2, std::min(16, P->opt.k2_stages)) : 8;
         const size_t tile_bytes = ((size_t)T * P->acc_size + 127) & ~(size_t)127;
         P->k2_smem = tile_bytes + (size_t)P->nstages2 * P->stage_bytes2;
         if (!P->fused && P->k2_smem + 2048 > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
@@ -648,7 +648,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         d_seg.alloc(0);
 
         const int64_t per_cta2 = nnz / 2048 / std::max(1, P->sm_count);
-        const int32_t cap = P->opt.reserved[7] > 0 ? P->opt.reserved[7]
+        const int32_t cap = P->opt.k2_chunk_cap > 0 ? P->opt.k2_chunk_cap
                           : (int32_t)std::min<int64_t>(P->fused ? 48 : kChunkCapK2, std::max<int64_t>(8, per_cta2 / 4));
         StreamDesc sd{W, HU, units, P->fused ? std::min(cap, 255) : cap};
         sd.ragged = P->fused && !fused_uniform;
@@ -668,7 +668,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const std::vector<int32_t>& ss_tile = sd.ss_tile;
         P->nss2 = (int32_t)ss_cost.size(); P->nslices2 = P->nss2 * W; P->units2 = sd.ss_off.back();
         if (P->fused) {
-            if (sd.too_long) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel: a beamlet segment has more than 32 640 nonzeros (use reserved[8] = 1)");
+            if (sd.too_long) return fail(VMAT_E_UNSUPPORTED, "fused evaluation kernel: a beamlet segment has more than 32 640 nonzeros (use eval_kernels = 1)");
             // the queue: dose items (group order), then transposed items (tile order)
             std::vector<FItem> fi((size_t)P->nss1 + P->nss2);
             for (int32_t i = 0; i < P->nss1; ++i) {
@@ -815,7 +815,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const size_t xbytes = (((size_t)B * as + 127) & ~(size_t)127) + (((size_t)nb * 8 + 127) & ~(size_t)127);   // x and y
         P->x_in_smem = xbytes + 2 * (size_t)P->stage_bytes1 + 4096 <= (size_t)P->smem_optin;
         const size_t avail = (size_t)P->smem_optin - 4096 - (P->x_in_smem ? xbytes : 0);
-        const size_t want = P->opt.reserved[0] > 0 ? (size_t)P->opt.reserved[0] : (P->W1 == 4 ? 8 : 16);
+        const size_t want = P->opt.k1_stages > 0 ? (size_t)P->opt.k1_stages : (P->W1 == 4 ? 8 : 16);
         P->nstages1 = (int)std::max<size_t>(2, std::min<size_t>({(size_t)16, want, avail / P->stage_bytes1}));
         P->k1_smem = (P->x_in_smem ? xbytes : 0) + (size_t)P->nstages1 * P->stage_bytes1;
         P->k1_threads = (P->W1 + 1) * 32;
@@ -881,7 +881,7 @@ static int launch_fused_t(vmat_plan* P, cudaStream_t st, int phase, bool inline_
     a.sync = P->syncF.as<unsigned int>(); a.fblock = P->fblock.as<double>();
     a.beam_ptr = P->beam_ptr_d.as<int32_t>(); a.w_grad = P->w_grad.as<double>();
     a.gbf = P->gbf.as<double>(); a.result = P->result.as<double>();
-    a.claim_lead = P->opt.reserved[6] > 0 ? P->opt.reserved[6] : kClaimLeadDefault;
+    a.claim_lead = P->opt.claim_lead > 0 ? P->opt.claim_lead : kClaimLeadDefault;
     a.dose_only = P->col_mode ? 1 : 0;
     a.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
     if (inline_y) {
@@ -930,7 +930,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.d = P->d.as<AT>(); a1.vg = P->vg.as<AT>(); a1.fpart = P->fpart.as<double>();
         a1.counter = P->counter.as<unsigned int>();
         a1.nb = P->nb;
-        a1.claim_lead = P->opt.reserved[6] > 0 ? P->opt.reserved[6] : kClaimLeadDefault;
+        a1.claim_lead = P->opt.claim_lead > 0 ? P->opt.claim_lead : kClaimLeadDefault;
         a1.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
         if (inline_y) {              // the intensities travel in the launch parameters; CTA 0 mirrors them into P->y
             a1.y_mirror = P->y.as<double>();

@@ -56,14 +56,13 @@ class DosePlan:
         opt.acc_dtype = _lib.DTYPE_CODES[acc]
         opt.tile_voxels, opt.k1_threads, opt.k2_threads, opt.k2_tasks = tile_voxels, k1_threads, k2_threads, k2_tasks
         opt.use_graph = 1 if use_graph else 0
-        opt.reserved[0], opt.reserved[1] = k1_stages, k2_stages      # ring depths (0 = default)
-        opt.reserved[2] = chunk_cap
-        opt.reserved[3] = 0 if pdl else 1
-        opt.reserved[4] = host_path
-        opt.reserved[6] = claim_lead           # dose kernel: stages before a super-slice's end at which the next is claimed (0 = default)
-        opt.reserved[7] = k2_chunk_cap         # chunk cap of the transposed layout (chunk_cap is the dose layout's)
-        opt.reserved[5] = index_bytes          # 4 forces int32 column indices, 1 byte deltas; 0 = uint16 whenever they fit
-        opt.reserved[8] = fused                # 0 / 1 = the three kernels K1/K2/K3 (default), 2 = the single fused evaluation kernel
+        opt.k1_stages, opt.k2_stages = k1_stages, k2_stages          # ring depths (0 = default)
+        opt.chunk_cap, opt.k2_chunk_cap = chunk_cap, k2_chunk_cap    # chunk caps of the dose / transposed layouts
+        opt.no_pdl = 0 if pdl else 1
+        opt.host_path = host_path
+        opt.claim_lead = claim_lead            # dose kernel: stages before a super-slice's end at which the next is claimed
+        opt.index_bytes = index_bytes          # 4 forces int32 column indices, 1 byte deltas; 0 = uint16 whenever they fit
+        opt.eval_kernels = fused               # 0 / 1 = the three kernels K1/K2/K3 (default), 2 = the single fused evaluation kernel
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         over = np.ascontiguousarray(over, dtype=np.float64)
