@@ -467,11 +467,13 @@ def kelly_measure(l, r):
 
 
 def col_gen(st: OracleState, C, kappasize, max_iter=None, C2=1.0, C3=1.0, b=0.5, vmax=2.25,
-            speedlim=0.83, bw=0.5, RU=10.0, clean=False, elimination=False, threshold=10E-3):
-    """colGen (greedyVMATsampling.py:937-1046, non-WholeCircle branch) without plots/pickle.
+            speedlim=0.83, bw=0.5, RU=10.0, clean=False, elimination=False, threshold=10E-3, kappa0=None):
+    """colGen (greedyVMATsampling.py:937-1046) without plots/pickle.  `kappa0`: the module-level candidate
+    ordering of the WholeCircle branch (:959-966; the reference hard-codes its 178-entry k-medoid ordering, :30);
+    default: the non-WholeCircle branch (0 .. numbeams-1, :968-980).
     Returns the greedy history: per iteration idx, l, r, pstar, x, fun."""
     YU = RU / speedlim
-    kappa = list(range(st.numbeams))
+    kappa = list(range(st.numbeams)) if kappa0 is None else list(kappa0)
     random.seed(13)
     kappa = random.sample(kappa, len(kappa))
     for _ in range(min(kappasize, len(kappa))):

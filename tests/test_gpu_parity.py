@@ -880,3 +880,24 @@ def test_lean_rmp_loop_equals_scipy_minimize():
     assert len(runs[True]) > 0 and runs[True] == runs[False]
     a, b = runs[(True, "state")], runs[(False, "state")]
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_greedy_loop_whole_circle_branch_with_the_reference_kappa():
+    """colGen(C, WholeCircle=True, ...) (greedyVMATsampling.py:959-966): the candidates come from the module-level
+    `kappa`, for which the reference hard-codes its 178-entry k-medoid ordering of the 2-degree control points (:30,
+    recorded in tests/golden/kmedoids.npz).  178 control points, gantry step 2: neighbouring apertures bound the
+    leaf ranges (travel 10.8 beamlets)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmedoids.npz"))
+    kappa = [int(v) for v in z["kappa178"]]
+    case = make_case(V=8000, nb=178, M=4, N=14, density=0.004, seed=178, gastep=2)
+    want = O.col_gen(O.OracleState(case), C=0.02, kappasize=16, max_iter=7, clean=True, kappa0=kappa)
+    data = vl.bind(case, store="f32", acc="f64")
+    vl.kappa = list(kappa)
+    try:
+        vl.colGen(0.02, True, 16, max_iter=7)
+    finally:
+        vl.kappa = []
+    assert len(want) > 0 and [h["idx"] for h in data.history] == [w["idx"] for w in want]
+    for h, w in zip(data.history, want):
+        assert h["l"] == w["l"] and h["r"] == w["r"]
+    data.plan.close()
