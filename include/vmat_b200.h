@@ -60,6 +60,9 @@ typedef struct vmat_options {
                                (default), 2 = one fused persistent kernel (dose, transposed product, reductions and
                                exchange in a single launch; fails if x does not fit in shared memory); with the
                                fused kernel k2_tasks is the grid size (default: one CTA per SM)                      */
+    int32_t k2_pool_pct;    /* share (percent) of the transposed layout that is not statically partitioned but claimed
+                               in small tasks by CTAs that have finished their piece (default 12; -1 = none)          */
+    int32_t reserved[3];
 } vmat_options_t;
 
 /* Library / build identification. */

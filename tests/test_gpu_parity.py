@@ -152,7 +152,10 @@ def test_eval_random_state_vs_oracle(shape, store, acc, val_dtype, tol, fused):
                                   dict(fused=2, k1_stages=3, tile_voxels=64, k2_tasks=5), dict(fused=2, chunk_cap=1, k2_chunk_cap=1),
                                   dict(fused=2, chunk_cap=1000, k2_chunk_cap=1000, tile_voxels=128), dict(fused=2, index_bytes=4, claim_lead=1),
                                   dict(fused=2, pdl=False, use_graph=False), dict(fused=2, tile_voxels=64, claim_lead=100, k2_tasks=200),
-                                  dict(fused=1), dict(fused=1, k2_tasks=7, tile_voxels=64)])
+                                  dict(fused=1), dict(fused=1, k2_tasks=7, tile_voxels=64),
+                                  # the transposed kernel's dynamic tail: none, half of the work, with few CTAs / tiny tiles
+                                  dict(k2_pool_pct=-1), dict(k2_pool_pct=50, tile_voxels=64), dict(k2_pool_pct=30, k2_tasks=7),
+                                  dict(k2_pool_pct=90, k2_chunk_cap=2, tile_voxels=128)])
 def test_plan_options_do_not_change_results(opts):
     case = make_case(V=9000, nb=8, M=4, N=6, density=0.02, seed=71)
     st = O.OracleState(case)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(PriceRow) == 56
     assert ctypes.sizeof(_lib.PriceParams) == 64          # C, C2, C3, b, M, N, variant, reserved[5]
-    assert ctypes.sizeof(_lib.Options) == 64
+    assert ctypes.sizeof(_lib.Options) == 80
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -71,6 +71,12 @@ def main():
                     out[f"items_cta{cta}"] = rows
         else:
             out["trace_us"] = dict(k1_done=us(k1[:, 3]), k2_entry=us(k2[:, 0]), k2_done=us(k2[:, 3]))
+            plan.set_timing(True)
+            for _ in range(200):
+                plan.eval_async(side.cuda_stream)
+            torch.cuda.synchronize()
+            out["kernels_us"] = {k: round(v * 1e3, 2) for k, v in plan.get_timing().items() if k.endswith("_ms")}
+            plan.set_timing(False)
         print(json.dumps(out), flush=True)
         plan.close()
 

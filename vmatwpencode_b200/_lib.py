@@ -28,7 +28,8 @@ class Options(C.Structure):
                 ("k1_threads", C.c_int32), ("k2_threads", C.c_int32), ("k2_tasks", C.c_int32),
                 ("use_graph", C.c_int32), ("k1_stages", C.c_int32), ("k2_stages", C.c_int32), ("chunk_cap", C.c_int32),
                 ("no_pdl", C.c_int32), ("host_path", C.c_int32), ("index_bytes", C.c_int32), ("claim_lead", C.c_int32),
-                ("k2_chunk_cap", C.c_int32), ("eval_kernels", C.c_int32)]
+                ("k2_chunk_cap", C.c_int32), ("eval_kernels", C.c_int32), ("k2_pool_pct", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class PriceRow(C.Structure):

@@ -59,7 +59,8 @@ struct vmat_plan {
     int32_t nslices1 = 0, nss1 = 0, W1 = 16, nstages1 = 8, stage_bytes1 = 0;
     int64_t units1 = 0;
     // K2 layout
-    DevBuf sell2, off2, tpr2, tasks2, cta_ptr2;
+    DevBuf sell2, off2, tpr2, tasks2, cta_ptr2, pool2;
+    int32_t npool2 = 0;
     int k2_grid = 1;
     int32_t nslices2 = 0, nss2 = 0, ntasks2 = 0, ntiles = 0, T = 0, W2 = 4, nstages2 = 8, stage_bytes2 = 0;
     int64_t units2 = 0;
@@ -718,8 +719,36 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         if (int rc = k2_occupancy(P, &occ)) return rc;
         const int64_t G = P->opt.k2_tasks > 0 ? P->opt.k2_tasks : (int64_t)P->sm_count * occ;
         P->k2_grid = (int)std::max<int64_t>(1, std::min<int64_t>(G, std::max<int64_t>(1, (int64_t)P->nss2)));
+        // Dynamic tail: the shortest super-slices of every tile (its last ones) - about k2_pool_pct percent of the
+        // tile's stages - are kept out of the static pieces and cut into small tasks that CTAs claim from a counter
+        // once their own piece is done.  Equal stage counts do not mean equal times (the pieces of config 3 are
+        // equal to 0.5 % and finish between 121 and 136 us), and a CTA that is done early has nothing else to do.
+        const int32_t pool_pct = P->opt.k2_pool_pct < 0 ? 0 : (P->opt.k2_pool_pct > 0 ? std::min(P->opt.k2_pool_pct, 90) : 12);
+        std::vector<int32_t> pool_begin(P->nss2 + 1, 0);      // per super-slice index of a tile's first one: where its pool part starts
+        std::vector<K2Task> pool;
+        {
+            const int32_t nss = P->nss2;
+            const int64_t task_cost = 8;                        // stages per pool task (one or a few short super-slices)
+            int32_t t0 = 0;
+            while (t0 < nss) {
+                int32_t t1 = t0;
+                int64_t tile_w = 0;
+                while (t1 < nss && ss_tile[t1] == ss_tile[t0]) tile_w += ss_cost[t1++];
+                int32_t pb = t1;
+                int64_t w = 0;
+                while (pb > t0 + 1 && (w + ss_cost[pb - 1]) * 100 <= tile_w * pool_pct) w += ss_cost[--pb];
+                for (int32_t k = t0; k < t1; ++k) pool_begin[k] = pb;
+                int32_t a0 = pb;
+                int64_t acc = 0;
+                for (int32_t k = pb; k < t1; ++k) {
+                    acc += ss_cost[k];
+                    if (acc >= task_cost || k == t1 - 1) { pool.push_back(K2Task{ss_tile[t0], a0, k + 1, 0}); a0 = k + 1; acc = 0; }
+                }
+                t0 = t1;
+            }
+        }
         int64_t total_w = 0;
-        for (int64_t c : ss_cost) total_w += c;
+        for (int32_t k = 0; k < P->nss2; ++k) if (k < pool_begin[k]) total_w += ss_cost[k];
         std::vector<K2Task> tasks;
         std::vector<int32_t> cta_ptr(P->k2_grid + 1, 0);
         {
@@ -728,7 +757,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             auto next_tile = [&]() {
                 f = tend;
                 while (tend < nss && ss_tile[tend] == ss_tile[f]) ++tend;
-                bk = tend;
+                bk = f < nss ? pool_begin[f] : tend;  // the rest of the tile belongs to the pool
             };
             next_tile();
             int64_t assigned = 0;
@@ -756,6 +785,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
                                   sd.seg_cb, sd.rows, nullptr, nullptr, nullptr, 0, d_bcol, d_bval,
                                   P->sell2, P->off2, P->tpr2)) return rc;
         if (upload_vec(P->tasks2, tasks, st)) return VMAT_E_CUDA;
+        if (upload_vec(P->pool2, pool, st)) return VMAT_E_CUDA;
+        P->npool2 = (int32_t)pool.size();
         }
     }
     up_bcol.alloc(0); up_bval.alloc(0); up_brow.alloc(0);
@@ -932,6 +963,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.nb = P->nb;
         a1.claim_lead = P->opt.claim_lead > 0 ? P->opt.claim_lead : kClaimLeadDefault;
         a1.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
+        a1.k2_pool_counter = (P->npool2 > 0 && !P->col_mode) ? P->counter.as<unsigned int>() + 2 : nullptr;
         if (inline_y) {              // the intensities travel in the launch parameters; CTA 0 mirrors them into P->y
             a1.y_mirror = P->y.as<double>();
             a1.y_inline_n = P->nb;
@@ -959,6 +991,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a2.k1_counter = P->counter.as<unsigned int>();
         a2.fpart = P->fpart.as<double>(); a2.fblock = P->fblock.as<double>(); a2.nfpart = P->nslices1;
         a2.trace = P->tracing ? P->trace.as<unsigned long long>() + (size_t)P->k1_grid * kTraceSlots : nullptr;
+        a2.pool_tasks = P->pool2.as<K2Task>(); a2.npool = P->npool2; a2.pool_counter = P->counter.as<unsigned int>() + 2;
         DISPATCH_IW(IW, {   // always launched (even with an empty task list): it also folds the objective partials
             DISPATCH_W2(W2c, {
                 auto kern2 = k2_beamlet_grad<VT, AT, W2c, IW>;

@@ -181,6 +181,7 @@ struct K1Args {
     // first stage landed, consumers done, producer done]; nullptr = off
     unsigned long long* trace;
     int32_t claim_lead;           // stages before the end of a super-slice at which the next one is claimed
+    unsigned int* k2_pool_counter; // the transposed kernel's dynamic-tail counter, reset here for this evaluation (or nullptr)
 };
 
 // four consecutive elements with one (float) or two (double) 16-byte loads
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     if (blockIdx.x == 0 && warp < W) {
         if (XS && a.y_mirror != nullptr) { for (int j = tid; j < a.nb; j += W * 32) a.y_mirror[j] = ys[j]; }
         if (a.seq != nullptr && tid == 0) atomicAdd(a.seq, 1ull);
+        if (a.k2_pool_counter != nullptr && tid == 0) *a.k2_pool_counter = 0u;      // (the previous evaluation is complete)
     }
 
     if (warp == W) {
@@ -403,6 +405,11 @@ struct K2Args {
     double* fblock;               // [gridDim.x] ... folded here into one fixed-order sum per CTA
     int32_t nfpart;
     unsigned long long* trace;    // diagnostics, as in K1Args: [entry, K1 done, first stage, consumers done, producer done]
+    // dynamic tail: the shortest super-slices of every tile are not part of the static pieces but of a pool of small
+    // tasks that CTAs claim when their own piece is done - it absorbs the spread of the pieces' finish times
+    const K2Task* pool_tasks;     // [npool], ordered by tile
+    int32_t npool;
+    unsigned int* pool_counter;   // reset by the dose kernel of the same evaluation
 };
 
 template <typename VT, typename AT, int W, int IW>
@@ -432,8 +439,18 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
         if (lane == 0) {
             const uint64_t pol = l2_evict_first_policy();
             RingPos pos;
-            for (int ti = t_begin; ti < t_end; ++ti) {
-                const K2Task task = a.tasks[ti];
+            bool dynamic = false;
+            for (int ti = t_begin;; ++ti) {
+                K2Task task;
+                if (!dynamic && ti < t_end) {
+                    task = a.tasks[ti];
+                } else {
+                    if (a.npool == 0) break;
+                    if (!dynamic) { pdl_wait(); dynamic = true; }      // the dose kernel has reset the pool counter
+                    const unsigned int q = atomicAdd(a.pool_counter, 1u);
+                    if (q >= (unsigned)a.npool) break;
+                    task = a.pool_tasks[q];
+                }
                 int64_t o0 = a.ss_off[task.ss_begin];
                 for (int ss = task.ss_begin; ss < task.ss_end; ++ss) {
                     const int64_t o1 = a.ss_off[ss + 1];

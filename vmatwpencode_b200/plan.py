@@ -40,7 +40,7 @@ class DosePlan:
                  tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0, k2_tasks: int = 0,
                  use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0,
                  index_bytes: int = 0, k1_stages: int = 0, k2_stages: int = 0, claim_lead: int = 0,
-                 k2_chunk_cap: int = 0, fused: int = 0):
+                 k2_chunk_cap: int = 0, fused: int = 0, k2_pool_pct: int = 0):
         """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
         {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
         lib = _lib.load()
@@ -63,6 +63,7 @@ class DosePlan:
         opt.claim_lead = claim_lead            # dose kernel: stages before a super-slice's end at which the next is claimed
         opt.index_bytes = index_bytes          # 4 forces int32 column indices, 1 byte deltas; 0 = uint16 whenever they fit
         opt.eval_kernels = fused               # 0 / 1 = the three kernels K1/K2/K3 (default), 2 = the single fused evaluation kernel
+        opt.k2_pool_pct = k2_pool_pct          # transposed kernel: percent of the work claimed dynamically at the end (0 = default, -1 = none)
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         over = np.ascontiguousarray(over, dtype=np.float64)
