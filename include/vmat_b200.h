@@ -235,6 +235,18 @@ int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
 int vmat_kmedoid_costs_shard(int device, int64_t n_cand, const double* cand, int64_t n, int32_t dim,
                              const double* points, const double* curmin, double* cost /* n_cand */);
 
+/* The same with the point set resident on the device between insertion steps (a whole ordering is thousands of
+ * steps over the same points): vmat_kmedoid_open uploads this rank's points (n x dim), their curmin and the candidate
+ * coordinates once; vmat_kmedoid_costs_resident computes cost[n_cand] (to the host, and/or leaves it on the device for
+ * the caller's all-reduce: *cost_dev); vmat_kmedoid_insert(medoid) lowers curmin by one more medoid, in the operation
+ * order of the host bookkeeping (bit-identical). */
+typedef struct vmat_kmedoid vmat_kmedoid_t;
+int vmat_kmedoid_open(vmat_kmedoid_t** session, int device, int64_t n, int32_t dim, const double* points,
+                      const double* curmin, int64_t n_cand, const double* cand);
+int vmat_kmedoid_insert(vmat_kmedoid_t* session, const double* medoid /* dim */);
+int vmat_kmedoid_costs_resident(vmat_kmedoid_t* session, double* cost_host /* n_cand or NULL */, void** cost_dev /* or NULL */);
+int vmat_kmedoid_close(vmat_kmedoid_t* session);
+
 /*
  * Restricted-master-problem fast path (solveRMC, greedyVMATsampling.py:858-885): while the
  * apertures of the listed control points stay fixed, vmat_rmp_begin caches their dose columns

@@ -904,3 +904,26 @@ def test_greedy_loop_whole_circle_branch_with_the_reference_kappa():
     for h, w in zip(data.history, want):
         assert h["l"] == w["l"] and h["r"] == w["r"]
     data.plan.close()
+
+
+def test_kmedoid_resident_session_with_candidate_subset():
+    """Voxel sampling with the candidates restricted to a subset and the points resident on the device between the
+    insertion steps (vmat_kmedoid_open / insert / costs_resident): step by step the same medoids as a brute-force
+    numpy argmin over the candidate set, for a small (sequential-sum kernel) and a large (tiled kernel) point set."""
+    from vmatwpencode_b200 import kmedoids as km
+    rng = np.random.default_rng(23)
+    for n, stride, k in ((900, 7, 12), (9000, 31, 10)):
+        P = np.round(rng.random((n, 3)) * 40)
+        cand = np.arange(0, n, stride)
+        start = int(cand[len(cand) // 2])
+        got = km.sample_voxels(P, k, start=start, candidates=cand)
+        kap = [start]
+        cur = np.sqrt(((P - P[start]) ** 2).sum(axis=1))
+        for _ in range(k - 1):
+            cost = np.array([np.minimum(cur, np.sqrt(((P - P[c]) ** 2).sum(axis=1))).sum() if c not in kap else np.inf
+                             for c in cand])
+            best = int(cand[int(np.argmin(cost))])
+            assert abs(cost.min() - np.minimum(cur, np.sqrt(((P - P[got[len(kap)]]) ** 2).sum(axis=1))).sum()) <= 1e-9 * cost.min()
+            kap.append(best)
+            cur = np.minimum(cur, np.sqrt(((P - P[best]) ** 2).sum(axis=1)))
+        assert got == kap

@@ -82,6 +82,10 @@ SIGNATURES = {
     "vmat_price_ex": (C.c_int, [_P, C.c_int32, _P, C.POINTER(PriceParams), C.POINTER(PriceRow), _P, _P, _P, _P]),
     "vmat_kmedoid_costs": (C.c_int, [C.c_int, C.c_int64, C.c_int32, _P, _P, _P]),
     "vmat_kmedoid_costs_shard": (C.c_int, [C.c_int, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
+    "vmat_kmedoid_open": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P]),
+    "vmat_kmedoid_insert": (C.c_int, [_P, _P]),
+    "vmat_kmedoid_costs_resident": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "vmat_kmedoid_close": (C.c_int, [_P]),
 }
 
 _lib = None

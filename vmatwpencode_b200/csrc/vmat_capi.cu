@@ -1659,6 +1659,78 @@ extern "C" int vmat_kmedoid_costs_shard(int device, int64_t nc, const double* ca
     return VMAT_OK;
 }
 
+// ---- resident session: points, candidates and curmin stay on the device between insertion steps ----------------
+struct vmat_kmedoid {
+    int device = 0;
+    int64_t n = 0, nc = 0;
+    int32_t dim = 0;
+    DevBuf points, cand, curmin, cost, medoid;
+};
+
+static int km_launch_costs(int64_t n, int64_t nc, int32_t dim, const double* dc, const double* dp, const double* dm, double* dout) {
+    if (n <= kKmSequentialMax) {
+        k6_kmedoid_cost<<<(unsigned)nc, kKmThreads>>>(n, dim, dc, dp, dm, dout);
+    } else {
+        const unsigned grid = (unsigned)((nc + kKmTile - 1) / kKmTile);
+#define VMAT_KM_CASE(D) case D: k6_kmedoid_cost_tiled<D><<<grid, kKmThreads>>>(n, nc, dc, dp, dm, dout); break;
+        switch (dim) { VMAT_KM_CASE(1) VMAT_KM_CASE(2) VMAT_KM_CASE(3) VMAT_KM_CASE(4) VMAT_KM_CASE(5) VMAT_KM_CASE(6) VMAT_KM_CASE(7) VMAT_KM_CASE(8) }
+#undef VMAT_KM_CASE
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vmat_kmedoid_open(vmat_kmedoid_t** out, int device, int64_t n, int32_t dim, const double* points,
+                                 const double* curmin, int64_t n_cand, const double* cand) {
+    if (!out || n < 0 || n_cand <= 0 || dim <= 0 || dim > 8 || !cand || (n > 0 && (!points || !curmin)))
+        return fail(VMAT_E_ARG, "vmat_kmedoid_open: bad argument");
+    CU(cudaSetDevice(device));
+    vmat_kmedoid* K = new (std::nothrow) vmat_kmedoid();
+    if (!K) return fail(VMAT_E_NOMEM, "out of host memory");
+    struct Guard { vmat_kmedoid* p; ~Guard() { delete p; } } guard{K};
+    K->device = device; K->n = n; K->nc = n_cand; K->dim = dim;
+    CU(K->points.alloc((size_t)n * dim * 8)); CU(K->curmin.alloc((size_t)n * 8));
+    CU(K->cand.alloc((size_t)n_cand * dim * 8)); CU(K->cost.alloc((size_t)n_cand * 8)); CU(K->medoid.alloc(8 * 8));
+    if (n > 0) {
+        CU(cudaMemcpy(K->points.p, points, (size_t)n * dim * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(K->curmin.p, curmin, (size_t)n * 8, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(K->cand.p, cand, (size_t)n_cand * dim * 8, cudaMemcpyHostToDevice));
+    guard.p = nullptr;
+    *out = K;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_kmedoid_insert(vmat_kmedoid_t* K, const double* medoid) {
+    if (!K || !medoid) return fail(VMAT_E_ARG, "vmat_kmedoid_insert: null");
+    CU(cudaSetDevice(K->device));
+    CU(cudaMemcpy(K->medoid.p, medoid, (size_t)K->dim * 8, cudaMemcpyHostToDevice));
+    if (K->n > 0) {
+        k6_update_curmin<<<(unsigned)((K->n + 255) / 256), 256>>>(K->n, K->dim, K->points.as<double>(), K->medoid.as<double>(), K->curmin.as<double>());
+        CU(cudaGetLastError());
+    }
+    return VMAT_OK;
+}
+
+extern "C" int vmat_kmedoid_costs_resident(vmat_kmedoid_t* K, double* cost_host, void** cost_dev) {
+    if (!K) return fail(VMAT_E_ARG, "vmat_kmedoid_costs_resident: null");
+    CU(cudaSetDevice(K->device));
+    if (K->n > 0) { if (int rc = km_launch_costs(K->n, K->nc, K->dim, K->cand.as<double>(), K->points.as<double>(), K->curmin.as<double>(), K->cost.as<double>())) return rc; }
+    else CU(cudaMemset(K->cost.p, 0, (size_t)K->nc * 8));
+    if (cost_host) CU(cudaMemcpy(cost_host, K->cost.p, (size_t)K->nc * 8, cudaMemcpyDeviceToHost));
+    else CU(cudaDeviceSynchronize());
+    if (cost_dev) *cost_dev = K->cost.p;
+    return VMAT_OK;
+}
+
+extern "C" int vmat_kmedoid_close(vmat_kmedoid_t* K) {
+    if (!K) return VMAT_OK;
+    cudaSetDevice(K->device);
+    cudaDeviceSynchronize();
+    delete K;
+    return VMAT_OK;
+}
+
 extern "C" int vmat_kmedoid_costs(int device, int64_t n, int32_t dim, const double* points,
                                   const double* curmin, double* cost) {
     return vmat_kmedoid_costs_shard(device, n, points, n, dim, points, curmin, cost);

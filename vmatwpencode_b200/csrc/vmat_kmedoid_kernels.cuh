@@ -119,6 +119,21 @@ __global__ void __launch_bounds__(kKmThreads) k6_kmedoid_cost_tiled(int64_t n, i
     if (tid < kKmTile && c0 + tid < nc) cost[c0 + tid] = sh[tid][0];
 }
 
+// curmin[j] = min(curmin[j], ||m - p_j||): one more medoid (one more row of D[kappa, :], kmedoids.py:38-41).  Same
+// operation order as km_dist and as numpy's sqrt(((d0*d0) + d1*d1) + d2*d2): the resident session (points and curmin
+// stay on the device between insertion steps) and the host bookkeeping agree bit for bit.
+__global__ void k6_update_curmin(int64_t n, int dim, const double* __restrict__ P, const double* __restrict__ medoid,
+                                 double* __restrict__ curmin) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int d = 0; d < dim; ++d) {
+        const double df = __dsub_rn(P[j * dim + d], medoid[d]);
+        s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    curmin[j] = fmin(curmin[j], __dsqrt_rn(s));
+}
+
 // ---------------------------------------------------------------------------------
 // K7: dose-volume histograms (printresults, greedyVMATsampling.py:888-912).  Integer counts with
 // integer atomics: exact whatever the order.  Bin k holds edges[k] <= d < edges[k+1]; the last bin

@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .plan import kmedoid_costs
+from .plan import kmedoid_costs, KMedoidSession
 
 
 def _points(ba) -> np.ndarray:
@@ -91,15 +91,28 @@ def insertnewelement(kappa, ba, device: int = 0, _state=None, group=None):
     cur = _nearest(P, kappa) if _state is None else _state["cur"]
     cidx = None if _state is None else _state.get("cand")
     if cidx is not None:        # candidates restricted to a subset of the points (sample_voxels(candidates=...))
-        Pc = _state["Pc"]
-        cost = kmedoid_costs(P, cur, device, candidates=Pc) if group is None else _sharded_costs(P, cur, device, group, Pc)
+        ses = _state.get("session")
+        if ses is None:         # this rank's share of the points, the candidates and curmin go to the device once
+            if group is None:
+                j0, j1 = 0, P.shape[0]
+            else:
+                import torch.distributed as dist
+                rank, world = dist.get_rank(group), dist.get_world_size(group)
+                j0, j1 = P.shape[0] * rank // world, P.shape[0] * (rank + 1) // world
+            ses = _state["session"] = KMedoidSession(P[j0:j1], cur[j0:j1], _state["Pc"], device)
+        if group is None:
+            cost = ses.costs()
+        else:
+            import torch.distributed as dist
+            t = ses.costs_device()
+            dist.all_reduce(t, group=group)
+            cost = t.cpu().numpy()
         cost = np.where(_state["cand_taken"], np.inf, cost)
         k = int(np.argmin(cost))
         _state["cand_taken"][k] = True
         best = int(cidx[k])
         kappa.append(best)
-        diff = P - P[best]
-        _state["cur"] = np.minimum(cur, np.sqrt((diff * diff).sum(axis=1)))
+        ses.insert(P[best])     # curmin lives on the device (same operation order as _nearest: bit-identical)
         return kappa
     cost = kmedoid_costs(P, cur, device) if group is None else _sharded_costs(P, cur, device, group)
     order = _candidate_order(kappa, ba, P.shape[0]) if _state is None else _state["order"]
@@ -132,8 +145,12 @@ def givemewholelist(kappa, ba, device: int = 0, group=None, limit=None, candidat
         state.update(cand=cidx, Pc=np.ascontiguousarray(P[cidx]), cand_taken=np.isin(cidx, kappa))
         limit = min(limit if limit is not None else len(cidx), len(kappa) + int((~state["cand_taken"]).sum()))
     stop = P.shape[0] if limit is None else min(limit, P.shape[0])
-    while len(kappa) < stop:
-        kappa = insertnewelement(kappa, ba, device, state, group)
+    try:
+        while len(kappa) < stop:
+            kappa = insertnewelement(kappa, ba, device, state, group)
+    finally:
+        if state.get("session") is not None:
+            state["session"].close()
     return kappa
 
 

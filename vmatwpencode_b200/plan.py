@@ -330,3 +330,46 @@ def kmedoid_costs(points, curmin, device: int = 0, candidates=None) -> np.ndarra
     check(lib.vmat_kmedoid_costs_shard(device, Cc.shape[0], _ptr(Cc), P.shape[0], P.shape[1], _ptr(P), _ptr(cm),
                                        _ptr(out)), "vmat_kmedoid_costs_shard")
     return out
+
+
+class KMedoidSession:
+    """Points, candidates and the running nearest-medoid distance resident on the device between insertion steps
+    (vmat_kmedoid_open / _insert / _costs_resident): a step costs one distance pass, not an upload of the point set."""
+
+    def __init__(self, points, curmin, candidates, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p(0)
+        self.device = device
+        P = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, np.shape(candidates)[1])
+        Cc = np.ascontiguousarray(candidates, dtype=np.float64)
+        cm = np.ascontiguousarray(curmin, dtype=np.float64)
+        self.n_cand, self.dim = Cc.shape
+        check(self._lib.vmat_kmedoid_open(C.byref(self._h), device, P.shape[0], self.dim, _ptr(P), _ptr(cm),
+                                          self.n_cand, _ptr(Cc)), "vmat_kmedoid_open")
+
+    def insert(self, medoid):
+        m = np.ascontiguousarray(medoid, dtype=np.float64)
+        check(self._lib.vmat_kmedoid_insert(self._h, _ptr(m)), "vmat_kmedoid_insert")
+
+    def costs(self) -> np.ndarray:
+        out = np.empty(self.n_cand)
+        check(self._lib.vmat_kmedoid_costs_resident(self._h, _ptr(out), None), "vmat_kmedoid_costs_resident")
+        return out
+
+    def costs_device(self):
+        """torch view (float64[n_cand]) of the costs, left on the device (for an all-reduce)."""
+        import torch
+        p = C.c_void_p()
+        check(self._lib.vmat_kmedoid_costs_resident(self._h, None, C.byref(p)), "vmat_kmedoid_costs_resident")
+        return torch.as_tensor(_DeviceArray(p.value, self.n_cand), device=f"cuda:{self.device}")
+
+    def close(self):
+        if self._h.value:
+            self._lib.vmat_kmedoid_close(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
