@@ -352,6 +352,10 @@ def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, h
             trace_us = {n: q(plan.trace_raw[:, i]) for i, n in enumerate(names)}
         else:
             trace_us = dict(k1_done=q(k1t[:, 3]), k2_entry=q(k2t[:, 0]), k2_done=q(k2t[:, 3]))
+            k3t = plan.trace_k3
+            if k3t is not None:      # reduction kernel: start, own partials reduced (and pushed), every rank's values in, done
+                trace_us.update(k3_start=q(k3t[:, 0]), k3_own_partials_pushed=q(k3t[:, 1]), k3_all_ranks_summed=q(k3t[:, 2]),
+                                k3_done=q(k3t[:, 3]))
         barrier()
 
     # ---- check (outside every timed region) ---------------------------------------------------

@@ -133,7 +133,9 @@ int vmat_get_timing(vmat_plan_t* plan, double* ms /* 4 */, int32_t* n);
 /* Diagnostics: run one evaluation (current intensities) with per-CTA time stamps. out receives
  * 8 uint64 per CTA, the dose kernel's CTAs first, then the transposed kernel's: globaltimer ns at
  * [0] kernel entry, [1] inputs staged and predecessor finished, [2] first stage landed,
- * [3] consumers done, [4] producer done. cap = capacity of out in elements. */
+ * [3] consumers done, [4] producer done.  Behind them, one block of 8 per control point (the reduction kernel's
+ * CTAs): [0] predecessor finished, [1] this rank's partials reduced and (multi-GPU) stored into the peers' buffers,
+ * [2] all ranks' values summed, [3] done.  cap = capacity of out in elements. */
 int vmat_trace_eval(vmat_plan_t* plan, uint64_t* out, int64_t cap, int32_t* k1_ctas, int32_t* k2_ctas);
 
 /* Device pointer and element count (B+1 doubles: gb then f) of the buffer a multi-GPU

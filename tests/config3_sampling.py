@@ -42,7 +42,6 @@ def main():
     group = dist.group.WORLD if world > 1 else None
     from vmatwpencode_b200 import VMATlibrary as vl, kmedoids as km
     from vmatwpencode_b200.synth import make_device_config, voxel_coordinates, subsample_device_case
-    from vmatwpencode_b200.plan import kmedoid_costs
 
     def sync():
         torch.cuda.synchronize()
@@ -60,13 +59,15 @@ def main():
     # K6 on one GPU (rank 0, a few insertion steps) for the scaling figure
     single = None
     if rank == 0 and args.single_steps > 0:
+        from vmatwpencode_b200.plan import KMedoidSession
         cur = np.sqrt(((xyz - xyz[start]) ** 2).sum(axis=1))
-        pc = np.ascontiguousarray(xyz[cand])
-        kmedoid_costs(xyz, cur, local, candidates=pc)      # warm-up at full size (module load, clocks)
+        ses = KMedoidSession(xyz, cur, np.ascontiguousarray(xyz[cand]), local)     # the whole point set on one GPU
+        ses.costs()                                                                 # warm-up (module load, clocks)
         t1 = time.perf_counter()
         for _ in range(args.single_steps):
-            kmedoid_costs(xyz, cur, local, candidates=pc)
+            ses.costs()
         single = (time.perf_counter() - t1) / args.single_steps
+        ses.close()
     sync()
 
     t1 = time.perf_counter()

@@ -1006,6 +1006,7 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
     a3.fpart = P->fpart.as<double>(); a3.nfpart = P->nslices1; a3.gbf = P->gbf.as<double>();
     a3.result = P->result.as<double>();
     a3.fblock = P->fblock.as<double>(); a3.nfblock = P->k2_grid;
+    a3.trace = P->tracing ? P->trace.as<unsigned long long>() + ((size_t)P->k1_grid + P->k2_grid) * kTraceSlots : nullptr;
     if (P->comm_nranks > 1 && phase == 0) {
         CommArgs c{};
         c.peer_bufs = P->comm_ptrs.as<double*>(); c.rank = P->comm_rank; c.nranks = P->comm_nranks;
@@ -1208,7 +1209,8 @@ extern "C" int vmat_get_timing(vmat_plan_t* P, double* ms, int32_t* n) {
 
 extern "C" int vmat_trace_eval(vmat_plan_t* P, uint64_t* out, int64_t cap, int32_t* k1_ctas, int32_t* k2_ctas) {
     if (!P || !out || !k1_ctas || !k2_ctas) return fail(VMAT_E_ARG, "null");
-    const size_t n = P->fused ? (size_t)P->gridF * (kTraceSlots + kFTraceItems * 8) : ((size_t)P->k1_grid + (size_t)P->k2_grid) * kTraceSlots;
+    const size_t n = P->fused ? (size_t)P->gridF * (kTraceSlots + kFTraceItems * 8)
+                              : ((size_t)P->k1_grid + (size_t)P->k2_grid + (size_t)P->nb) * kTraceSlots;      // K1, K2, then K3's CTAs
     if (cap < (int64_t)n) return fail(VMAT_E_ARG, "vmat_trace_eval: buffer too small");
     CU(cudaSetDevice(P->device));
     CU(cudaDeviceSynchronize());

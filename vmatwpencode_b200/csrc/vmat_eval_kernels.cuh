@@ -568,6 +568,9 @@ struct K3Args {
     double* host_result;          // [nb+1] or nullptr
     volatile unsigned long long* host_tags;   // [nb+1]
     const unsigned long long* seq;
+    // diagnostics (vmat_trace_eval): per CTA, globaltimer at [0] predecessor finished, [1] this rank's partials reduced
+    // (and stored into the peers' buffers), [2] all ranks' values summed (= every peer's values have arrived), [3] done
+    unsigned long long* trace;
 };
 
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
@@ -615,6 +618,8 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
     pdl_launch_dependents();
     const int lo = a.beam_ptr[blockIdx.x], hi = a.beam_ptr[blockIdx.x + 1];
     pdl_wait();
+    unsigned long long* const trace = a.trace ? a.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
+    if (trace && tid == 0) trace[0] = global_timer_ns();
     // objective (block 0): the per-CTA sums K2 left in fblock, added in index order; the loads are
     // issued before the beamlet loop so that they share its memory round trip
     double fv = 0.0;
@@ -635,6 +640,7 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
         }
         contrib += wg * s;
     }
+    if (trace && tid == 0) trace[1] = trace[2] = global_timer_ns();
     const bool to_host = a.host_result != nullptr && phase == 0;
     unsigned long long seq = 0;
     if (to_host && tid == 0) seq = *a.seq;
@@ -749,6 +755,8 @@ __global__ void __launch_bounds__(256, 4) k3_reduce_exchange(const K3Args<AT> a,
     pdl_launch_dependents();
     const int lo = a.beam_ptr[blockIdx.x], hi = a.beam_ptr[blockIdx.x + 1];
     pdl_wait();
+    unsigned long long* const trace = a.trace ? a.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
+    if (trace && tid == 0) trace[0] = global_timer_ns();
     const int parity = (int)(c.epoch & 1ull);
     const uint32_t ep = (uint32_t)c.epoch;
     // ---- A: this rank's partial for my beamlets (and the objective), stored into every rank's buffer
@@ -765,6 +773,7 @@ __global__ void __launch_bounds__(256, 4) k3_reduce_exchange(const K3Args<AT> a,
         s += __shfl_xor_sync(0xffffffffu, s, 2);       // all four lanes hold the sum: lane q serves ranks q, q+4, ...
         if (j < hi) for (int p = q; p < c.nranks; p += 4) ll_store(c.peer_bufs[p], comm_entry(parity, c.rank, c.nranks, a.B, (size_t)j), s, ep);
     }
+    if (trace) { __syncthreads(); if (tid == 0) trace[1] = global_timer_ns(); }
     // ---- B/C: add the ranks' partials in rank order as they arrive in this rank's own buffer
     double contrib = 0.0;
     int ok = 1;
@@ -777,8 +786,10 @@ __global__ void __launch_bounds__(256, 4) k3_reduce_exchange(const K3Args<AT> a,
     double f = 0.0;
     if (blockIdx.x == 0 && tid == 0 && ok) ok = comm_sum_ranks(c, a.B, (size_t)a.B, f) ? 1 : 0;
     ok = __syncthreads_and(ok);
+    if (trace && tid == 0) trace[2] = global_timer_ns();
     const double g = block_sum_256(contrib, sh);
     if (tid == 0) {
+        if (trace) trace[3] = global_timer_ns();
         a.result[1 + blockIdx.x] = ok ? g : nan("");
         if (blockIdx.x == 0) { a.gbf[a.B] = ok ? f : nan(""); a.result[0] = ok ? f : nan(""); }
         if (!ok) { atomicExch(c.error, 1); *c.status = 1.0; }

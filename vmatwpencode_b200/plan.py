@@ -189,6 +189,10 @@ class DosePlan:
         full = np.where(full > 0, full - t0, -1)
         self.trace_raw = full            # all 8 slots (the fused kernel uses 7: see tools/fused_probe.py)
         t = full[:, :5]
+        self.trace_k3 = None
+        if n2.value > 0:                 # three-kernel path: the reduction kernel's CTAs follow (one per control point)
+            k3 = buf[8 * (n1.value + n2.value): 8 * (n1.value + n2.value + self.nb)].reshape(-1, 8).astype(np.int64)
+            self.trace_k3 = np.where(k3 > 0, k3 - t0, -1)[:, :4]
         return t[:n1.value], t[n1.value:]
 
     def reduce_buffer(self):
