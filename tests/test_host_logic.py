@@ -212,3 +212,32 @@ def test_subsample_case_keeps_rows_and_rescales_weights():
         if kept:
             sel = sub.struct_id == s
             assert np.allclose(sub.over[sel], case.over[rows][sel] * full / kept, rtol=1e-15)
+
+
+def test_lean_lbfgsb_loop_equals_scipy_minimize_bitwise():
+    """VMATlibrary._lbfgsb_lean drives scipy's compiled L-BFGS-B routine with the loop, work arrays and stopping rules
+    of scipy.optimize.minimize(method="L-BFGS-B"): same iterates, objective, iteration and evaluation counts, bit for
+    bit (the greedy loop's aperture sequences depend on it)."""
+    import warnings
+    from scipy.optimize import minimize
+    assert vl._lean_available()
+    rng = np.random.default_rng(3)
+    for n, ftol, maxiter in ((40, 1e-1, 200), (25, 1e-9, 7), (60, 1e-6, 1000)):
+        A = rng.random((n + 20, n))
+        b = rng.random(n + 20) * 5
+
+        def fg(x):
+            r = A @ x - b
+            rp = np.maximum(r, 0)
+            return float((rp ** 3).sum() + (r ** 2).sum()), A.T @ (3 * rp ** 2 + 2 * r)
+
+        up = np.where(rng.random(n) > 0.3, 12.048, 0.0)
+        lo = np.zeros(n)
+        x0 = rng.random(n) * up
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = minimize(fg, x0, method="L-BFGS-B", jac=True, bounds=list(zip(lo, up)),
+                           options={"ftol": ftol, "maxiter": maxiter})
+        got = vl._lbfgsb_lean(fg, x0, lo, up, ftol=ftol, maxiter=maxiter)
+        assert np.array_equal(ref.x, got.x) and ref.fun == got.fun
+        assert (ref.nit, ref.nfev, ref.status) == (got.nit, got.nfev, got.status)
