@@ -651,6 +651,7 @@ __global__ void __launch_bounds__(256) k3_reduce(const K3Args<AT> a, int phase) 
             if (to_host) { a.host_result[1 + blockIdx.x] = g; __threadfence_system(); a.host_tags[1 + blockIdx.x] = seq; }
         }
     }
+    if (trace && tid == 0) trace[3] = global_timer_ns();
     if (blockIdx.x == 0) {
         if (phase == 2) {
             if (tid == 0) a.result[0] = a.gbf[a.B];
