@@ -53,7 +53,8 @@ typedef struct vmat_options {
     int32_t host_path;      /* host-buffer path of vmat_eval, bits: 1 y read from mapped host memory, 2 results +
                                completion tags written to mapped host memory, 4 y inside the launch parameters
                                (default), 8 none (copy nodes)                                                        */
-    int32_t index_bytes;    /* 4 = int32 column indices, 1 = byte deltas (default: uint16 whenever they fit)         */
+    int32_t index_bytes;    /* 4 = int32 column indices, 2 = uint16 whenever they fit, 1 = byte deltas (needs sorted rows);
+                               0 = byte deltas for fp32 storage + fp32 accumulation from 5*10^6 nonzeros on, else as 2  */
     int32_t claim_lead;     /* stages before a super-slice's end at which the dose kernel claims the next            */
     int32_t k2_chunk_cap;   /* chunk cap of the transposed layout (default: 24, less on small slabs)                 */
     int32_t eval_kernels;   /* 0 or 1 = the three kernels K1/K2/K3 chained by programmatic dependent launch
@@ -62,7 +63,9 @@ typedef struct vmat_options {
                                fused kernel k2_tasks is the grid size (default: one CTA per SM)                      */
     int32_t k2_pool_pct;    /* share (percent) of the transposed layout that is not statically partitioned but claimed
                                in small tasks by CTAs that have finished their piece (default 12; -1 = none)          */
-    int32_t reserved[3];
+    int32_t consume_batch;  /* ring stages a consumer warp takes per pass (their barrier tests, loads and gathers in
+                               flight together): 4, 2 or 1; 0 = 2 (four measured no faster)                          */
+    int32_t reserved[2];
 } vmat_options_t;
 
 /* Library / build identification. */
@@ -137,6 +140,14 @@ int vmat_get_timing(vmat_plan_t* plan, double* ms /* 4 */, int32_t* n);
  * CTAs): [0] predecessor finished, [1] this rank's partials reduced and (multi-GPU) stored into the peers' buffers,
  * [2] all ranks' values summed, [3] done.  cap = capacity of out in elements. */
 int vmat_trace_eval(vmat_plan_t* plan, uint64_t* out, int64_t cap, int32_t* k1_ctas, int32_t* k2_ctas);
+
+/* Index guard (diagnostics).  With byte-delta indices (index_bytes 1) a column index is the result of arithmetic on
+ * streamed bytes; a kernel that computes one outside the gathered vector writes a record into pinned host memory and
+ * traps (the call fails with VMAT_E_CUDA) instead of reading wild shared memory.  out[0] != 0: tripped; out[1] kernel
+ * (1 dose, 2 transposed) << 32 | CTA, out[2] thread << 32 | ring slot, out[3] super-slice << 32 | data stage,
+ * out[4] running index on entry << 32 | after the stages, out[5] limit.  Valid after a failed call as well.
+ * (Absolute indices, index_bytes 2 / 4, are range-checked once when the plan is built.)  No reference counterpart. */
+int vmat_guard_status(const vmat_plan_t* plan, uint64_t* out, int32_t nwords);
 
 /* Device pointer and element count (B+1 doubles: gb then f) of the buffer a multi-GPU
  * caller must sum across ranks between phase 1 and phase 2. */

@@ -176,8 +176,9 @@ def test_plan_options_do_not_change_results(opts):
 @pytest.mark.parametrize("store,acc,tol", [("f32", "f64", 1e-11), ("f32", "f32", 1e-5), ("f64", "f64", 1e-11), ("bf16", "f32", 1e-5)])
 def test_byte_delta_indices_bridge_large_gaps(store, acc, tol):
     """index_bytes=1 stores column indices as byte deltas.  A matrix far too sparse for that (70 000
-    beamlets, ~30 nonzeros per voxel row: gaps in the thousands, bridged by several zero entries
-    each; also more beamlets than 16 bits address) still evaluates to the oracle's numbers."""
+    beamlets, ~30 nonzeros per voxel row: gaps in the thousands, each bridged by a zero-valued entry
+    whose delta counts units of 256; also more beamlets than 16 bits address) still evaluates to the
+    oracle's numbers."""
     import scipy.sparse as sp
     rng = np.random.default_rng(21)
     V, nb, per = 3000, 10, 7000
@@ -197,6 +198,14 @@ def test_byte_delta_indices_bridge_large_gaps(store, acc, tol):
         D.data = torch.tensor(D.data, dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
     else:
         D.data = np.float32(D.data).astype(np.float64)
+    # stored zeros (the layout marks bridge entries by a zero value, so real entries that are zero - or become zero
+    # in the storage type - must not move the running index): explicit zeros, also first and last of a row, and
+    # values that underflow to zero in fp32 / bf16 storage
+    zero_at = rng.choice(D.nnz, 3000, replace=False)
+    D.data[zero_at[:2000]] = 0.0
+    D.data[zero_at[2000:2500]] = 1e-60
+    D.data[zero_at[2500:]] = 1e-45       # a float32 denormal: a real entry in fp32 storage, zero in bf16 storage
+    D.data[D.indptr[7]] = 0.0; D.data[D.indptr[8] - 1] = 0.0; D.data[D.indptr[9]:D.indptr[9] + 3] = 0.0
     beam_ptr = np.arange(nb + 1, dtype=np.int32) * per
     thr = rng.random(V); over = rng.random(V) / V; under = rng.random(V) / V
     y = rng.random(nb) * 2
@@ -214,7 +223,48 @@ def test_byte_delta_indices_bridge_large_gaps(store, acc, tol):
     f, g = plan.eval(y)
     assert abs(f - f0) <= tol * abs(f0) and relerr(g, g0) <= tol
     assert relerr(plan.dose(), d0) <= tol and relerr(plan.beamlet_grad(), gb0) <= tol
+    assert plan.guard_status() is None          # no running index ever left the gathered vector
     plan.close()
+
+
+def test_default_index_width_follows_size_precision_and_sortedness():
+    """index_bytes=0: fp32 storage with fp32 accumulation stores byte deltas from 5 M nonzeros on; 8-byte
+    accumulation keeps absolute indices; so does a caller whose voxel-major rows are not sorted (byte deltas
+    need sorted rows, and choosing them was the library's idea) - with the same results."""
+    import torch
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    V, nb, per, L = 52_000, 20, 110, 100
+    B = nb * per
+    first = rng.integers(0, B - 4 * L, V)
+    step = rng.integers(1, 5, V)
+    cols = first[:, None] + step[:, None] * np.arange(L)[None, :]                 # sorted, distinct within a row
+    vals = np.float32(0.05 + rng.random((V, L)))
+    indptr = np.arange(V + 1, dtype=np.int64) * L
+    D = sp.csr_matrix((vals.ravel().astype(np.float64), cols.ravel(), indptr), shape=(V, B))
+    assert D.nnz >= 5_000_000
+    Dc = D.tocsc(); Dc.sort_indices()
+    beam_ptr = np.arange(nb + 1, dtype=np.int32) * per
+    thr = rng.random(V) * 5; over = rng.random(V) / V; under = rng.random(V) / V
+    y = rng.random(nb)
+    w = np.ones(B)
+    dev = lambda a, t: torch.as_tensor(np.ascontiguousarray(a), dtype=t, device="cuda")
+    def parts(c, v):
+        return dict(vrowptr=dev(indptr, torch.int64), vcol=dev(c.ravel(), torch.int32), vval=dev(v.ravel(), torch.float32),
+                    browptr=dev(Dc.indptr, torch.int64), bcol=dev(Dc.indices, torch.int32), bval=dev(Dc.data, torch.float32))
+    out = {}
+    for name, c, v, acc in (("sorted", cols, vals, "f32"), ("reversed", cols[:, ::-1], vals[:, ::-1], "f32"), ("f64", cols, vals, "f64")):
+        plan = DosePlan(parts(c, v), beam_ptr, thr, over, under, store="f32", acc=acc)
+        plan.set_weights(w, w)
+        f, g = plan.eval(y)
+        out[name] = (plan.info()["index_bytes"], f, g.copy(), plan.dose())
+        plan.close()
+    assert out["sorted"][0] == 1 and out["reversed"][0] == 2 and out["f64"][0] == 2
+    for name in ("sorted", "reversed"):
+        assert abs(out[name][1] - out["f64"][1]) <= 1e-5 * abs(out["f64"][1])
+        assert relerr(out[name][2], out["f64"][2]) <= 1e-5 and relerr(out[name][3], out["f64"][3]) <= 1e-5
+    with pytest.raises(_lib.VmatError, match="sorted"):                           # asked for explicitly: an error
+        DosePlan(parts(cols[:, ::-1], vals[:, ::-1]), beam_ptr, thr, over, under, store="f32", acc="f32", index_bytes=1)
 
 
 def test_evaluation_is_bitwise_reproducible_and_apertures_update():

@@ -29,7 +29,7 @@ class Options(C.Structure):
                 ("use_graph", C.c_int32), ("k1_stages", C.c_int32), ("k2_stages", C.c_int32), ("chunk_cap", C.c_int32),
                 ("no_pdl", C.c_int32), ("host_path", C.c_int32), ("index_bytes", C.c_int32), ("claim_lead", C.c_int32),
                 ("k2_chunk_cap", C.c_int32), ("eval_kernels", C.c_int32), ("k2_pool_pct", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("consume_batch", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class PriceRow(C.Structure):
@@ -63,6 +63,7 @@ SIGNATURES = {
     "vmat_set_timing": (C.c_int, [_P, C.c_int]),
     "vmat_get_timing": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "vmat_trace_eval": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vmat_guard_status": (C.c_int, [_P, _P, C.c_int32]),
     "vmat_reduce_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "vmat_comm_handle": (C.c_int, [_P, _P]),
     "vmat_comm_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),

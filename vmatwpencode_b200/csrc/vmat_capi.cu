@@ -75,6 +75,8 @@ struct vmat_plan {
     int32_t max_beamlets = 0;
     bool weights_in_flight = false;    // vmat_set_aperture's copies may still be running on the plan's stream
     double* h_y = nullptr;       // pinned + mapped: K1 reads it directly on the host-buffer path
+    unsigned long long* h_guard = nullptr;   // pinned + mapped: the index guard's record (Guard, vmat_eval_kernels.cuh)
+    unsigned long long* d_guard = nullptr;
     double* h_res = nullptr;     // pinned + mapped: K3 writes results here ...
     unsigned long long* h_tags = nullptr;   // ... each followed by a completion tag the host polls
     double *d_hy = nullptr, *d_hres = nullptr;          // device views of the mapped host buffers
@@ -124,6 +126,7 @@ struct vmat_plan {
         if (h_w) cudaFreeHost(h_w);
         if (h_y) cudaFreeHost(h_y);
         if (h_res) cudaFreeHost(h_res);
+        if (h_guard) cudaFreeHost(h_guard);
         if (h_tags) cudaFreeHost(h_tags);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -221,6 +224,25 @@ static int build_stream(vmat_plan* P, int store_dtype, int src_dtype, int32_t W,
     }); });
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(P->stream));
+    return 0;
+}
+
+// index_bytes = 0: fp32 / fp32 plans with at least this many nonzeros store byte deltas (measured down to 7.3 M
+// nonzeros - a quarter of config 2, both layouts in L2 - where they still gain 1.5 %)
+constexpr int64_t kAutoDeltaNnz = 5000000;
+
+// byte-delta layout: bridge entries each segment needs (k_count_pads), for the plan's storage type
+static int count_pads(vmat_plan* P, int src_dtype, int64_t nseg, const int64_t* d_bounds, const int32_t* d_col,
+                      const void* d_val, int32_t* d_pads) {
+    if (nseg <= 0) return 0;
+    const unsigned blocks = (unsigned)((nseg + 255) / 256);
+    DISPATCH_STORE(P->opt.store_dtype, VT, {
+        if (src_dtype == VMAT_F32)
+            k_count_pads<VT, float><<<blocks, 256, 0, P->stream>>>(nseg, d_bounds, d_col, static_cast<const float*>(d_val), d_pads);
+        else
+            k_count_pads<VT, double><<<blocks, 256, 0, P->stream>>>(nseg, d_bounds, d_col, static_cast<const double*>(d_val), d_pads);
+    });
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -431,13 +453,26 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaDeviceGetAttribute(&P->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaStream_t st = P->stream;
+    bool iw_automatic = false;      // byte deltas chosen by default: given up again if the voxel-major rows are not sorted
+    int iw_absolute = 2;
     {   // index width: uint16 when every stored index fits (x index < B; K2 indices are tile-local, < T)
         const int32_t T0 = P->opt.tile_voxels > 0 ? P->opt.tile_voxels : default_tile_voxels(V, P->acc_size);
         const bool fits16 = B <= 65536 && ((T0 + 63) / 64 * 64) <= 65536;
-        // index_bytes: 4 forces int32 indices, 1 selects byte deltas (any B: a lane's start index is a u32 in the header)
-        P->iw = P->opt.index_bytes == 1 ? 1 : (P->opt.index_bytes == 4 || !fits16) ? 4 : 2;
+        // index_bytes: 4 forces int32 indices, 2 absolute indices (uint16 when they fit), 1 byte deltas (any B: a
+        // lane's start index is a u32 in the header); 0 = byte deltas for fp32 storage with 4-byte accumulation
+        // from kAutoDeltaNnz nonzeros on (5 instead of 6 bytes per nonzero; measured, DESIGN.md section 2: config 2
+        // 63.9 -> 58.7 us, config 3 264.7 -> 230.5 us; bf16 storage and 8-byte accumulation, whose kernels are
+        // bound by the consumers' instruction and shared-memory rates, are slower with them), else absolute
+        const int ib = P->opt.index_bytes;
+        int64_t nnz_peek = 0;
+        CU(cudaMemcpy(&nnz_peek, vrowptr + V, 8, location == VMAT_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+        const bool automatic = ib == 0 && P->acc_size == 4 && (P->opt.eval_kernels & 3) != 2 &&
+                               P->opt.store_dtype == VMAT_F32 && nnz_peek >= kAutoDeltaNnz;
+        iw_absolute = (ib == 4 || !fits16) ? 4 : 2;
+        P->iw = (ib == 1 || automatic) ? 1 : iw_absolute;
+        iw_automatic = automatic;
     }
-    {   // dose-kernel CTA shape
+    auto dose_shape = [&]() {   // dose-kernel CTA shape
         const size_t as0 = P->acc_size;
         const size_t xy = (((size_t)B * as0 + 127) & ~(size_t)127) + (((size_t)nb * 8 + 127) & ~(size_t)127);
         const int hu1 = 8 + 3 * (32 * (int)as0 / 16) + header_base_units(P->iw);
@@ -445,7 +480,8 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const bool fits2 = 2 * (xy + 8 * stage4 + 2048) <= (size_t)P->smem_optin;
         // measured on config 2: one 16-warp CTA per SM (48.8 us) beats three 4-warp CTAs (52.0 us)
         P->W1 = (P->opt.k1_threads > 0 && P->opt.k1_threads < 512 && fits2) ? 4 : 16;
-    }
+    };
+    dose_shape();
 
     // ---- one fused kernel or the three-kernel path --------------------------------------------------
     // eval_kernels & 3: 0 / 1 = the three kernels K1/K2/K3 chained by programmatic dependent launch (default:
@@ -510,14 +546,16 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     std::vector<int32_t> vpads;            // per voxel row (byte-delta layout only)
     CU(csr_flag.alloc(4)); CU(cudaMemsetAsync(csr_flag.p, 0, 4, st));
     auto check_csr = [&](int64_t nrows, int64_t ncols, int sorted, const int64_t* d_rowptr, const int32_t* d_col,
-                         const char* what) -> int {
+                         const char* what, bool* unsorted = nullptr) -> int {
         if (nnz == 0) return 0;
+        CU(cudaMemsetAsync(csr_flag.p, 0, 4, st));
         k_check_csr<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, ncols, sorted, d_rowptr, d_col, csr_flag.as<int>());
         CU(cudaGetLastError());
         int bad = 0;
         CU(cudaMemcpyAsync(&bad, csr_flag.p, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (bad & 1) return fail(VMAT_E_ARG, std::string(what) + " CSR: index out of range");
+        if ((bad & 2) && unsorted) { *unsorted = true; return 0; }
         if (bad & 2) return fail(VMAT_E_ARG, std::string(what) + " CSR: indices must be sorted within a row");
         return 0;
     };
@@ -528,12 +566,16 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             CU(cudaMemcpyAsync(up_vrow.p, vrowptr, (V + 1) * 8, cudaMemcpyHostToDevice, st));
             d_vrow = up_vrow.as<int64_t>();
         }
-        if (int rc = check_csr(V, B, P->iw == 1 ? 1 : 0, d_vrow, d_vcol, "voxel-major")) return rc;
+        bool unsorted = false;
+        if (int rc = check_csr(V, B, P->iw == 1 ? 1 : 0, d_vrow, d_vcol, "voxel-major", iw_automatic ? &unsorted : nullptr)) return rc;
+        if (unsorted) {                    // byte deltas were this library's choice, not the caller's: absolute indices then
+            P->iw = iw_absolute;
+            dose_shape();
+        }
         if (P->iw == 1 && nnz > 0) {      // byte deltas: slots a row needs = nonzeros + bridge entries over gaps > 255
             DevBuf d_pads;
             CU(d_pads.alloc(V * 4));
-            k_count_pads<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, d_vrow, d_vcol, d_pads.as<int32_t>());
-            CU(cudaGetLastError());
+            if (int rc = count_pads(P, src_dtype, V, d_vrow, d_vcol, d_vval, d_pads.as<int32_t>())) return rc;
             vpads.resize(V);
             CU(cudaMemcpyAsync(vpads.data(), d_pads.p, V * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -621,7 +663,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
         const int32_t W = P->fused ? kFW : P->opt.k2_threads >= 512 ? 16 : P->opt.k2_threads >= 256 ? 8 : 4, HU = header_units_k2(P->iw);
         P->W2 = W;
         P->stage_bytes2 = W * std::max<int>(units, HU) * 16;
-        P->nstages2 = P->opt.k2_stages > 0 ? std::max(2, std::min(16, P->opt.k2_stages)) : 8;
+        // ring depth: with byte deltas a stage is 2.5 KB and consumers take four per pass - 12 measured best on configs 2
+        // and 3 (8 / 10 / 12 / 16 stages: 236.2 / 232.1 / 230.5 / 235.0 us on config 3)
+        P->nstages2 = P->opt.k2_stages > 0 ? std::max(2, std::min(16, P->opt.k2_stages)) : (P->iw == 1 ? 12 : 8);
         const size_t tile_bytes = ((size_t)T * P->acc_size + 127) & ~(size_t)127;
         P->k2_smem = tile_bytes + (size_t)P->nstages2 * P->stage_bytes2;
         if (!P->fused && P->k2_smem + 2048 > (size_t)P->smem_optin) return fail(VMAT_E_ARG, "tile_voxels too large for shared memory");
@@ -639,8 +683,7 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
             DevBuf d_pads;
             CU(d_pads.alloc(nseg * 4));
             CU(cudaMemsetAsync(d_pads.p, 0, nseg * 4, st));
-            k_count_pads<<<(unsigned)((nseg - 1 + 255) / 256), 256, 0, st>>>(nseg - 1, d_seg.as<int64_t>(), d_bcol, d_pads.as<int32_t>());
-            CU(cudaGetLastError());
+            if (int rc = count_pads(P, src_dtype, nseg - 1, d_seg.as<int64_t>(), d_bcol, d_bval, d_pads.as<int32_t>())) return rc;
             spads.resize(nseg);
             CU(cudaMemcpyAsync(spads.data(), d_pads.p, nseg * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -832,6 +875,9 @@ extern "C" int vmat_plan_create(vmat_plan_t** out, int device, int64_t V, int64_
     CU(cudaHostGetDevicePointer(&P->d_hy, P->h_y, 0));
     CU(cudaHostGetDevicePointer(&P->d_hres, P->h_res, 0));
     CU(cudaHostGetDevicePointer(&P->d_htags, P->h_tags, 0));
+    CU(cudaHostAlloc(&P->h_guard, kGuardWords * 8, cudaHostAllocMapped));
+    std::memset(P->h_guard, 0, kGuardWords * 8);
+    CU(cudaHostGetDevicePointer(&P->d_guard, P->h_guard, 0));
 
     // K1 launch shape: persistent CTAs of W1 consumer warps + a producer warp; x (and y) staged
     // once per CTA, the rest of the CTA's shared memory is the TMA ring
@@ -895,6 +941,20 @@ extern "C" int vmat_plan_info(const vmat_plan_t* P, int64_t* nnz, int64_t* layou
 // ---------------------------------------------------------------------------------
 // evaluation
 // ---------------------------------------------------------------------------------
+// ring stages a consumer warp takes per pass (their barrier tests, loads and gathers in flight together).  Two by
+// default: four measured the same on configs 2 and 3 (59.5 / 59.0 us and 242.4 / 241.6 us) and, the warp holding
+// them until all have arrived, lost 30 % on a shallow ring (config 3 with 8-byte accumulation, 7 stages)
+static int consume_batch_for(const vmat_plan* P, int nstages, int kernel) {
+    // option: low 4 bits = both kernels, or (tuning) bits 4..7 = the transposed kernel's own value
+    int o = P->opt.consume_batch > 0 ? P->opt.consume_batch : 0;
+    if (kernel == 2 && (o >> 4)) o >>= 4;
+    o &= 15;
+    int b = o > 0 ? o : 2;
+    b = b >= 4 ? 4 : b >= 2 ? 2 : 1;
+    while (b > 1 && b > nstages) b >>= 1;
+    return b;
+}
+
 // the fused path: one launch of kf_eval (phase 0 or 1: everything up to gbf/result, with the exchange when
 // ranks are attached and phase == 0; phase 2 is the aperture gradient from an externally all-reduced gbf)
 template <typename VT, typename AT>
@@ -913,6 +973,7 @@ static int launch_fused_t(vmat_plan* P, cudaStream_t st, int phase, bool inline_
     a.beam_ptr = P->beam_ptr_d.as<int32_t>(); a.w_grad = P->w_grad.as<double>();
     a.gbf = P->gbf.as<double>(); a.result = P->result.as<double>();
     a.claim_lead = P->opt.claim_lead > 0 ? P->opt.claim_lead : kClaimLeadDefault;
+    a.zero = 0u;
     a.dose_only = P->col_mode ? 1 : 0;
     a.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
     if (inline_y) {
@@ -964,6 +1025,9 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a1.claim_lead = P->opt.claim_lead > 0 ? P->opt.claim_lead : kClaimLeadDefault;
         a1.trace = P->tracing ? P->trace.as<unsigned long long>() : nullptr;
         a1.k2_pool_counter = (P->npool2 > 0 && !P->col_mode) ? P->counter.as<unsigned int>() + 2 : nullptr;
+        a1.batch = consume_batch_for(P, P->nstages1, 1);
+        a1.guard = Guard{P->d_guard, (uint32_t)P->B, 1};
+        a1.zero = 0u;
         if (inline_y) {              // the intensities travel in the launch parameters; CTA 0 mirrors them into P->y
             a1.y_mirror = P->y.as<double>();
             a1.y_inline_n = P->nb;
@@ -992,6 +1056,9 @@ static int launch_eval_t(vmat_plan* P, cudaStream_t st, int phase, bool host_mod
         a2.fpart = P->fpart.as<double>(); a2.fblock = P->fblock.as<double>(); a2.nfpart = P->nslices1;
         a2.trace = P->tracing ? P->trace.as<unsigned long long>() + (size_t)P->k1_grid * kTraceSlots : nullptr;
         a2.pool_tasks = P->pool2.as<K2Task>(); a2.npool = P->npool2; a2.pool_counter = P->counter.as<unsigned int>() + 2;
+        a2.batch = consume_batch_for(P, P->nstages2, 2);
+        a2.guard = Guard{P->d_guard, (uint32_t)P->T, 2};
+        a2.zero = 0u;
         DISPATCH_IW(IW, {   // always launched (even with an empty task list): it also folds the objective partials
             DISPATCH_W2(W2c, {
                 auto kern2 = k2_beamlet_grad<VT, AT, W2c, IW>;
@@ -1166,6 +1233,14 @@ extern "C" int vmat_fetch_result(vmat_plan_t* P, double* f, double* g) {
     if (int rc = check_comm(P)) return rc;
     if (f) *f = P->h_res[0];
     if (g) std::memcpy(g, P->h_res + 1, P->nb * 8);
+    return VMAT_OK;
+}
+
+// The index guard's record (all zero while it has not tripped): see Guard / guard_trip in vmat_eval_kernels.cuh.
+// Readable after a failed call too - the record lives in pinned host memory.
+extern "C" int vmat_guard_status(const vmat_plan_t* P, uint64_t* out, int32_t nwords) {
+    if (!P || !out || nwords < 1) return fail(VMAT_E_ARG, "vmat_guard_status: null");
+    for (int32_t k = 0; k < nwords; ++k) out[k] = k < kGuardWords && P->h_guard ? (uint64_t)((volatile unsigned long long*)P->h_guard)[k] : 0;
     return VMAT_OK;
 }
 

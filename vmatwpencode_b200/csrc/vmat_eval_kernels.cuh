@@ -38,10 +38,29 @@ __host__ __device__ constexpr int header_units_k2(int IW) { return 8 + header_ba
 template <typename AT> struct ChunkRegs { uint32_t i[4]; AT v[4]; };
 
 // IW == 1: the index word holds four byte deltas; `cur` is the lane's running index (set from the
-// header's start index, advanced here).  Gaps of 256 or more were bridged with zero-valued entries
-// when the stream was built.
+// header's start index, advanced here).  An entry whose stored value is zero contributes nothing, and
+// its delta counts units of 256: one such entry bridges a gap of up to 65 280 (k_fill_stream puts
+// them in front of every nonzero that is 256 or more away from its predecessor).
 template <typename VT, typename AT, int IW>
 __device__ __forceinline__ void chunk_load(const unsigned char* __restrict__ cp, int lane, ChunkRegs<AT>& c, uint32_t& cur) {
+    const unsigned char* vp = cp + idx_units(IW) * 16;
+    bool z0, z1, z2, z3;                     // stored value is (+-)0 (used by IW == 1 only)
+    if constexpr (sizeof(VT) == 4) {
+        const uint4 r = *reinterpret_cast<const uint4*>(vp + lane * 16);
+        c.v[0] = (AT)__uint_as_float(r.x); c.v[1] = (AT)__uint_as_float(r.y);
+        c.v[2] = (AT)__uint_as_float(r.z); c.v[3] = (AT)__uint_as_float(r.w);
+        z0 = (r.x << 1) == 0u; z1 = (r.y << 1) == 0u; z2 = (r.z << 1) == 0u; z3 = (r.w << 1) == 0u;
+    } else if constexpr (sizeof(VT) == 2) {
+        const uint2 r = *reinterpret_cast<const uint2*>(vp + lane * 8);
+        c.v[0] = (AT)__uint_as_float(r.x << 16); c.v[1] = (AT)__uint_as_float(r.x & 0xffff0000u);
+        c.v[2] = (AT)__uint_as_float(r.y << 16); c.v[3] = (AT)__uint_as_float(r.y & 0xffff0000u);
+        z0 = (r.x & 0x7fffu) == 0u; z1 = (r.x & 0x7fff0000u) == 0u; z2 = (r.y & 0x7fffu) == 0u; z3 = (r.y & 0x7fff0000u) == 0u;
+    } else {
+        const double2 a = *reinterpret_cast<const double2*>(vp + lane * 16);
+        const double2 b = *reinterpret_cast<const double2*>(vp + 512 + lane * 16);
+        c.v[0] = (AT)a.x; c.v[1] = (AT)a.y; c.v[2] = (AT)b.x; c.v[3] = (AT)b.y;
+        z0 = a.x == 0.0; z1 = a.y == 0.0; z2 = b.x == 0.0; z3 = b.y == 0.0;
+    }
     if constexpr (IW == 4) {
         const uint4 idx = *reinterpret_cast<const uint4*>(cp + lane * 16);
         c.i[0] = idx.x; c.i[1] = idx.y; c.i[2] = idx.z; c.i[3] = idx.w;
@@ -50,25 +69,12 @@ __device__ __forceinline__ void chunk_load(const unsigned char* __restrict__ cp,
         c.i[0] = idx.x & 0xffffu; c.i[1] = idx.x >> 16; c.i[2] = idx.y & 0xffffu; c.i[3] = idx.y >> 16;
     } else {
         const uint32_t d = *reinterpret_cast<const uint32_t*>(cp + lane * 4);
-        c.i[0] = cur + (d & 0xffu);
-        c.i[1] = c.i[0] + ((d >> 8) & 0xffu);
-        c.i[2] = c.i[1] + ((d >> 16) & 0xffu);
-        c.i[3] = c.i[2] + (d >> 24);
+        const uint32_t d0 = d & 0xffu, d1 = (d >> 8) & 0xffu, d2 = (d >> 16) & 0xffu, d3 = d >> 24;
+        c.i[0] = cur + (z0 ? d0 << 8 : d0);
+        c.i[1] = c.i[0] + (z1 ? d1 << 8 : d1);
+        c.i[2] = c.i[1] + (z2 ? d2 << 8 : d2);
+        c.i[3] = c.i[2] + (z3 ? d3 << 8 : d3);
         cur = c.i[3];
-    }
-    const unsigned char* vp = cp + idx_units(IW) * 16;
-    if constexpr (sizeof(VT) == 4) {
-        const uint4 r = *reinterpret_cast<const uint4*>(vp + lane * 16);
-        c.v[0] = (AT)__uint_as_float(r.x); c.v[1] = (AT)__uint_as_float(r.y);
-        c.v[2] = (AT)__uint_as_float(r.z); c.v[3] = (AT)__uint_as_float(r.w);
-    } else if constexpr (sizeof(VT) == 2) {
-        const uint2 r = *reinterpret_cast<const uint2*>(vp + lane * 8);
-        c.v[0] = (AT)__uint_as_float(r.x << 16); c.v[1] = (AT)__uint_as_float(r.x & 0xffff0000u);
-        c.v[2] = (AT)__uint_as_float(r.y << 16); c.v[3] = (AT)__uint_as_float(r.y & 0xffff0000u);
-    } else {
-        const double2 a = *reinterpret_cast<const double2*>(vp + lane * 16);
-        const double2 b = *reinterpret_cast<const double2*>(vp + 512 + lane * 16);
-        c.v[0] = (AT)a.x; c.v[1] = (AT)a.y; c.v[2] = (AT)b.x; c.v[3] = (AT)b.y;
     }
 }
 
@@ -94,41 +100,110 @@ __device__ __forceinline__ void ring_push(unsigned char* ring, int stage_bytes, 
     pos.advance(nstages);
 }
 
-// consumer side, data stage at `pos`: acc += this warp's chunk . gathered vector.  When the stage is
-// not the last of its super-slice the next stage is data of the same super-slice too: both are
-// taken in one pass (two sets of shared-memory loads and gathers in flight, one round of barrier
-// traffic per two chunks).  The row sum order is unchanged.  On return `pos`/`info` describe the
-// last stage consumed (the caller advances past it).
-template <typename VT, typename AT, int IW, typename Gather>
-__device__ __forceinline__ void consume_data(const unsigned char* ring, int SB, int warp_off, uint64_t* full,
-                                             uint64_t* empty, const StageInfo* sinfo, RingPos& pos, int nst,
-                                             StageInfo& info, int lane, AT& acc, uint32_t& cur, Gather g) {
-    ChunkRegs<AT> A;
-    chunk_load<VT, AT, IW>(ring + (size_t)pos.stage * SB + warp_off, lane, A, cur);
-    if (info.flags & kStageLast) {
-        AT x0 = g(A.i[0]), x1 = g(A.i[1]), x2 = g(A.i[2]), x3 = g(A.i[3]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[pos.stage]);
-        acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
-        acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
-        return;
+// mbarrier.try_wait once (it suspends the thread for a hardware-defined time; the answer takes ~90 cycles even
+// when the phase is complete, so several are issued back to back before any is looked at)
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+
+// Index guard of the byte-delta layout (IW == 1), where an index is the result of arithmetic on streamed bytes: a
+// running index past the gathered vector means the stream, or the synchronisation around the ring, is broken.  The
+// thread that sees one writes a record into pinned host memory (it survives the context) and traps; the host
+// reports it (vmat_guard_status).  Absolute indices (IW 2 / 4) are range-checked when the plan is built.
+constexpr int kGuardWords = 8;
+struct Guard {
+    unsigned long long* host;     // [kGuardWords] mapped pinned host memory; word 0 != 0: tripped
+    uint32_t limit;               // valid indices are < limit
+    int32_t kernel;               // 1 = dose kernel, 2 = transposed kernel
+};
+__device__ __forceinline__ void guard_check(const Guard& gd, uint32_t cur_in, uint32_t cur, int ss, int c, int slot) {
+    if (cur >= gd.limit) {        // indices only grow along a lane: the last one bounds them all
+        volatile unsigned long long* h = gd.host;
+        h[1] = ((unsigned long long)(uint32_t)gd.kernel << 32) | blockIdx.x;
+        h[2] = ((unsigned long long)threadIdx.x << 32) | (uint32_t)slot;
+        h[3] = ((unsigned long long)(uint32_t)ss << 32) | (uint32_t)c;
+        h[4] = ((unsigned long long)cur_in << 32) | cur;
+        h[5] = gd.limit;
+        __threadfence_system();
+        h[0] = 0x6775617264ull;   // "guard"
+        __threadfence_system();
+        __trap();
     }
-    RingPos nx = pos;
-    nx.advance(nst);
-    mbar_wait(&full[nx.stage], nx.phase);
-    const StageInfo info2 = sinfo[nx.stage];
-    ChunkRegs<AT> Bc;
-    chunk_load<VT, AT, IW>(ring + (size_t)nx.stage * SB + warp_off, lane, Bc, cur);
-    AT x0 = g(A.i[0]), x1 = g(A.i[1]), x2 = g(A.i[2]), x3 = g(A.i[3]);
-    AT y0 = g(Bc.i[0]), y1 = g(Bc.i[1]), y2 = g(Bc.i[2]), y3 = g(Bc.i[3]);
+}
+
+// Release of a ring stage (or of anything else the producer refills).  SYNCS.ARRIVE does not wait for shared-memory
+// loads that are still in flight - ptxas gives it no dependency on them - so a load whose result is not needed
+// before the arrive can execute after the producer has refilled the slot (seen on config 4 with byte deltas, where
+// the producer is always waiting: a header word read after the refill, then a wild gather).  `dep` is any value
+// computed from every such load, `zero` a kernel argument that is 0: the address then depends on the loads.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep, uint32_t zero) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar) + (dep & zero)) : "memory");
+}
+__device__ __forceinline__ uint32_t dep_bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t dep_bits(double v) { return (uint32_t)__double2loint(v) ^ (uint32_t)__double2hiint(v); }
+
+// consumer side: U data stages starting at `pos` (all of one super-slice): acc += this warp's chunks . gathered
+// vector, in chunk order.  The U barrier tests, the U sets of shared-memory loads and the 4U gathers are in
+// flight together; the stages go back to the producer with one warp synchronisation.  `pos` ends past them.
+template <typename VT, typename AT, int IW, int U, typename Gather>
+__device__ __forceinline__ void consume_stages(const unsigned char* ring, int SB, int warp_off, uint64_t* full,
+                                               uint64_t* empty, RingPos& pos, int nst, int lane, AT& acc,
+                                               uint32_t& cur, Gather g, const Guard& gd, uint32_t zero, int ss, int c) {
+    int st[U];
+    bool ok[U];
+    uint32_t ph[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { st[u] = pos.stage; ph[u] = pos.phase; pos.advance(nst); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) ok[u] = mbar_try(&full[st[u]], ph[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (!ok[u]) mbar_wait(&full[st[u]], ph[u]);
+    ChunkRegs<AT> R[U];
+    const uint32_t cur_in = cur;
+#pragma unroll
+    for (int u = 0; u < U; ++u) chunk_load<VT, AT, IW>(ring + (size_t)st[u] * SB + warp_off, lane, R[u], cur);
+    if constexpr (IW == 1) guard_check(gd, cur_in, cur, ss, c, st[0]);
+    AT x[U][4];
+    uint32_t dep = 0;             // every load from the ring: the indices feed the gathers, the values feed `dep`
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[u][k] = g(R[u].i[k]);
+        dep |= dep_bits(R[u].v[0]) | dep_bits(R[u].v[3]);
+    }
     __syncwarp();
-    if (lane == 0) { mbar_arrive(&empty[pos.stage]); mbar_arrive(&empty[nx.stage]); }
-    acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
-    acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
-    acc = fma_acc(Bc.v[0], y0, acc); acc = fma_acc(Bc.v[1], y1, acc);
-    acc = fma_acc(Bc.v[2], y2, acc); acc = fma_acc(Bc.v[3], y3, acc);
-    pos = nx;
-    info = info2;
+    if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) mbar_arrive_after(&empty[st[u]], dep, zero);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc = fma_acc(R[u].v[k], x[u][k], acc);
+    }
+}
+
+// the nch data stages of a super-slice, `batch` (4, 2 or 1) at a time, then two, then one.  The consumers hold a
+// batch until all of its stages have arrived, so the batch may not exceed the ring depth - and on a shallow ring
+// a large batch leaves the producer too few free stages (the host picks it, consume_batch_for).  The row sum order
+// is the chunk order whatever the grouping.
+template <typename VT, typename AT, int IW, typename Gather>
+__device__ __forceinline__ void consume_run(const unsigned char* ring, int SB, int warp_off, uint64_t* full,
+                                            uint64_t* empty, RingPos& pos, int nst, int nch, int lane, AT& acc,
+                                            uint32_t& cur, Gather g, int batch, const Guard& gd, uint32_t zero, int ss) {
+    int c = 0;
+    if (batch >= 4)
+        for (; c + 4 <= nch; c += 4) consume_stages<VT, AT, IW, 4>(ring, SB, warp_off, full, empty, pos, nst, lane, acc, cur, g, gd, zero, ss, c);
+    if (batch >= 2)
+        for (; c + 2 <= nch; c += 2) consume_stages<VT, AT, IW, 2>(ring, SB, warp_off, full, empty, pos, nst, lane, acc, cur, g, gd, zero, ss, c);
+    for (; c < nch; ++c) consume_stages<VT, AT, IW, 1>(ring, SB, warp_off, full, empty, pos, nst, lane, acc, cur, g, gd, zero, ss, c);
 }
 
 // ---------------------------------------------------------------------------------
@@ -182,6 +257,9 @@ struct K1Args {
     unsigned long long* trace;
     int32_t claim_lead;           // stages before the end of a super-slice at which the next one is claimed
     unsigned int* k2_pool_counter; // the transposed kernel's dynamic-tail counter, reset here for this evaluation (or nullptr)
+    int32_t batch;                // ring stages a consumer warp takes per pass (1, 2 or 4; at most the ring depth)
+    Guard guard;                  // index guard of the byte-delta layout
+    uint32_t zero;                // 0 (mbar_arrive_after)
 };
 
 // four consecutive elements with one (float) or two (double) 16-byte loads
@@ -302,7 +380,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
                 bool claimed = false, loaded = false;
                 const int c_claim = max(0, nch - lead), c_load = min(c_claim + 4, max(0, nch - 1));
                 ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                          StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0), 0, tpr},
+                          StageInfo{(int32_t)cur, kStageHeader | (nch == 0 ? kStageLast : 0) | (nch << 8), 0, tpr},
                           a.sell + o0, W * HU * 16, pol);
                 const uint4* data = a.sell + o0 + W * HU;
                 for (int c = 0; c < nch; ++c) {
@@ -339,10 +417,11 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
     uint32_t cur = 0;
     if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }    // outside the hot loop
     while (true) {
+        // a super-slice: its header stage (which says how many data stages follow), the data stages, the epilogue
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
-        StageInfo info = sinfo[pos.stage];
+        const StageInfo info = sinfo[pos.stage];
         if (info.ss < 0) break;
-        if (info.flags & kStageHeader) {
+        {
             const unsigned char* hp = ring + (size_t)pos.stage * SB + warp * (HU * 16);
             row = reinterpret_cast<const int32_t*>(hp)[lane];
             t  = reinterpret_cast<const AT*>(hp + 128)[lane];
@@ -351,11 +430,12 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
             if constexpr (IW == 1) cur = reinterpret_cast<const uint32_t*>(hp + (HU - 8) * 16)[lane];
             acc = (AT)0;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[pos.stage]);
-        } else {
-            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, cur, gather);
+            // the slot goes back only when the header words have arrived in registers (mbar_arrive_after)
+            if (lane == 0) mbar_arrive_after(&empty[pos.stage], (uint32_t)row | cur | dep_bits(t) | dep_bits(ov) | dep_bits(un), a.zero);
+            pos.advance(nst);
         }
-        if (info.flags & kStageLast) {
+        consume_run<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, pos, nst, info.flags >> 8, lane, acc, cur, gather, a.batch, a.guard, a.zero, info.ss);
+        {
             for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // tpr lanes of a row
             double fterm = 0.0;
             if (row >= 0) {
@@ -373,7 +453,6 @@ __global__ void __launch_bounds__((W + 1) * 32) k1_dose_penalty(const __grid_con
             fterm = warp_sum(fterm);      // butterfly: same value and order in every lane, every run
             if (lane == 0) a.fpart[(int64_t)info.ss * W + warp] = fterm;
         }
-        pos.advance(nst);
     }
     if (trace && tid == 0) trace[3] = global_timer_ns();
 }
@@ -410,6 +489,9 @@ struct K2Args {
     const K2Task* pool_tasks;     // [npool], ordered by tile
     int32_t npool;
     unsigned int* pool_counter;   // reset by the dose kernel of the same evaluation
+    int32_t batch;                // ring stages a consumer warp takes per pass (1, 2 or 4; at most the ring depth)
+    Guard guard;                  // index guard of the byte-delta layout
+    uint32_t zero;                // 0 (mbar_arrive_after)
 };
 
 template <typename VT, typename AT, int W, int IW>
@@ -457,7 +539,7 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
                     const int nch = (int)((o1 - o0 - W * HU) / (W * KU));
                     const int tpr = a.ss_tpr[ss];
                     ring_push(ring, SB, full, empty, sinfo, pos, nst,
-                              StageInfo{ss, kStageHeader | (nch == 0 ? kStageLast : 0), task.tile, tpr},
+                              StageInfo{ss, kStageHeader | (nch == 0 ? kStageLast : 0) | (nch << 8), task.tile, tpr},
                               a.sell + o0, W * HU * 16, pol);
                     const uint4* data = a.sell + o0 + W * HU;
                     for (int c = 0; c < nch; ++c)
@@ -505,10 +587,11 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
     uint32_t tparity = 0;
     if (trace) { mbar_wait(&full[0], 0); if (tid == 0) trace[2] = global_timer_ns(); }    // outside the hot loop
     while (true) {
+        // a super-slice: its header stage (which says how many data stages follow), the data stages, the store
         mbar_wait(&full[pos.stage], pos.phase);      // every lane polls: a single polling lane + __syncwarp measured 2.5x slower
-        StageInfo info = sinfo[pos.stage];
+        const StageInfo info = sinfo[pos.stage];
         if (info.ss < 0) break;
-        if (info.flags & kStageHeader) {
+        {
             const unsigned char* sp = ring + (size_t)pos.stage * SB;
             if (info.tile != cur_tile) {
                 named_bar_sync(1, W * 32);            // all consumers are done with the previous tile
@@ -532,15 +615,13 @@ __global__ void __launch_bounds__((W + 1) * 32) k2_beamlet_grad(const K2Args<AT>
             if constexpr (IW == 1) cur = reinterpret_cast<const uint32_t*>(sp + warp * (HU * 16) + (HU - 8) * 16)[lane];
             acc = (AT)0;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[pos.stage]);
-        } else {
-            consume_data<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, sinfo, pos, nst, info, lane, acc, cur, gather);
+            // the slot goes back only when the header words have arrived in registers (mbar_arrive_after)
+            if (lane == 0) mbar_arrive_after(&empty[pos.stage], (uint32_t)row | cur, a.zero);
+            pos.advance(nst);
         }
-        if (info.flags & kStageLast) {
-            for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (row >= 0) a.partial[(int64_t)cur_tile * a.B + row] = acc;
-        }
-        pos.advance(nst);
+        consume_run<VT, AT, IW>(ring, SB, warp * (KU * 16), full, empty, pos, nst, info.flags >> 8, lane, acc, cur, gather, a.batch, a.guard, a.zero, info.ss);
+        for (int o = 1; o < info.tpr; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (row >= 0) a.partial[(int64_t)cur_tile * a.B + row] = acc;
     }
     if (trace && tid == 0) trace[3] = global_timer_ns();
 }
@@ -817,17 +898,33 @@ __global__ void k_check_csr(int64_t nrows, int64_t ncols, int sorted, const int6
     if (bad) atomicOr(flag, bad);
 }
 
-// byte-delta layout: bridge entries a segment needs (one per 255 of every index gap above 255);
-// segment k spans CSR positions bounds[k*stride] .. bounds[k*stride + 1] (stride 1 = plain rows)
+template <typename T> struct StoreCvt;
+template <> struct StoreCvt<float>  { template <typename S> __device__ static float  cvt(S v) { return (float)v; } };
+template <> struct StoreCvt<double> { template <typename S> __device__ static double cvt(S v) { return (double)v; } };
+template <> struct StoreCvt<__nv_bfloat16> {
+    template <typename S> __device__ static __nv_bfloat16 cvt(S v) { return __float2bfloat16_rn((float)v); }
+};
+template <typename VT> __device__ __forceinline__ bool stored_zero(VT v) { return (float)v == 0.0f; }
+template <> __device__ __forceinline__ bool stored_zero<double>(double v) { return v == 0.0; }
+
+// byte-delta layout: a nonzero `gap` (>= 0) away from its predecessor is reached by entries of value 0 whose
+// delta counts units of 256 (at most 255 of them each), then its own delta gap & 255
+__host__ __device__ __forceinline__ int32_t bridge_entries(int32_t gap) { return ((gap >> 8) + 254) / 255; }
+
+// byte-delta layout: bridge entries a segment needs.  Entries whose STORED value is zero stay where the running
+// index is (delta 0; the decoder would scale their delta), so gaps are measured between the entries that remain
+// nonzero after conversion to the storage type.  Segment k spans CSR positions bounds[k] .. bounds[k + 1].
+template <typename VT, typename ST>
 __global__ void k_count_pads(int64_t nseg, const int64_t* __restrict__ bounds, const int32_t* __restrict__ col,
-                             int32_t* __restrict__ pads) {
+                             const ST* __restrict__ val, int32_t* __restrict__ pads) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nseg) return;
     const int64_t p0 = bounds[k], p1 = bounds[k + 1];
-    int32_t n = 0;
+    int32_t n = 0, idx = p0 < p1 ? col[p0] : 0;
     for (int64_t p = p0 + 1; p < p1; ++p) {
-        const int32_t gap = col[p] - col[p - 1];
-        if (gap > 255) n += (gap - 1) / 255;
+        if (stored_zero<VT>(StoreCvt<VT>::cvt(val[p]))) continue;
+        n += bridge_entries(col[p] - idx);
+        idx = col[p];
     }
     pads[k] = n;
 }
@@ -848,12 +945,6 @@ __global__ void k_segment_bounds(int32_t B, int32_t ntiles, int32_t T, const int
     segstart[gid] = lo;
 }
 
-template <typename T> struct StoreCvt;
-template <> struct StoreCvt<float>  { template <typename S> __device__ static float  cvt(S v) { return (float)v; } };
-template <> struct StoreCvt<double> { template <typename S> __device__ static double cvt(S v) { return (double)v; } };
-template <> struct StoreCvt<__nv_bfloat16> {
-    template <typename S> __device__ static __nv_bfloat16 cvt(S v) { return __float2bfloat16_rn((float)v); }
-};
 
 // one warp per slice s = ss*W + w: writes the warp's part of the super-slice header (row ids and,
 // when `tables` is set, thr/over/under of elem size `es`) and copies the lane's segment (CSR
@@ -892,38 +983,40 @@ __global__ void k_fill_stream(int32_t nslices, int32_t W, int32_t HU, const int6
     const int tpr = ss_tpr[ss], part = lane % tpr;
     uint4* data = sell + off + (int64_t)W * HU;
     if constexpr (IW == 1) {
-        // Byte-delta indices.  The row is first expanded: a gap of 256 or more to the previous
-        // index is bridged by zero-valued entries 255 apart (k_count_pads sized the row for them).
-        // Lane `part` of the row then owns the expanded entries [part*4*nch, (part+1)*4*nch): a
-        // contiguous block, so in-lane deltas are plain neighbour gaps; its first entry's index goes
-        // into the header, its delta is 0.  Entries past the row's end repeat the last index with value 0.
+        // Byte-delta indices.  The row is first expanded: in front of a nonzero that is 256 or more past its
+        // predecessor go bridge entries (value 0, delta in units of 256, k_count_pads sized the row for them);
+        // entries whose stored value is zero keep the running index (delta 0).  Lane `part` of the row then
+        // owns the expanded entries [part*4*nch, (part+1)*4*nch): a contiguous block; the running index at its
+        // first entry goes into the header, that entry's delta is 0.  Entries past the row's end: delta 0, value 0.
         const int64_t first = (int64_t)part * 4 * nch, last = first + (int64_t)4 * nch;
         int32_t e = 0;                               // next source element
-        int32_t pads_left = 0;                       // bridge entries still to emit before element e
-        int32_t idx = 0;                             // index of the entry emitted last
-        uint32_t base = 0, prev = 0, word = 0;
+        int32_t jump_left = 0;                       // units of 256 still to bridge before element e
+        int32_t idx = 0;                             // running index after the entry emitted last
+        uint32_t base = 0, word = 0;
         VT vv[4];
         for (int64_t s = 0; s < last; ++s) {
             VT v = StoreCvt<VT>::cvt(0.0f);
+            uint32_t dbyte = 0;
             if (e < len) {
-                if (pads_left > 0) { idx += 255; --pads_left; }
-                else {
-                    idx = col[st + e] - cb;
-                    v = StoreCvt<VT>::cvt(val[st + e]);
+                if (jump_left > 0) {
+                    const int32_t piece = jump_left < 255 ? jump_left : 255;
+                    dbyte = (uint32_t)piece; idx += piece << 8; jump_left -= piece;
+                } else {
+                    const VT sv = StoreCvt<VT>::cvt(val[st + e]);
+                    const int32_t c = col[st + e] - cb;
+                    if (e == 0) idx = c;
+                    if (!stored_zero<VT>(sv)) { dbyte = (uint32_t)(c - idx); idx = c; v = sv; }
                     ++e;
-                    if (e < len) {
-                        const int32_t gap = (col[st + e] - cb) - idx;
-                        pads_left = gap > 255 ? (gap - 1) / 255 : 0;
-                    }
+                    if (e < len && !stored_zero<VT>(StoreCvt<VT>::cvt(val[st + e])))
+                        jump_left = ((col[st + e] - cb) - idx) >> 8;
                 }
-            }                                         // past the end: the last index again, value 0
+            }
             if (s < first) continue;
             const int k = (int)((s - first) & 3);
-            if (s == first) { base = (uint32_t)idx; prev = base; }
+            if (s == first) { base = (uint32_t)idx; dbyte = 0; }
             if (k == 0) word = 0;
-            word |= ((uint32_t)idx - prev) << (8 * k);
+            word |= dbyte << (8 * k);
             vv[k] = v;
-            prev = (uint32_t)idx;
             if (k == 3) {
                 uint4* chunk = data + ((s - first) >> 2) * W * KU + (int64_t)w * KU;
                 reinterpret_cast<uint32_t*>(chunk)[lane] = word;

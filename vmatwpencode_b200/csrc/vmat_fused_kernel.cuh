@@ -90,6 +90,7 @@ struct FArgs {
     double* y_mirror;                    // host-buffer path: y is mirrored into the device copy by CTA 0
     int32_t y_inline_n;
     int32_t claim_lead;
+    uint32_t zero;                // 0 (mbar_arrive_after)
     int32_t dose_only;                   // 1: dose items only, no reductions (RMP column build)
     unsigned long long* trace;           // [gridDim.x * kTraceSlots] or nullptr
     double y_inline[kInlineY];
@@ -468,7 +469,8 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                     mbar_wait(&tile_full[tbuf], (uint32_t)(tb2 >> 1));      // every warp, also one without chunks (see the producer)
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[pos.stage]);
+                // the slot goes back only when the header words have arrived in registers (mbar_arrive_after)
+                if (lane == 0) mbar_arrive_after(&empty[pos.stage], dose ? ((uint32_t)row | dep_bits(t) | dep_bits(ov) | dep_bits(un)) : (uint32_t)row, a.zero);
                 if (its) its[5] = global_timer_ns();
                 finished = my_nch == 0;
             } else if (warp < s_kact) {
@@ -490,7 +492,10 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                         y0 = vt[Bc.i[0]]; y1 = vt[Bc.i[1]]; y2 = vt[Bc.i[2]]; y3 = vt[Bc.i[3]];
                     }
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(&empty[pos.stage]); mbar_arrive(&empty[nx.stage]); }
+                    if (lane == 0) {
+                        const uint32_t dep = dep_bits(A.v[0]) | dep_bits(A.v[3]) | dep_bits(Bc.v[0]) | dep_bits(Bc.v[3]);
+                        mbar_arrive_after(&empty[pos.stage], dep, a.zero); mbar_arrive_after(&empty[nx.stage], dep, a.zero);
+                    }
                     acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
                     acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
                     acc = fma_acc(Bc.v[0], y0, acc); acc = fma_acc(Bc.v[1], y1, acc);
@@ -502,7 +507,7 @@ __global__ void __launch_bounds__(kFThreads) kf_eval(const __grid_constant__ FAr
                     if (dose) { x0 = xs[A.i[0]]; x1 = xs[A.i[1]]; x2 = xs[A.i[2]]; x3 = xs[A.i[3]]; }
                     else      { x0 = vt[A.i[0]]; x1 = vt[A.i[1]]; x2 = vt[A.i[2]]; x3 = vt[A.i[3]]; }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[pos.stage]);
+                    if (lane == 0) mbar_arrive_after(&empty[pos.stage], dep_bits(A.v[0]) | dep_bits(A.v[3]), a.zero);
                     acc = fma_acc(A.v[0], x0, acc); acc = fma_acc(A.v[1], x1, acc);
                     acc = fma_acc(A.v[2], x2, acc); acc = fma_acc(A.v[3], x3, acc);
                     cdone += 1;

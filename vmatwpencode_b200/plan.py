@@ -40,7 +40,7 @@ class DosePlan:
                  tile_voxels: int = 0, k1_threads: int = 0, k2_threads: int = 0, k2_tasks: int = 0,
                  use_graph: bool = True, Dt=None, chunk_cap: int = 0, pdl: bool = True, host_path: int = 0,
                  index_bytes: int = 0, k1_stages: int = 0, k2_stages: int = 0, claim_lead: int = 0,
-                 k2_chunk_cap: int = 0, fused: int = 0, k2_pool_pct: int = 0):
+                 k2_chunk_cap: int = 0, fused: int = 0, k2_pool_pct: int = 0, consume_batch: int = 0):
         """`D` is a scipy.sparse matrix (V x B, any format) or a dict of CUDA torch tensors
         {vrowptr, vcol, vval, browptr, bcol, bval} (int64 / int32 / float32|float64)."""
         lib = _lib.load()
@@ -61,9 +61,10 @@ class DosePlan:
         opt.no_pdl = 0 if pdl else 1
         opt.host_path = host_path
         opt.claim_lead = claim_lead            # dose kernel: stages before a super-slice's end at which the next is claimed
-        opt.index_bytes = index_bytes          # 4 forces int32 column indices, 1 byte deltas; 0 = uint16 whenever they fit
+        opt.index_bytes = index_bytes          # 4 int32 column indices, 2 uint16 whenever they fit, 1 byte deltas; 0 = byte deltas for fp32/fp32 plans of 5M nonzeros and more, else as 2
         opt.eval_kernels = fused               # 0 / 1 = the three kernels K1/K2/K3 (default), 2 = the single fused evaluation kernel
         opt.k2_pool_pct = k2_pool_pct          # transposed kernel: percent of the work claimed dynamically at the end (0 = default, -1 = none)
+        opt.consume_batch = consume_batch      # ring stages a consumer warp takes per pass (0 = default: 2)
         self.store, self.acc = store, acc
         thr = np.ascontiguousarray(thr, dtype=np.float64)
         over = np.ascontiguousarray(over, dtype=np.float64)
@@ -163,6 +164,18 @@ class DosePlan:
 
     def sync(self):
         check(self._lib.vmat_sync(self._h), "vmat_sync")
+
+    def guard_status(self):
+        """The index guard's record (vmat_guard_status): None while it has not tripped, else a dict.  Readable
+        after a failed evaluation too (the record lives in pinned host memory)."""
+        w = np.zeros(8, dtype=np.uint64)
+        check(self._lib.vmat_guard_status(self._h, _ptr(w), len(w)), "vmat_guard_status")
+        if not w[0]:
+            return None
+        hi = lambda k: int(w[k]) >> 32
+        lo = lambda k: int(w[k]) & 0xffffffff
+        return dict(kernel={1: "k1_dose_penalty", 2: "k2_beamlet_grad"}.get(hi(1), hi(1)), cta=lo(1), thread=hi(2), ring_slot=lo(2),
+                    super_slice=hi(3), data_stage=lo(3), index_on_entry=hi(4), index_after=lo(4), limit=lo(5))
 
     def set_timing(self, enable: bool = True):
         check(self._lib.vmat_set_timing(self._h, 1 if enable else 0), "vmat_set_timing")
