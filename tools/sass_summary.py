@@ -12,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "vmatwpencode_b200", "libvmat_b200.so")
-WANT = [r"k1_dose_penalty<float, float, true, 16, 2>", r"k2_beamlet_grad<float, float, 4, 2>", r"k3_reduce<float>",
+WANT = [r"k1_dose_penalty<float, float, true, 16, 1>", r"k2_beamlet_grad<float, float, 4, 1>",      # byte deltas: the default from 5 M nonzeros on
+        r"k1_dose_penalty<float, float, true, 16, 2>", r"k2_beamlet_grad<float, float, 4, 2>", r"k3_reduce<float>",
         r"k3_reduce_exchange<float>", r"kf_eval<float, float, 2>", r"k1_dose_penalty<float, double, true, 16, 2>",
         r"k2_beamlet_grad<float, double, 4, 2>", r"k5_price_dp", r"k6_kmedoid_cost_tiled<3>"]
 GROUPS = [("UBLKCP (cp.async.bulk, TMA)", r"\bUBLKCP"), ("UTMALDG (tensor-map TMA)", r"\bUTMALDG"),
