@@ -64,7 +64,8 @@ typedef struct vmat_options {
     int32_t k2_pool_pct;    /* share (percent) of the transposed layout that is not statically partitioned but claimed
                                in small tasks by CTAs that have finished their piece (default 12; -1 = none)          */
     int32_t consume_batch;  /* ring stages a consumer warp takes per pass (their barrier tests, loads and gathers in
-                               flight together): 4, 2 or 1; 0 = 2 (four measured no faster)                          */
+                               flight together): 4, 2 or 1; 0 = 2 (four measured no faster); tuning: bits 4..7, when
+                               set, are the transposed kernel's own value                                            */
     int32_t reserved[2];
 } vmat_options_t;
 

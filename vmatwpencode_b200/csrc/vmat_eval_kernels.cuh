@@ -95,6 +95,7 @@ __device__ __forceinline__ void ring_push(unsigned char* ring, int stage_bytes, 
         mbar_expect_tx(&full[pos.stage], bytes);
         tma_bulk_g2s_hint(ring + (size_t)pos.stage * stage_bytes, src, bytes, &full[pos.stage], policy);
     } else {
+        __threadfence_block();        // the descriptor store is performed before the arrive that publishes it (no copy, no latency, in between)
         mbar_arrive(&full[pos.stage]);
     }
     pos.advance(nstages);

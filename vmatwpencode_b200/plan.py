@@ -142,12 +142,28 @@ class DosePlan:
             self.set_aperture(i, w_dose[lo:hi], w_grad[lo:hi])
 
     # -- evaluation -----------------------------------------------------------------
+    def _check(self, rc, what):
+        """check() for the calls that run the evaluation kernels: a failure caused by the index guard carries its record."""
+        if rc == 0:
+            return
+        try:
+            check(rc, what)
+        except VmatError as e:
+            guard = None
+            try:
+                guard = self.guard_status()
+            except VmatError:
+                pass
+            if guard:
+                raise VmatError(f"{e}; index guard: {guard}") from None
+            raise
+
     def eval(self, y):
         """(f, g[nb]) for intensities y[nb]: host buffers in, host buffers out."""
         self._y[:] = y
         rc = self._lib.vmat_eval(*self._eval_args)
         if rc:
-            check(rc, "vmat_eval")
+            self._check(rc, "vmat_eval")
         return self._f.value, self._g.copy()
 
     def set_intensities(self, y):
@@ -155,15 +171,15 @@ class DosePlan:
         check(self._lib.vmat_set_intensities(self._h, _ptr(self._y)), "vmat_set_intensities")
 
     def eval_async(self, stream: Optional[int] = None, phase: int = 0):
-        check(self._lib.vmat_eval_async(self._h, C.c_void_p(stream or 0), phase), "vmat_eval_async")
+        self._check(self._lib.vmat_eval_async(self._h, C.c_void_p(stream or 0), phase), "vmat_eval_async")
 
     def fetch_result(self):
         f = C.c_double()
-        check(self._lib.vmat_fetch_result(self._h, C.byref(f), _ptr(self._g)), "vmat_fetch_result")
+        self._check(self._lib.vmat_fetch_result(self._h, C.byref(f), _ptr(self._g)), "vmat_fetch_result")
         return f.value, self._g.copy()
 
     def sync(self):
-        check(self._lib.vmat_sync(self._h), "vmat_sync")
+        self._check(self._lib.vmat_sync(self._h), "vmat_sync")
 
     def guard_status(self):
         """The index guard's record (vmat_guard_status): None while it has not tripped, else a dict.  Readable
