@@ -25,7 +25,7 @@
 namespace vmat {
 
 constexpr int kStageHeader = 1;     // stage carries the super-slice header
-constexpr int kStageLast = 2;       // last stage of the super-slice: run the epilogue
+constexpr int kStageLast = 2;       // last stage of the super-slice (K1/K2 consumers count the stages from the header's flags >> 8 instead)
 struct StageInfo { int32_t ss, flags, tile, tpr; };
 
 // header units (16 B) per warp: 32 row ids (+ thr, over, under as AT for K1)
