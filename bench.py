@@ -426,7 +426,11 @@ def run_case(args, name, K, W, rank, local, world, dist, torch, sampler, opts, h
                                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                                "algorithmic_bytes_per_launch": kb, "launch_ms": kms,
                                "scope": "rank 0's slab" if world > 1 else "whole case",
-                               "note": ("slab fits L2: not an HBM measurement" if fits else None)}
+                               "bytes_per_nonzero": sv + si,
+                               "note": ("slab fits L2: not an HBM measurement" if fits else
+                                        ("byte-delta indices: %d algorithmic bytes per nonzero (uint16 indices: %d) - fewer "
+                                         "bytes in less time, at a lower fraction of the peak than the uint16 layout "
+                                         "reaches (DESIGN.md section 3)" % (sv + 1, sv + 2)) if si == 1 else None)}
             out["kernels_ms"] = {k: kt[k] for k in ("k1_ms", "k2_ms", "k3_ms", "eval_ms")}
             algo = info["algorithmic_bytes_per_eval"]
             ach_eval = algo / (ms / K * 1e-3) / 1e9
@@ -461,7 +465,7 @@ def main():
     ap.add_argument("--k2-tasks", type=int, default=0)
     ap.add_argument("--k2-threads", type=int, default=0)
     ap.add_argument("--k1-threads", type=int, default=0)
-    ap.add_argument("--index-bytes", type=int, default=0, help="4 forces int32 column indices (default: uint16 when they fit)")
+    ap.add_argument("--index-bytes", type=int, default=0, help="index form: 1 byte deltas, 2 uint16 when it fits, 4 int32 (0 = the library's default: byte deltas for fp32/fp32 plans of 5 M nonzeros and more, else uint16)")
     ap.add_argument("--claim-lead", type=int, default=0, help="dose kernel: stages before a super-slice's end at which the next is claimed (tuning; 0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--fused", type=int, default=0, help="0 / 1 = the three kernels K1/K2/K3 (default), 2 = the single fused evaluation kernel")
